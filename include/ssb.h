@@ -1,0 +1,151 @@
+/* ssb.h -- C-ABI of the B200-native StrongSORT per-frame tracking path.
+ *
+ * Boundary: the reference's tracker seam is the single call
+ *     results = model.track(image, ..., persist=True, tracker="botsort.yaml")
+ * at /root/reference/yolo_multi_model.py:41, behind which a StrongSORT plug-in
+ * exposes  StrongSORT.update(dets[N,6], img[H,W,3]) -> rows[M,7]
+ * (the upstream strong_sort/ package is absent from the
+ * snapshot).  Every entry point below is what a Python/ctypes (or any FFI)
+ * binding of that seam would bind; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - plain C types only; all *_dev pointers are device pointers into buffers
+ *     the CALLER owns (torch CUDA tensors in the Python host); the library
+ *     never allocates device memory: ssb_create() carves the caller-provided
+ *     workspace of ssb_workspace_bytes() bytes.
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as
+ *     void*); no entry point synchronises; graph-capturable.
+ *   - return 0 on success, negative on error; ssb_last_error() returns a
+ *     thread-local message.  No exceptions cross the ABI.
+ *   - one handle per video stream; a handle is not thread-safe, distinct
+ *     handles are independent.
+ */
+#ifndef SSB_H_
+#define SSB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ssb_tracker ssb_tracker;
+typedef void *ssb_stream_t; /* cudaStream_t */
+
+/* Constructor knobs == strong_sort.yaml of upstream. */
+typedef struct ssb_config {
+    int32_t max_tracks;      /* track slots in the device table (>= live tracks) */
+    int32_t max_dets;        /* max detections per frame                        */
+    int32_t nn_budget;       /* NN_BUDGET   (100)                               */
+    int32_t feat_dim;        /* 512                                             */
+    int32_t n_init;          /* N_INIT      (3)                                 */
+    int32_t max_age;         /* MAX_AGE     (30)                                */
+    double max_dist;         /* MAX_DIST    (0.2)  appearance threshold         */
+    double max_iou_distance; /* MAX_IOU_DISTANCE (0.7)                          */
+    double mc_lambda;        /* MC_LAMBDA   (0.995)                             */
+    double ema_alpha;        /* EMA_ALPHA   (0.9)                               */
+} ssb_config;
+
+/* counts written by ssb_update() to counts_dev[8] */
+enum {
+    SSB_CNT_OUT_ROWS = 0,   /* M rows written to out_dev                */
+    SSB_CNT_TRACKS = 1,     /* live tracks after the update             */
+    SSB_CNT_CONFIRMED = 2,  /* confirmed tracks after the update        */
+    SSB_CNT_NEXT_ID = 3,    /* next track id to be issued               */
+    SSB_CNT_MATCHES_A = 4,  /* matches of the appearance stage          */
+    SSB_CNT_MATCHES_B = 5,  /* matches of the IoU stage                 */
+    SSB_CNT_NEW = 6,        /* tracks initiated this frame              */
+    SSB_CNT_ERROR = 7,      /* !=0: table overflow (tracks/dets dropped)*/
+    SSB_CNT_N = 8
+};
+#define SSB_OUT_COLS 8 /* x1,y1,x2,y2,track_id,cls,conf,det_index(-1 if none) */
+
+int ssb_version(void);
+const char *ssb_last_error(void);
+void ssb_default_config(ssb_config *cfg);
+
+/* ---- lifecycle ---------------------------------------------------------- */
+int64_t ssb_workspace_bytes(const ssb_config *cfg);
+int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t workspace_bytes,
+               ssb_tracker **out);
+int ssb_destroy(ssb_tracker *t);
+/* forget all tracks, ids restart at 1 */
+int ssb_reset(ssb_tracker *t, ssb_stream_t stream);
+
+/* ---- ReID weights (OSNet-x0.25, BN folded by the host; see weights.py) --- */
+int ssb_reid_num_tensors(void);
+/* fills sizes[ssb_reid_num_tensors()] with the element count of each folded
+ * tensor in canonical order */
+int ssb_reid_tensor_sizes(int64_t *sizes);
+int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const int64_t *sizes, int n);
+
+/* ---- the per-frame hot path: StrongSORT.update(dets, img) ---------------- */
+/* dets_dev  : float32 [n,6] x1,y1,x2,y2,conf,cls
+ * img_dev   : uint8 BGR, h rows of `pitch` bytes (pitch >= 3*w)
+ * feats_dev : NULL -> embeddings are computed by the built-in OSNet from img;
+ *             else float32 [n,feat_dim] caller-supplied embeddings (tests)
+ * out_dev   : float64 [max_tracks, SSB_OUT_COLS]
+ * counts_dev: int32 [SSB_CNT_N]
+ * track_hint: upper bound on live tracks entering this frame (the
+ *             SSB_CNT_TRACKS of the previous frame), or -1 for max_tracks;
+ *             only sizes launch grids, never changes results.            */
+int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_dev,
+               int h, int w, int pitch, const float *feats_dev, double *out_dev,
+               int32_t *counts_dev, int track_hint, ssb_stream_t stream);
+
+/* ---- stage entry points (parity tests call these one by one) ------------- */
+/* OSNet embeddings of n crops: boxes_dev int32 [n,4] x1,y1,x2,y2 with crop =
+ * img[y1:y2, x1:x2]; out float32 [n,512].                                   */
+int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, int pitch,
+             const int32_t *boxes_dev, int n, float *feats_out_dev, ssb_stream_t stream);
+/* crop boxes exactly as _get_features/_xywh_to_xyxy derive them from dets    */
+int ssb_crop_boxes(const float *dets_dev, int n, int h, int w, int32_t *boxes_out_dev,
+                   ssb_stream_t stream);
+/* batched Kalman filter on caller arrays: mean [n,8], cov [n,8,8] float64    */
+int ssb_kf_predict(double *mean_dev, double *cov_dev, int n, ssb_stream_t stream);
+int ssb_kf_update(double *mean_dev, double *cov_dev, const float *xyah_dev,
+                  const float *conf_dev, int n, ssb_stream_t stream);
+/* squared Mahalanobis (4 dof): maha_out [n_tracks, n_meas]                   */
+int ssb_kf_gating(const double *mean_dev, const double *cov_dev, int n_tracks,
+                  const float *xyah_dev, int n_meas, double *maha_out_dev,
+                  ssb_stream_t stream);
+/* appearance cost: gallery float32 [n_tracks, budget, dim] with counts[n_tracks]
+ * valid samples each; feats [n_dets, dim]; cost_out float32 [n_tracks, n_dets] */
+int ssb_appearance_cost(const float *gallery_dev, const int32_t *counts_dev,
+                        int n_tracks, int budget, const float *feats_dev, int n_dets,
+                        int dim, float *cost_out_dev, ssb_stream_t stream);
+/* 1 - IoU: track tlwh float64 [n_tracks,4], det tlwh float32 [n_dets,4]       */
+int ssb_iou_cost(const double *track_tlwh_dev, int n_tracks, const float *det_tlwh_dev,
+                 int n_dets, double *cost_out_dev, ssb_stream_t stream);
+/* rectangular LSAP with scipy's tie-breaks: cost float64 [nr,nc] row-major;
+ * col4row_out int32 [nr] (-1 = unassigned), row4col_out int32 [nc]          */
+int ssb_lsap(const double *cost_dev, int nr, int nc, int32_t *col4row_out_dev,
+             int32_t *row4col_out_dev, ssb_stream_t stream);
+/* YOLO post-process (thresholds of yolo_multi_model.py:18-21):
+ * pred float32 [4+nc(+extra), A] (xywh, class scores, extra channels);
+ * out float32 [max_det, 6+extra] x1,y1,x2,y2,conf,cls,extra...; count int32[1];
+ * scratch_dev >= ssb_nms_scratch_bytes(A) bytes                              */
+int64_t ssb_nms_scratch_bytes(int num_anchors);
+int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_anchors,
+                 float conf_thres, float iou_thres, int max_det, int agnostic,
+                 float *out_dev, int32_t *count_dev, void *scratch_dev,
+                 ssb_stream_t stream);
+
+/* ---- introspection for tests: copy the live track table (list order) ----- */
+/* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];
+ * mean float64 [T,8]; cov [T,8,8]; feat float32 [T,dim]                     */
+int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, int32_t *hits,
+                      int32_t *age, int32_t *tsu, int32_t *gallery_len, double *mean,
+                      double *cov, float *feat, ssb_stream_t stream);
+/* per-frame association trace of the LAST ssb_update (device buffers, valid
+ * until the next update): appearance cost [nA_rows, n] float32 is NOT kept;
+ * the gated/clamped stage-A cost matrix float64 [rows_a, n] and the stage-B
+ * matrix [rows_b, cols_b] are.  dims_out int32 [4] = rows_a, cols_a, rows_b,
+ * cols_b (device).                                                          */
+int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev, const double **cost_b_dev,
+                        const int32_t **dims_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SSB_H_ */

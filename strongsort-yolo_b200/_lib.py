@@ -1,0 +1,101 @@
+"""ctypes binding of libssb.so (include/ssb.h).  No CPU fallback: a missing
+library or a missing CUDA device raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libssb.so")
+
+# every symbol include/ssb.h declares (tests/test_abi.py checks the export list)
+SYMBOLS = [
+    "ssb_version", "ssb_last_error", "ssb_default_config", "ssb_workspace_bytes",
+    "ssb_create", "ssb_destroy", "ssb_reset", "ssb_reid_num_tensors",
+    "ssb_reid_tensor_sizes", "ssb_reid_set_weights", "ssb_update", "ssb_reid",
+    "ssb_crop_boxes", "ssb_kf_predict", "ssb_kf_update", "ssb_kf_gating",
+    "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
+    "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs",
+]
+
+SSB_CNT_N = 8
+SSB_OUT_COLS = 8
+
+
+class SsbConfig(C.Structure):
+    _fields_ = [("max_tracks", C.c_int32), ("max_dets", C.c_int32),
+                ("nn_budget", C.c_int32), ("feat_dim", C.c_int32),
+                ("n_init", C.c_int32), ("max_age", C.c_int32),
+                ("max_dist", C.c_double), ("max_iou_distance", C.c_double),
+                ("mc_lambda", C.c_double), ("ema_alpha", C.c_double)]
+
+
+class SsbError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load libssb.so once; raise loudly if it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise SsbError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.ssb_version.restype = i32
+    lib.ssb_last_error.restype = C.c_char_p
+    lib.ssb_default_config.argtypes = [C.POINTER(SsbConfig)]
+    lib.ssb_default_config.restype = None
+    lib.ssb_workspace_bytes.argtypes = [C.POINTER(SsbConfig)]
+    lib.ssb_workspace_bytes.restype = i64
+    lib.ssb_create.argtypes = [C.POINTER(SsbConfig), vp, i64, C.POINTER(vp)]
+    lib.ssb_destroy.argtypes = [vp]
+    lib.ssb_reset.argtypes = [vp, vp]
+    lib.ssb_reid_num_tensors.restype = i32
+    lib.ssb_reid_tensor_sizes.argtypes = [C.POINTER(i64)]
+    lib.ssb_reid_set_weights.argtypes = [vp, vp, C.POINTER(i64), i32]
+    lib.ssb_update.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp]
+    lib.ssb_reid.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp]
+    lib.ssb_crop_boxes.argtypes = [vp, i32, i32, i32, vp, vp]
+    lib.ssb_kf_predict.argtypes = [vp, vp, i32, vp]
+    lib.ssb_kf_update.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.ssb_kf_gating.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    lib.ssb_appearance_cost.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp]
+    lib.ssb_iou_cost.argtypes = [vp, i32, vp, i32, vp, vp]
+    lib.ssb_lsap.argtypes = [vp, i32, i32, vp, vp, vp]
+    lib.ssb_nms_scratch_bytes.argtypes = [i32]
+    lib.ssb_nms_scratch_bytes.restype = i64
+    lib.ssb_yolo_nms.argtypes = [vp, i32, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp]
+    lib.ssb_export_tracks.argtypes = [vp] * 11
+    lib.ssb_debug_cost_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ("ssb_version", "ssb_reid_num_tensors"):
+            fn.restype = i32
+    _lib = lib
+    return lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = load().ssb_last_error().decode("utf-8", "replace")
+        raise SsbError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """device/host pointer of a torch tensor (or None)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise SsbError("strongsort_yolo_b200 needs a CUDA device (B200, sm_100a); "
+                       "there is no CPU fallback")
+    return torch

@@ -1,0 +1,199 @@
+// extern "C" boundary of libssb.so (include/ssb.h): handle lifecycle, workspace
+// carving and the per-frame orchestration of StrongSORT.update(dets, img)
+// (seam: /root/reference/yolo_multi_model.py:41).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "ssb_common.cuh"
+
+int ssb_launch_reset(ssb_tracker *t, cudaStream_t st);
+int ssb_launch_export(ssb_tracker *t, int *ids, int *state, int *hits, int *age, int *tsu, int *gal,
+                      double *mean, double *cov, float *feat, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void ssb_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *ssb_last_error(void) { return g_err; }
+extern "C" int ssb_version(void) { return 100; }
+
+extern "C" void ssb_default_config(ssb_config *c) {
+    c->max_tracks = 1024;
+    c->max_dets = 512;
+    c->nn_budget = 100;
+    c->feat_dim = 512;
+    c->n_init = 3;
+    c->max_age = 30;
+    c->max_dist = 0.2;
+    c->max_iou_distance = 0.7;
+    c->mc_lambda = 0.995;
+    c->ema_alpha = 0.9;
+}
+
+static int check_cfg(const ssb_config *c) {
+    if (!c) { ssb_set_error("null config"); return -1; }
+    if (c->max_tracks < 1 || c->max_tracks > 4096) { ssb_set_error("max_tracks must be in [1,4096]"); return -1; }
+    if (c->max_dets < 1 || c->max_dets > 4096) { ssb_set_error("max_dets must be in [1,4096]"); return -1; }
+    if (c->nn_budget < 1 || c->nn_budget > 1024) { ssb_set_error("nn_budget must be in [1,1024]"); return -1; }
+    if (c->feat_dim != 512) { ssb_set_error("feat_dim must be 512 (OSNet)"); return -1; }
+    if (c->n_init < 1 || c->max_age < 1) { ssb_set_error("n_init/max_age must be >= 1"); return -1; }
+    return 0;
+}
+
+// bump allocator over the caller's workspace; pass base==nullptr to size it
+struct Carver {
+    char *base;
+    size_t off;
+    template <typename T>
+    T *take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T *p = base ? reinterpret_cast<T *>(base + off) : nullptr;
+        off += n * sizeof(T);
+        return p;
+    }
+};
+
+static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratch *fs,
+                    float **reid_ws, int64_t *reid_floats, int **boxes_tmp) {
+    const size_t S = c->max_tracks, N = c->max_dets, B = c->nn_budget, D = c->feat_dim;
+    const size_t L = S > N ? S : N;
+    Carver k{base, 0};
+    TrackTable t;
+    t.mean = k.take<double>(S * 8);
+    t.cov = k.take<double>(S * 64);
+    t.track_id = k.take<int>(S); t.state = k.take<int>(S); t.hits = k.take<int>(S);
+    t.age = k.take<int>(S); t.tsu = k.take<int>(S); t.cls = k.take<int>(S);
+    t.last_det = k.take<int>(S);
+    t.conf = k.take<float>(S);
+    t.feat = k.take<float>(S * D);
+    t.gallery = k.take<float>(S * B * D);
+    t.gal_count = k.take<int>(S); t.gal_head = k.take<int>(S);
+    t.order = k.take<int>(S); t.order_tmp = k.take<int>(S); t.free_stack = k.take<int>(S);
+    t.scalars = k.take<int>(SC_COUNT);
+    FrameScratch f;
+    f.det_tlwh = k.take<float>(N * 4); f.det_xyah = k.take<float>(N * 4);
+    f.det_box = k.take<int>(N * 4);
+    f.det_conf = k.take<float>(N); f.det_cls = k.take<float>(N);
+    f.feats = k.take<float>(N * D);
+    f.det_norm = k.take<float>(N);
+    f.app_cost = k.take<float>(S * N);
+    f.cost_a = k.take<double>(S * N);
+    f.cost_b = k.take<double>(S * N);
+    f.conf_list = k.take<int>(S); f.unconf_list = k.take<int>(S); f.cand_b = k.take<int>(S);
+    f.untrk_a_keep = k.take<int>(S);
+    f.undet_a = k.take<int>(N); f.undet = k.take<int>(N);
+    f.untrk = k.take<int>(S);
+    f.match_trk = k.take<int>(L); f.match_det = k.take<int>(L);
+    f.col4row = k.take<int>(L); f.row4col = k.take<int>(L);
+    f.cnt = k.take<int>(FC_COUNT);
+    f.lsap_ws = k.take<double>(16);
+    const int64_t rf = ssb_reid_ws_floats((int)N);
+    float *rw = k.take<float>((size_t)rf);
+    int *bt = k.take<int>(N * 4);
+    if (tt) *tt = t;
+    if (fs) *fs = f;
+    if (reid_ws) *reid_ws = rw;
+    if (reid_floats) *reid_floats = rf;
+    if (boxes_tmp) *boxes_tmp = bt;
+    return (k.off + 255) & ~(size_t)255;
+}
+
+extern "C" int64_t ssb_workspace_bytes(const ssb_config *cfg) {
+    if (check_cfg(cfg)) return -1;
+    return (int64_t)carve(cfg, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+}
+
+extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t workspace_bytes,
+                          ssb_tracker **out) {
+    if (check_cfg(cfg)) return -1;
+    if (!out || !workspace_dev) { ssb_set_error("null argument"); return -1; }
+    const int64_t need = ssb_workspace_bytes(cfg);
+    if (workspace_bytes < need) {
+        ssb_set_error("workspace too small: %lld < %lld", (long long)workspace_bytes, (long long)need);
+        return -1;
+    }
+    if (((uintptr_t)workspace_dev & 255) != 0) { ssb_set_error("workspace must be 256-byte aligned"); return -1; }
+    ssb_tracker *t = (ssb_tracker *)calloc(1, sizeof(ssb_tracker));
+    if (!t) { ssb_set_error("out of host memory"); return -1; }
+    t->cfg = *cfg;
+    t->ws_base = (char *)workspace_dev;
+    t->ws_bytes = workspace_bytes;
+    carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp);
+    SsbDims &d = t->dims;
+    d.S = cfg->max_tracks; d.N = cfg->max_dets; d.B = cfg->nn_budget; d.D = cfg->feat_dim;
+    d.n_init = cfg->n_init; d.max_age = cfg->max_age;
+    d.max_dist = cfg->max_dist; d.max_iou = cfg->max_iou_distance;
+    d.mc_lambda = cfg->mc_lambda; d.one_minus_lambda = 1 - cfg->mc_lambda;
+    // python-float weights applied to float32 arrays: rounded once to float32
+    d.ema_alpha = (float)cfg->ema_alpha;
+    d.one_minus_alpha = (float)(1.0 - cfg->ema_alpha);
+    *out = t;
+    return 0;
+}
+
+extern "C" int ssb_destroy(ssb_tracker *t) {
+    if (!t) return 0;
+    free(t->w_off);
+    free(t);
+    return 0;
+}
+
+extern "C" int ssb_reset(ssb_tracker *t, ssb_stream_t stream) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    return ssb_launch_reset(t, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_dev,
+                          int h, int w, int pitch, const float *feats_dev, double *out_dev,
+                          int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
+    if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
+    if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
+    if (n > 0 && !dets_dev) { ssb_set_error("null dets"); return -1; }
+    if (h <= 0 || w <= 0) { ssb_set_error("bad image size %dx%d", w, h); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = ssb_launch_prep(t->dims, dets_dev, n, h, w, t->fs, st);
+    if (rc) return rc;
+    const float *feats = feats_dev;
+    if (!feats) {
+        if (n > 0) {
+            if (!img_dev || pitch < 3 * w) { ssb_set_error("null image / bad pitch"); return -1; }
+            if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
+            rc = ssb_reid_forward(t, img_dev, h, w, pitch, t->fs.det_box, n, t->fs.feats, st);
+            if (rc) return rc;
+        }
+        feats = t->fs.feats;
+    }
+    return ssb_launch_track_frame(t, n, h, w, feats, out_dev, counts_dev, track_hint, st);
+}
+
+extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, int pitch,
+                        const int32_t *boxes_dev, int n, float *feats_out_dev, ssb_stream_t stream) {
+    if (!t || !img_dev || !feats_out_dev) { ssb_set_error("null argument"); return -1; }
+    if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
+    if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
+    if (n == 0) return 0;
+    return ssb_reid_forward(t, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, int32_t *hits,
+                                 int32_t *age, int32_t *tsu, int32_t *gallery_len, double *mean,
+                                 double *cov, float *feat, ssb_stream_t stream) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    return ssb_launch_export(t, ids, state, hits, age, tsu, gallery_len, mean, cov, feat, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev,
+                                   const double **cost_b_dev, const int32_t **dims_dev) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    if (cost_a_dev) *cost_a_dev = t->fs.cost_a;
+    if (cost_b_dev) *cost_b_dev = t->fs.cost_b;
+    if (dims_dev) *dims_dev = t->fs.cnt + FC_ROWS_A;
+    return 0;
+}

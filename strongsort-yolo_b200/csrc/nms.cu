@@ -1,0 +1,211 @@
+// YOLO post-process: confidence filter + class-aware NMS.
+// In-tree facts: conf 0.3, iou 0.4, agnostic_nms False, max_det 1000
+// (/root/reference/yolo_multi_model.py:18-21).  The arithmetic mirrors
+// ultralytics' non_max_suppression -> torchvision.ops.nms (third-party, not
+// vendored): best class only, xywh->xyxy in float32, class offset 7680,
+// stable descending score order, greedy suppression on IoU > thr, first
+// max_det survivors.  Bit-exact vs torchvision's CPU kernel (same float32
+// expression order, IEEE division).
+//
+// HBM-bound on the score read ((4+nc)*A*4 bytes); everything after the filter
+// touches only the few hundred candidates.
+#include "ssb_common.cuh"
+
+#define NMS_MAX_WH 7680.0f
+
+struct NmsScratch {
+    float *conf;        // [A]
+    int *cls;           // [A]
+    int *cand;          // [A] anchors passing the filter, anchor order
+    int *order;         // [A] candidate index sorted by score (stable, desc)
+    float *sbox;        // [A][4] offset boxes in sorted order
+    float *sarea;       // [A]
+    unsigned long long *mask;   // [M][ceil(M/64)]
+    int *count;         // [4]: M
+};
+
+__host__ __device__ inline size_t nms_align(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static size_t nms_carve(char *base, int A, NmsScratch *s) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) { char *p = base ? base + off : nullptr; off = nms_align(off + bytes); return p; };
+    NmsScratch t;
+    t.conf = (float *)take((size_t)A * 4);
+    t.cls = (int *)take((size_t)A * 4);
+    t.cand = (int *)take((size_t)A * 4);
+    t.order = (int *)take((size_t)A * 4);
+    t.sbox = (float *)take((size_t)A * 16);
+    t.sarea = (float *)take((size_t)A * 4);
+    t.count = (int *)take(64);
+    const size_t words = ((size_t)A + 63) / 64;
+    t.mask = (unsigned long long *)take((size_t)A * words * 8);
+    if (s) *s = t;
+    return off;
+}
+
+extern "C" int64_t ssb_nms_scratch_bytes(int num_anchors) {
+    if (num_anchors <= 0) return 0;
+    return (int64_t)nms_carve(nullptr, num_anchors, nullptr);
+}
+
+// best class per anchor: pred is channel-major [4+nc+extra][A] -> coalesced over anchors
+__global__ void nms_score_kernel(const float *__restrict__ pred, int nc, int A, NmsScratch s) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    float best = pred[(size_t)4 * A + a];
+    int bi = 0;
+    for (int c = 1; c < nc; c++) {
+        const float v = pred[(size_t)(4 + c) * A + a];
+        if (v > best) { best = v; bi = c; }     // first maximum wins, like torch.max
+    }
+    s.conf[a] = best;
+    s.cls[a] = bi;
+}
+
+__device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// ordered compaction of anchors with conf > thr (single CTA, 1024 threads)
+__global__ void __launch_bounds__(1024)
+nms_compact_kernel(int A, float conf_thres, NmsScratch s) {
+    __shared__ int s_w[33];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int per = (A + 1023) / 1024;
+    const int b = tid * per, e = min(A, b + per);
+    int c = 0;
+    for (int a = b; a < e; a++) c += s.conf[a] > conf_thres;
+    int inc = warp_incl_scan_i(c, lane);
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = s_w[lane];
+        int wi = warp_incl_scan_i(w, lane);
+        s_w[lane] = wi - w;
+        if (lane == 31) s_w[32] = wi;
+    }
+    __syncthreads();
+    int off = s_w[wid] + inc - c;
+    for (int a = b; a < e; a++)
+        if (s.conf[a] > conf_thres) s.cand[off++] = a;
+    if (tid == 0) s.count[0] = s_w[32];
+}
+
+// stable descending rank by counting; writes order[], offset boxes and areas
+__global__ void nms_rank_kernel(const float *__restrict__ pred, int A, int agnostic, NmsScratch s) {
+    const int M = s.count[0];
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= M) return;
+    const int a = s.cand[k];
+    const float sc = s.conf[a];
+    int rank = 0;
+    for (int j = 0; j < M; j++) {
+        const float sj = s.conf[s.cand[j]];
+        rank += (sj > sc) || (sj == sc && j < k);
+    }
+    s.order[rank] = k;
+    // xywh -> xyxy (float32), then the class offset
+    const float x = pred[a], y = pred[(size_t)A + a];
+    const float dw = pred[(size_t)2 * A + a] / 2.f, dh = pred[(size_t)3 * A + a] / 2.f;
+    const float c = agnostic ? 0.f : (float)s.cls[a] * NMS_MAX_WH;
+    const float x1 = (x - dw) + c, y1 = (y - dh) + c, x2 = (x + dw) + c, y2 = (y + dh) + c;
+    s.sbox[rank * 4 + 0] = x1; s.sbox[rank * 4 + 1] = y1;
+    s.sbox[rank * 4 + 2] = x2; s.sbox[rank * 4 + 3] = y2;
+    s.sarea[rank] = (x2 - x1) * (y2 - y1);
+}
+
+// suppression bit matrix over score-sorted boxes: bit (i, j) = IoU(i, j) > thr, j > i
+__global__ void nms_mask_kernel(float iou_thres, NmsScratch s) {
+    const int M = s.count[0];
+    const int words = (M + 63) / 64;
+    const int i = blockIdx.y * blockDim.y + threadIdx.y;
+    const int wj = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M || wj >= words) return;
+    const float ix1 = s.sbox[i * 4], iy1 = s.sbox[i * 4 + 1];
+    const float ix2 = s.sbox[i * 4 + 2], iy2 = s.sbox[i * 4 + 3];
+    const float iarea = s.sarea[i];
+    unsigned long long bits = 0;
+    const int j0 = wj * 64;
+    for (int b = 0; b < 64; b++) {
+        const int j = j0 + b;
+        if (j >= M) break;
+        if (j <= i) continue;
+        const float xx1 = fmaxf(ix1, s.sbox[j * 4]), yy1 = fmaxf(iy1, s.sbox[j * 4 + 1]);
+        const float xx2 = fminf(ix2, s.sbox[j * 4 + 2]), yy2 = fminf(iy2, s.sbox[j * 4 + 3]);
+        const float w = fmaxf(0.f, xx2 - xx1), h = fmaxf(0.f, yy2 - yy1);
+        const float inter = w * h;
+        const float ovr = inter / (iarea + s.sarea[j] - inter);
+        if (ovr > iou_thres) bits |= 1ull << b;
+    }
+    s.mask[(size_t)i * words + wj] = bits;
+}
+
+// greedy scan + gather (single CTA)
+__global__ void __launch_bounds__(256)
+nms_scan_kernel(const float *__restrict__ pred, int nc, int n_extra, int A, int max_det,
+                NmsScratch s, float *__restrict__ out, int *__restrict__ count_out) {
+    extern __shared__ unsigned long long s_removed[];
+    __shared__ int s_keep_n;
+    __shared__ int s_cur_keep;
+    const int M = s.count[0];
+    const int words = (M + 63) / 64;
+    for (int w = threadIdx.x; w < words; w += blockDim.x) s_removed[w] = 0ull;
+    if (threadIdx.x == 0) s_keep_n = 0;
+    __syncthreads();
+    const int cols = 6 + n_extra;
+    for (int i = 0; i < M; i++) {
+        if (s_keep_n >= max_det) break;
+        const bool removed = (s_removed[i >> 6] >> (i & 63)) & 1ull;
+        __syncthreads();
+        if (removed) continue;
+        if (threadIdx.x == 0) { s_cur_keep = s_keep_n; s_keep_n = s_keep_n + 1; }
+        for (int w = threadIdx.x; w < words; w += blockDim.x)
+            s_removed[w] |= s.mask[(size_t)i * words + w];
+        __syncthreads();
+        // gather row (original, un-offset box)
+        const int row = s_cur_keep;
+        const int a = s.cand[s.order[i]];
+        if (threadIdx.x == 0) {
+            const float x = pred[a], y = pred[(size_t)A + a];
+            const float dw = pred[(size_t)2 * A + a] / 2.f, dh = pred[(size_t)3 * A + a] / 2.f;
+            float *o = out + (size_t)row * cols;
+            o[0] = x - dw; o[1] = y - dh; o[2] = x + dw; o[3] = y + dh;
+            o[4] = s.conf[a]; o[5] = (float)s.cls[a];
+        }
+        for (int e = threadIdx.x; e < n_extra; e += blockDim.x)
+            out[(size_t)row * cols + 6 + e] = pred[(size_t)(4 + nc + e) * A + a];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) count_out[0] = s_keep_n;
+}
+
+extern "C" int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_anchors,
+                            float conf_thres, float iou_thres, int max_det, int agnostic,
+                            float *out_dev, int32_t *count_dev, void *scratch_dev,
+                            ssb_stream_t stream) {
+    if (!pred_dev || !out_dev || !count_dev || !scratch_dev) { ssb_set_error("null argument"); return -1; }
+    if (num_classes < 1 || num_anchors < 1 || num_extra < 0 || max_det < 1) { ssb_set_error("bad NMS dims"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    NmsScratch s;
+    nms_carve((char *)scratch_dev, num_anchors, &s);
+    const int A = num_anchors;
+    nms_score_kernel<<<(A + 255) / 256, 256, 0, st>>>(pred_dev, num_classes, A, s);
+    SSB_CHECK_LAUNCH();
+    nms_compact_kernel<<<1, 1024, 0, st>>>(A, conf_thres, s);
+    SSB_CHECK_LAUNCH();
+    // the candidate count lives on the device: grids are sized for the worst case
+    nms_rank_kernel<<<(A + 127) / 128, 128, 0, st>>>(pred_dev, A, agnostic, s);
+    SSB_CHECK_LAUNCH();
+    const int words = (A + 63) / 64;
+    dim3 mb(32, 8), mg((words + 31) / 32, (A + 7) / 8);
+    nms_mask_kernel<<<mg, mb, 0, st>>>(iou_thres, s);
+    SSB_CHECK_LAUNCH();
+    nms_scan_kernel<<<1, 256, (size_t)words * 8, st>>>(pred_dev, num_classes, num_extra, A, max_det, s, out_dev, count_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}

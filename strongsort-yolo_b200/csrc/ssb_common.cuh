@@ -1,0 +1,111 @@
+// Shared declarations for the StrongSORT-on-B200 kernels (sm_100a).
+// Data layout in HBM (DESIGN.md "layout"): a slot-indexed struct-of-arrays
+// track table, a per-slot appearance gallery ring, and per-frame scratch, all
+// carved from ONE caller-owned workspace (include/ssb.h: ssb_create).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/ssb.h"
+
+#define SSB_TENTATIVE 1
+#define SSB_CONFIRMED 2
+#define SSB_DELETED 3
+#define SSB_INFTY_COST 1e5
+#define SSB_CHI2INV95_4 9.4877
+
+// device-side scalar slots (TrackTable::scalars)
+enum { SC_N_TRACKS = 0, SC_NEXT_ID, SC_N_FREE, SC_ERROR, SC_FRAME, SC_COUNT = 16 };
+// per-frame counters (FrameScratch::cnt)
+enum {
+    FC_N_CONF = 0, FC_N_UNCONF, FC_N_UNDET_A, FC_N_CAND_B, FC_N_UNTRK_A_KEEP,
+    FC_N_MATCH, FC_N_MATCH_A, FC_N_UNTRK, FC_N_UNDET, FC_N_NEW, FC_ROWS_A, FC_COLS_A,
+    FC_ROWS_B, FC_COLS_B, FC_COUNT = 32
+};
+
+struct TrackTable {
+    double *mean;      // [S][8]
+    double *cov;       // [S][64]
+    int *track_id, *state, *hits, *age, *tsu, *cls, *last_det;  // [S]
+    float *conf;       // [S]
+    float *feat;       // [S][D]   EMA-smoothed unit feature (Track.features[-1])
+    float *gallery;    // [S][B][D] ring of appended features (metric.samples[id])
+    int *gal_count, *gal_head;  // [S]
+    int *order;        // [S] list position -> slot  (== Tracker.tracks order)
+    int *order_tmp;    // [S]
+    int *free_stack;   // [S]
+    int *scalars;      // [SC_COUNT]
+};
+
+struct FrameScratch {
+    float *det_tlwh;   // [N][4] f32
+    float *det_xyah;   // [N][4] f32
+    int *det_box;      // [N][4] crop x1,y1,x2,y2
+    float *det_conf;   // [N]
+    float *det_cls;    // [N]
+    float *feats;      // [N][D] raw embeddings
+    float *det_norm;      // [N] L2 norm of each raw embedding
+    float *app_cost;   // [S][N] f32 nearest-neighbour cosine distance
+    double *cost_a;    // [S][N] gated + clamped stage-A cost
+    double *cost_b;    // [S][N] clamped IoU cost
+    int *conf_list, *unconf_list;       // [S] list positions
+    int *cand_b;       // [S]
+    int *untrk_a_keep; // [S] unmatched stage-A tracks with tsu != 1
+    int *undet_a;      // [N] unmatched dets after stage A (ordered)
+    int *undet;        // [N] final unmatched dets (ordered) -> new ids
+    int *untrk;        // [S] final unmatched tracks (positions)
+    int *match_trk, *match_det;         // [min(S,N)] positions / det index
+    int *col4row, *row4col;             // [max(S,N)] LSAP scratch results
+    int *cnt;          // [FC_COUNT]
+    double *lsap_ws;   // LSAP global workspace (u, v, spc when not in smem)
+};
+
+struct SsbDims {
+    int S, N, B, D;
+    int n_init, max_age;
+    double max_dist, max_iou, mc_lambda, one_minus_lambda;
+    float ema_alpha, one_minus_alpha;
+};
+
+// OSNet execution (reid.cu)
+struct ReidNet;
+struct ssb_tracker {
+    ssb_config cfg;
+    SsbDims dims;
+    TrackTable tt;
+    FrameScratch fs;
+    char *ws_base;
+    int64_t ws_bytes;
+    // reid
+    const float *w_blob;      // folded weights (device, caller-owned)
+    int64_t *w_off;           // host: offsets per tensor
+    int n_w;
+    float *reid_ws;           // activation workspace (device)
+    int64_t reid_ws_floats;
+    int *boxes_tmp;           // [N][4]
+};
+
+void ssb_set_error(const char *fmt, ...);
+#define SSB_CHECK_CUDA(expr)                                                        \
+    do {                                                                            \
+        cudaError_t _e = (expr);                                                    \
+        if (_e != cudaSuccess) {                                                    \
+            ssb_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),  \
+                          __FILE__, __LINE__);                                      \
+            return -2;                                                              \
+        }                                                                           \
+    } while (0)
+#define SSB_CHECK_LAUNCH()  SSB_CHECK_CUDA(cudaGetLastError())
+
+// launchers implemented across the .cu files --------------------------------
+int ssb_launch_prep(const SsbDims &d, const float *dets, int n, int h, int w,
+                    FrameScratch fs, cudaStream_t st);
+int ssb_launch_track_frame(ssb_tracker *t, int n, int h, int w, const float *feats,
+                           double *out, int *counts, int track_hint, cudaStream_t st);
+int ssb_launch_appearance(const float *gallery, const int *gal_count, const int *gal_head,
+                          const int *row_slot_list, const int *order, const int *n_rows_dev,
+                          int max_rows, int budget, const float *feats, int n_dets, int dim,
+                          float *cost, int ld, cudaStream_t st);
+int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch,
+                     const int *boxes, int n, float *feats_out, cudaStream_t st);
+int64_t ssb_reid_ws_floats(int max_dets);

@@ -1,0 +1,993 @@
+// Association-side kernels of StrongSORT.update(): detection prep, batched
+// Kalman filter, Mahalanobis gating, IoU cost, linear assignment with scipy's
+// tie-breaks, and the device-resident track table (state machine, id
+// allocation, gallery ring).  float64 throughout, compiled with -fmad=false so
+// that expression order matches the NumPy restatement (oracle/strongsort_np.py).
+//
+// Reference semantics: SURVEY.md Appendix A.4-A.8 (the upstream strong_sort/
+// package is absent from /root/reference; the seam is yolo_multi_model.py:41).
+// These kernels are latency-bound (working set <= 1-3 MB): the
+// design goal is few launches, no host round trip, coalesced SoA access.
+#include <math.h>
+#include <stdio.h>
+
+#include "ssb_common.cuh"
+
+#define KF_WP (1.0 / 20)
+#define KF_WV (1.0 / 160)
+
+// ---------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// exclusive scan of one int per thread over the block; returns exclusive
+// prefix, *total gets the block sum.  s_w: >= 33 ints of shared memory.
+__device__ int block_excl_scan(int v, int *s_w, int *total) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    int inc = warp_incl_scan(v, lane);
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        int w = lane < nw ? s_w[lane] : 0;
+        int wi = warp_incl_scan(w, lane);
+        s_w[lane] = wi - w;
+        if (lane == 31) s_w[32] = wi;
+    }
+    __syncthreads();
+    int ex = s_w[wid] + inc - v;
+    *total = s_w[32];
+    __syncthreads();
+    return ex;
+}
+
+// lower Cholesky of a symmetric 4x4 (only the lower triangle of S is read)
+__device__ __forceinline__ void chol4(const double S[4][4], double L[4][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        double d = S[j][j];
+#pragma unroll
+        for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+        d = sqrt(d);
+        L[j][j] = d;
+#pragma unroll
+        for (int i = j + 1; i < 4; i++) {
+            double s = S[i][j];
+#pragma unroll
+            for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+            L[i][j] = s / d;
+        }
+    }
+}
+
+// KalmanFilter.project (A.4): mu = mean[:4], S = cov[:4,:4] + diag(std^2)
+__device__ __forceinline__ void kf_project(const double *mean, const double *cov,
+                                           double conf, double mu[4], double S[4][4]) {
+    const double h = mean[3];
+    double std[4] = {KF_WP * h, KF_WP * h, 1e-1, KF_WP * h};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        mu[i] = mean[i];
+        std[i] = (1.0 - conf) * std[i];
+#pragma unroll
+        for (int j = 0; j < 4; j++) S[i][j] = cov[i * 8 + j];
+        S[i][i] = S[i][i] + std[i] * std[i];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// detection prep (A.2 / A.3): xyxy -> xywh -> tlwh, xyah, int crop boxes
+// ---------------------------------------------------------------------------
+__global__ void prep_dets_kernel(const float *__restrict__ dets, int n, int H, int W,
+                                 FrameScratch fs) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x1 = dets[i * 6 + 0], y1 = dets[i * 6 + 1];
+    const float x2 = dets[i * 6 + 2], y2 = dets[i * 6 + 3];
+    const float cx = (x1 + x2) / 2.f, cy = (y1 + y2) / 2.f;
+    const float w = x2 - x1, h = y2 - y1;
+    // _xywh_to_xyxy: python int() truncates toward zero
+    int bx1 = max((int)(cx - w / 2.f), 0);
+    int bx2 = min((int)(cx + w / 2.f), W - 1);
+    int by1 = max((int)(cy - h / 2.f), 0);
+    int by2 = min((int)(cy + h / 2.f), H - 1);
+    fs.det_box[i * 4 + 0] = bx1; fs.det_box[i * 4 + 1] = by1;
+    fs.det_box[i * 4 + 2] = bx2; fs.det_box[i * 4 + 3] = by2;
+    const float tx = cx - w / 2.0f, ty = cy - h / 2.0f;   // _xywh_to_tlwh
+    fs.det_tlwh[i * 4 + 0] = tx; fs.det_tlwh[i * 4 + 1] = ty;
+    fs.det_tlwh[i * 4 + 2] = w;  fs.det_tlwh[i * 4 + 3] = h;
+    // Detection.to_xyah in float32
+    fs.det_xyah[i * 4 + 0] = tx + w / 2.f;
+    fs.det_xyah[i * 4 + 1] = ty + h / 2.f;
+    fs.det_xyah[i * 4 + 2] = w / h;
+    fs.det_xyah[i * 4 + 3] = h;
+    fs.det_conf[i] = dets[i * 6 + 4];
+    fs.det_cls[i] = dets[i * 6 + 5];
+}
+
+__global__ void crop_boxes_kernel(const float *__restrict__ dets, int n, int H, int W,
+                                  int *__restrict__ boxes) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float x1 = dets[i * 6 + 0], y1 = dets[i * 6 + 1];
+    const float x2 = dets[i * 6 + 2], y2 = dets[i * 6 + 3];
+    const float cx = (x1 + x2) / 2.f, cy = (y1 + y2) / 2.f;
+    const float w = x2 - x1, h = y2 - y1;
+    boxes[i * 4 + 0] = max((int)(cx - w / 2.f), 0);
+    boxes[i * 4 + 1] = max((int)(cy - h / 2.f), 0);
+    boxes[i * 4 + 2] = min((int)(cx + w / 2.f), W - 1);
+    boxes[i * 4 + 3] = min((int)(cy + h / 2.f), H - 1);
+}
+
+// L2 norm of every raw embedding (float64 accumulation, rounded to float32)
+__global__ void det_norm_kernel(const float *__restrict__ feats, int n, int D,
+                                float *__restrict__ norm_out) {
+    int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    double s = 0;
+    for (int k = lane; k < D; k += 32) {
+        double v = feats[(size_t)w * D + k];
+        s += v * v;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) norm_out[w] = (float)sqrt(s);
+}
+
+// ---------------------------------------------------------------------------
+// batched Kalman predict: one warp per track, lanes own cov elements
+//   mean <- F mean ; cov <- F (cov F^T) + Q      (multi_dot order of the oracle)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void kf_predict_warp(double *mean, double *cov, int lane) {
+    double m_old = lane < 8 ? mean[lane] : 0.0;
+    double m_hi = lane < 4 ? mean[lane + 4] : 0.0;
+    double out[2];
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int e = lane + 32 * r, i = e >> 3, j = e & 7;
+        double x = cov[i * 8 + j];
+        if (j < 4) x = x + cov[i * 8 + j + 4];
+        if (i < 4) {
+            double y = cov[(i + 4) * 8 + j];
+            if (j < 4) y = y + cov[(i + 4) * 8 + j + 4];
+            x = x + y;
+        }
+        out[r] = x;
+    }
+    // motion noise from the OLD mean
+    const double m0 = __shfl_sync(0xffffffffu, m_old, 0), m1 = __shfl_sync(0xffffffffu, m_old, 1);
+    const double m2 = __shfl_sync(0xffffffffu, m_old, 2), m3 = __shfl_sync(0xffffffffu, m_old, 3);
+    __syncwarp();
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int e = lane + 32 * r, i = e >> 3, j = e & 7;
+        if (i == j) {
+            double s;
+            switch (i) {
+                case 0: s = KF_WP * m0; break;
+                case 1: s = KF_WP * m1; break;
+                case 2: s = 1 * m2; break;
+                case 3: s = KF_WP * m3; break;
+                case 4: s = KF_WV * m0; break;
+                case 5: s = KF_WV * m1; break;
+                case 6: s = 0.1 * m2; break;
+                default: s = KF_WV * m3; break;
+            }
+            out[r] = out[r] + s * s;
+        }
+        cov[e] = out[r];
+    }
+    if (lane < 4) mean[lane] = m_old + m_hi;
+}
+
+__global__ void kf_predict_tracks_kernel(TrackTable tt) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= tt.scalars[SC_N_TRACKS]) return;
+    const int s = tt.order[w];
+    kf_predict_warp(tt.mean + (size_t)s * 8, tt.cov + (size_t)s * 64, lane);
+    if (lane == 0) { tt.age[s] += 1; tt.tsu[s] += 1; }
+}
+
+__global__ void kf_predict_arrays_kernel(double *mean, double *cov, int n) {
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    kf_predict_warp(mean + (size_t)w * 8, cov + (size_t)w * 64, lane);
+}
+
+// KalmanFilter.update for one track, executed by a single thread
+__device__ void kf_update_thread(double *mean, double *cov, const float *xyah, double conf) {
+    double mu[4], S[4][4], L[4][4];
+    double m[8], P[64];
+#pragma unroll
+    for (int i = 0; i < 8; i++) m[i] = mean[i];
+    for (int i = 0; i < 64; i++) P[i] = cov[i];
+    kf_project(m, P, conf, mu, S);
+    chol4(S, L);
+    // K = (cho_solve(S, (P H^T)^T))^T : row i of K solves S k = P[i, :4]
+    double K[8][4];
+    for (int i = 0; i < 8; i++) {
+        double y[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {          // forward  L y = b
+            double s = P[i * 8 + r];
+#pragma unroll
+            for (int k = 0; k < r; k++) s -= L[r][k] * y[k];
+            y[r] = s / L[r][r];
+        }
+#pragma unroll
+        for (int r = 3; r >= 0; r--) {         // backward L^T x = y
+            double s = y[r];
+#pragma unroll
+            for (int k = r + 1; k < 4; k++) s -= L[k][r] * K[i][k];
+            K[i][r] = s / L[r][r];
+        }
+    }
+    double innov[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) innov[j] = (double)xyah[j] - mu[j];
+    for (int i = 0; i < 8; i++) {
+        double s = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) s += innov[j] * K[i][j];
+        mean[i] = m[i] + s;
+    }
+    // cov - K (S K^T)
+    double SKt[4][8];
+#pragma unroll
+    for (int a = 0; a < 4; a++)
+        for (int j = 0; j < 8; j++) {
+            double s = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) s += S[a][b] * K[j][b];
+            SKt[a][j] = s;
+        }
+    for (int i = 0; i < 8; i++)
+        for (int j = 0; j < 8; j++) {
+            double s = 0;
+#pragma unroll
+            for (int a = 0; a < 4; a++) s += K[i][a] * SKt[a][j];
+            cov[i * 8 + j] = P[i * 8 + j] - s;
+        }
+}
+
+__global__ void kf_update_arrays_kernel(double *mean, double *cov, const float *xyah,
+                                        const float *conf, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    kf_update_thread(mean + (size_t)i * 8, cov + (size_t)i * 64, xyah + i * 4, (double)conf[i]);
+}
+
+// squared Mahalanobis distance of all measurements to one projected track
+__device__ __forceinline__ double maha4(const double L[4][4], const double mu[4],
+                                        const float *z) {
+    double d0 = (double)z[0] - mu[0], d1 = (double)z[1] - mu[1];
+    double d2 = (double)z[2] - mu[2], d3 = (double)z[3] - mu[3];
+    double z0 = d0 / L[0][0];
+    double z1 = (d1 - L[1][0] * z0) / L[1][1];
+    double z2 = (d2 - L[2][0] * z0 - L[2][1] * z1) / L[2][2];
+    double z3 = (d3 - L[3][0] * z0 - L[3][1] * z1 - L[3][2] * z2) / L[3][3];
+    return z0 * z0 + z1 * z1 + z2 * z2 + z3 * z3;
+}
+
+__global__ void kf_gating_arrays_kernel(const double *mean, const double *cov, int n_tracks,
+                                        const float *xyah, int n_meas, double *out) {
+    const int r = blockIdx.x;
+    if (r >= n_tracks) return;
+    double mu[4], S[4][4], L[4][4];
+    kf_project(mean + (size_t)r * 8, cov + (size_t)r * 64, 0.0, mu, S);
+    chol4(S, L);
+    for (int j = threadIdx.x; j < n_meas; j += blockDim.x)
+        out[(size_t)r * n_meas + j] = maha4(L, mu, xyah + j * 4);
+}
+
+// ---------------------------------------------------------------------------
+// list building: confirmed / unconfirmed positions in track-list order (A.6)
+// ---------------------------------------------------------------------------
+__global__ void build_lists_kernel(TrackTable tt, FrameScratch fs) {
+    __shared__ int s_w[33];
+    const int T = tt.scalars[SC_N_TRACKS];
+    const int per = (T + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(T, b + per);
+    int c = 0;
+    for (int p = b; p < e; p++) c += tt.state[tt.order[p]] == SSB_CONFIRMED;
+    int tot;
+    int off = block_excl_scan(c, s_w, &tot);
+    int offu = b - off;   // unconfirmed before b
+    for (int p = b; p < e; p++) {
+        if (tt.state[tt.order[p]] == SSB_CONFIRMED) fs.conf_list[off++] = p;
+        else fs.unconf_list[offu++] = p;
+    }
+    if (threadIdx.x == 0) {
+        fs.cnt[FC_N_CONF] = tot;
+        fs.cnt[FC_N_UNCONF] = T - tot;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage-A cost: gate_cost_matrix + clamp (A.6).  One block per confirmed row.
+//   g = maha^2 ; cost = app ; cost[g > chi2] = 1e5 ; cost = l*cost + (1-l)*g ;
+//   cost[cost > max_dist] = max_dist + 1e-5
+// ---------------------------------------------------------------------------
+__global__ void gate_cost_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int n) {
+    const int r = blockIdx.x;
+    if (r >= fs.cnt[FC_N_CONF]) return;
+    const int s = tt.order[fs.conf_list[r]];
+    double mu[4], S[4][4], L[4][4];
+    kf_project(tt.mean + (size_t)s * 8, tt.cov + (size_t)s * 64, 0.0, mu, S);
+    chol4(S, L);
+    const double clampv = d.max_dist + 1e-5;
+    for (int j = threadIdx.x; j < n; j += blockDim.x) {
+        const double g = maha4(L, mu, fs.det_xyah + j * 4);
+        double c = (double)fs.app_cost[(size_t)r * n + j];
+        if (g > SSB_CHI2INV95_4) c = SSB_INFTY_COST;
+        c = d.mc_lambda * c + d.one_minus_lambda * g;
+        if (c > d.max_dist) c = clampv;
+        fs.cost_a[(size_t)r * n + j] = c;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// stage-B cost: iou_cost + clamp (A.7).  One block per candidate row.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double iou_cost_one(const double tl[4], const float *c) {
+    const double bx = tl[0], by = tl[1], bw = tl[2], bh = tl[3];
+    const double bbr_x = bx + bw, bbr_y = by + bh;
+    const float cbx = c[0] + c[2], cby = c[1] + c[3];        // float32 adds
+    const float carea = c[2] * c[3];                           // float32 product
+    const double tlx = fmax(bx, (double)c[0]), tly = fmax(by, (double)c[1]);
+    const double brx = fmin(bbr_x, (double)cbx), bry = fmin(bbr_y, (double)cby);
+    const double w = fmax(0.0, brx - tlx), h = fmax(0.0, bry - tly);
+    const double inter = w * h;
+    const double area_b = bw * bh;
+    return 1.0 - inter / (area_b + (double)carea - inter);
+}
+
+__global__ void iou_cost_kernel(TrackTable tt, FrameScratch fs, SsbDims d) {
+    const int r = blockIdx.x;
+    const int rows = fs.cnt[FC_N_CAND_B], cols = fs.cnt[FC_N_UNDET_A];
+    if (r >= rows) return;
+    const int s = tt.order[fs.cand_b[r]];
+    const double clampv = d.max_iou + 1e-5;
+    const bool stale = tt.tsu[s] > 1;
+    double tl[4];
+    {   // Track.to_tlwh
+        const double *m = tt.mean + (size_t)s * 8;
+        double w = m[2] * m[3];
+        tl[2] = w; tl[3] = m[3];
+        tl[0] = m[0] - w / 2; tl[1] = m[1] - m[3] / 2;
+    }
+    for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+        double c = stale ? SSB_INFTY_COST : iou_cost_one(tl, fs.det_tlwh + fs.undet_a[j] * 4);
+        if (c > d.max_iou) c = clampv;
+        fs.cost_b[(size_t)r * cols + j] = c;
+    }
+}
+
+__global__ void iou_cost_arrays_kernel(const double *tlwh, int n_tracks, const float *det_tlwh,
+                                       int n_dets, double *out) {
+    const int r = blockIdx.x;
+    if (r >= n_tracks) return;
+    double tl[4] = {tlwh[r * 4], tlwh[r * 4 + 1], tlwh[r * 4 + 2], tlwh[r * 4 + 3]};
+    for (int j = threadIdx.x; j < n_dets; j += blockDim.x)
+        out[(size_t)r * n_dets + j] = iou_cost_one(tl, det_tlwh + j * 4);
+}
+
+// ---------------------------------------------------------------------------
+// rectangular LSAP, one warp, scipy tie-breaks (oracle/lsap.c is the C twin)
+// ---------------------------------------------------------------------------
+struct LsapSmem {
+    double *u, *v, *spc, *cost;   // cost == nullptr -> read global
+    int *path, *row4col, *col4row, *remaining;
+    unsigned char *SR, *SC;
+};
+
+__device__ __forceinline__ size_t lsap_smem_fixed_bytes(int L) {
+    // u, v, spc: 3*L doubles; path,row4col,col4row,remaining: 4*L ints; SR,SC: 2*L bytes
+    return (size_t)L * (3 * 8 + 4 * 4 + 2) + 64;
+}
+
+__device__ void lsap_carve(unsigned char *base, int L, LsapSmem &m) {
+    m.u = (double *)base;            base += (size_t)L * 8;
+    m.v = (double *)base;            base += (size_t)L * 8;
+    m.spc = (double *)base;          base += (size_t)L * 8;
+    m.path = (int *)base;            base += (size_t)L * 4;
+    m.row4col = (int *)base;         base += (size_t)L * 4;
+    m.col4row = (int *)base;         base += (size_t)L * 4;
+    m.remaining = (int *)base;       base += (size_t)L * 4;
+    m.SR = base;                     base += L;
+    m.SC = base;                     base += L;
+    base = (unsigned char *)(((uintptr_t)base + 15) & ~(uintptr_t)15);
+    m.cost = (double *)base;
+}
+
+// Solve with the whole block staging, warp 0 iterating.  C is [nr0][nc0]
+// row-major (ld = nc0).  Results in ORIGINAL orientation: col4row_out[nr0],
+// row4col_out[nc0] (-1 = unassigned).  Must be called by all threads.
+__device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapSmem m,
+                           size_t cost_smem_bytes, int *col4row_out, int *row4col_out) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (nr0 == 0 || nc0 == 0) {
+        for (int i = tid; i < nr0; i += blockDim.x) col4row_out[i] = -1;
+        for (int j = tid; j < nc0; j += blockDim.x) row4col_out[j] = -1;
+        __syncthreads();
+        return;
+    }
+    const bool tr = nc0 < nr0;
+    const int nr = tr ? nc0 : nr0, nc = tr ? nr0 : nc0;
+    const bool staged = (size_t)nr * nc * 8 <= cost_smem_bytes;
+    if (staged) {
+        for (int e = tid; e < nr0 * nc0; e += blockDim.x) {
+            const int i0 = e / nc0, j0 = e - i0 * nc0;
+            const double c = C[e];
+            if (tr) m.cost[(size_t)j0 * nc + i0] = c; else m.cost[e] = c;
+        }
+    }
+    for (int i = tid; i < nr; i += blockDim.x) { m.u[i] = 0.0; m.col4row[i] = -1; }
+    for (int j = tid; j < nc; j += blockDim.x) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
+    __syncthreads();
+
+    if (tid < 32) {
+        bool failed = false;
+        for (int curRow = 0; curRow < nr && !failed; curRow++) {
+            for (int j = lane; j < nc; j += 32) {
+                m.remaining[j] = nc - j - 1;
+                m.spc[j] = INFINITY;
+                m.SC[j] = 0;
+            }
+            for (int i = lane; i < nr; i += 32) m.SR[i] = 0;
+            __syncwarp();
+            double minVal = 0.0;
+            int i = curRow, num_remaining = nc, sink = -1;
+            while (sink == -1) {
+                if (lane == 0) m.SR[i] = 1;
+                const double ui = m.u[i];
+                double best_v = INFINITY;
+                int best_it = -1, best_un = 0;
+                for (int it = lane; it < num_remaining; it += 32) {
+                    const int j = m.remaining[it];
+                    double cij;
+                    if (staged) cij = m.cost[(size_t)i * nc + j];
+                    else cij = tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j];
+                    const double r = minVal + cij - ui - m.v[j];
+                    double sj = m.spc[j];
+                    if (r < sj) { m.path[j] = i; m.spc[j] = r; sj = r; }
+                    const int un = m.row4col[j] == -1;
+                    if (sj < best_v || (sj == best_v && un)) { best_v = sj; best_it = it; best_un = un; }
+                }
+                // warp arg-min with scipy's rule: lower value; on ties an unassigned
+                // column wins (the LAST such in scan order), else the FIRST scanned.
+#pragma unroll
+                for (int o = 16; o; o >>= 1) {
+                    const double ov = __shfl_xor_sync(0xffffffffu, best_v, o);
+                    const int oit = __shfl_xor_sync(0xffffffffu, best_it, o);
+                    const int oun = __shfl_xor_sync(0xffffffffu, best_un, o);
+                    bool take;
+                    if (oit < 0) take = false;
+                    else if (best_it < 0) take = true;
+                    else if (ov != best_v) take = ov < best_v;
+                    else if (oun != best_un) take = oun > best_un;
+                    else take = oun ? (oit > best_it) : (oit < best_it);
+                    if (take) { best_v = ov; best_it = oit; best_un = oun; }
+                }
+                if (best_it < 0 || !(best_v < INFINITY)) {   // NaN/inf costs: infeasible
+                    failed = true;
+                    break;
+                }
+                minVal = best_v;
+                const int j = m.remaining[best_it];
+                const int rj = m.row4col[j];
+                __syncwarp();
+                if (lane == 0) {
+                    m.SC[j] = 1;
+                    m.remaining[best_it] = m.remaining[num_remaining - 1];
+                }
+                num_remaining--;
+                if (rj == -1) sink = j; else i = rj;
+                __syncwarp();
+            }
+            if (failed) break;
+            // dual updates
+            if (lane == 0) m.u[curRow] += minVal;
+            for (int r = lane; r < nr; r += 32)
+                if (m.SR[r] && r != curRow) m.u[r] += minVal - m.spc[m.col4row[r]];
+            for (int j = lane; j < nc; j += 32)
+                if (m.SC[j]) m.v[j] -= minVal - m.spc[j];
+            __syncwarp();
+            if (lane == 0) {           // augment
+                int j = sink;
+                while (true) {
+                    const int r = m.path[j];
+                    m.row4col[j] = r;
+                    const int t = m.col4row[r];
+                    m.col4row[r] = j;
+                    j = t;
+                    if (r == curRow) break;
+                }
+            }
+            __syncwarp();
+        }
+        if (failed) {   // leave everything unassigned; callers treat rows as unmatched
+            for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
+            for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
+        }
+    }
+    __syncthreads();
+    if (!tr) {
+        for (int i = tid; i < nr0; i += blockDim.x) col4row_out[i] = m.col4row[i];
+        for (int j = tid; j < nc0; j += blockDim.x) row4col_out[j] = m.row4col[j];
+    } else {   // working rows == original columns
+        for (int i = tid; i < nr0; i += blockDim.x) col4row_out[i] = m.row4col[i];
+        for (int j = tid; j < nc0; j += blockDim.x) row4col_out[j] = m.col4row[j];
+    }
+    __syncthreads();
+}
+
+__global__ void lsap_kernel(const double *C, int nr, int nc, int L, size_t cost_smem_bytes,
+                            int *col4row_out, int *row4col_out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    LsapSmem m;
+    lsap_carve(smem, L, m);
+    lsap_block(C, nr, nc, m, cost_smem_bytes, col4row_out, row4col_out);
+}
+
+// Stage A: LSAP over confirmed x dets, then min_cost_matching's list building
+// and the stage-B candidate list (A.6).
+__global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int n, int L,
+                                      size_t cost_smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    LsapSmem m;
+    lsap_carve(smem, L, m);
+    const int rows = fs.cnt[FC_N_CONF], cols = n;
+    lsap_block(fs.cost_a, rows, cols, m, cost_smem_bytes, fs.col4row, fs.row4col);
+    if (threadIdx.x == 0) {
+        int nu = 0;
+        for (int c = 0; c < cols; c++)
+            if (fs.row4col[c] < 0) fs.undet_a[nu++] = c;
+        int nm = 0, nb = 0, nk = 0;
+        const int n_unconf = fs.cnt[FC_N_UNCONF];
+        for (int k = 0; k < n_unconf; k++) fs.cand_b[nb++] = fs.unconf_list[k];
+        for (int r = 0; r < rows; r++) {
+            const int pos = fs.conf_list[r];
+            const int c = fs.col4row[r];
+            bool matched = false;
+            if (c >= 0) {
+                if (fs.cost_a[(size_t)r * cols + c] > d.max_dist) fs.undet_a[nu++] = c;
+                else { fs.match_trk[nm] = pos; fs.match_det[nm] = c; nm++; matched = true; }
+            }
+            if (!matched) {
+                if (tt.tsu[tt.order[pos]] == 1) fs.cand_b[nb++] = pos;
+                else fs.untrk_a_keep[nk++] = pos;
+            }
+        }
+        fs.cnt[FC_N_UNDET_A] = nu;
+        fs.cnt[FC_N_CAND_B] = nb;
+        fs.cnt[FC_N_UNTRK_A_KEEP] = nk;
+        fs.cnt[FC_N_MATCH] = nm;
+        fs.cnt[FC_N_MATCH_A] = nm;
+        fs.cnt[FC_ROWS_A] = rows; fs.cnt[FC_COLS_A] = cols;
+    }
+}
+
+// Stage B: LSAP over candidates x leftover dets (IoU), final lists.
+__global__ void assign_stage_b_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int L,
+                                      size_t cost_smem_bytes) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    LsapSmem m;
+    lsap_carve(smem, L, m);
+    const int rows = fs.cnt[FC_N_CAND_B], cols = fs.cnt[FC_N_UNDET_A];
+    lsap_block(fs.cost_b, rows, cols, m, cost_smem_bytes, fs.col4row, fs.row4col);
+    if (threadIdx.x == 0) {
+        int nm = fs.cnt[FC_N_MATCH], nu = 0, nt = 0;
+        const int nk = fs.cnt[FC_N_UNTRK_A_KEEP];
+        for (int k = 0; k < nk; k++) fs.untrk[nt++] = fs.untrk_a_keep[k];
+        for (int c = 0; c < cols; c++)
+            if (fs.row4col[c] < 0) fs.undet[nu++] = fs.undet_a[c];
+        for (int r = 0; r < rows; r++) {
+            const int pos = fs.cand_b[r];
+            const int c = fs.col4row[r];
+            if (c < 0) { fs.untrk[nt++] = pos; continue; }
+            if (fs.cost_b[(size_t)r * cols + c] > d.max_iou) {
+                fs.untrk[nt++] = pos;
+                fs.undet[nu++] = fs.undet_a[c];
+            } else {
+                fs.match_trk[nm] = pos; fs.match_det[nm] = fs.undet_a[c]; nm++;
+            }
+        }
+        fs.cnt[FC_N_MATCH] = nm;
+        fs.cnt[FC_N_UNTRK] = nt;
+        fs.cnt[FC_N_UNDET] = nu;
+        fs.cnt[FC_ROWS_B] = rows; fs.cnt[FC_COLS_B] = cols;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Track.update for every match: KF update (thread 0) + EMA feature (block)
+// ---------------------------------------------------------------------------
+__device__ double block_sum_f64(double v, double *s_red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s_red[wid] = v;
+    __syncthreads();
+    double t = 0;
+    const int nw = (blockDim.x + 31) >> 5;
+    for (int k = 0; k < nw; k++) t += s_red[k];
+    __syncthreads();
+    return t;
+}
+
+__global__ void update_matched_kernel(TrackTable tt, FrameScratch fs, SsbDims d) {
+    __shared__ double s_red[32];
+    const int k = blockIdx.x;
+    if (k >= fs.cnt[FC_N_MATCH]) return;
+    const int pos = fs.match_trk[k], det = fs.match_det[k];
+    const int s = tt.order[pos];
+    const int D = d.D;
+    const float *f = fs.feats + (size_t)det * D;
+    float *tf = tt.feat + (size_t)s * D;
+    // feature = det.feature / ||det.feature||
+    const float nrm = fs.det_norm[det];
+    double acc = 0;
+    for (int i = threadIdx.x; i < D; i += blockDim.x) {
+        const float fn = f[i] / nrm;
+        const float sm = d.ema_alpha * tf[i] + d.one_minus_alpha * fn;
+        tf[i] = sm;       // own elements only: safe in place
+        acc += (double)sm * (double)sm;
+    }
+    const double tot = block_sum_f64(acc, s_red);
+    const float n2 = (float)sqrt(tot);
+    for (int i = threadIdx.x; i < D; i += blockDim.x) tf[i] = tf[i] / n2;
+    if (threadIdx.x == 0) {
+        kf_update_thread(tt.mean + (size_t)s * 8, tt.cov + (size_t)s * 64,
+                         fs.det_xyah + det * 4, (double)fs.det_conf[det]);
+        tt.conf[s] = fs.det_conf[det];
+        tt.cls[s] = (int)fs.det_cls[det];
+        tt.last_det[s] = det;
+        const int h = tt.hits[s] + 1;
+        tt.hits[s] = h;
+        tt.tsu[s] = 0;
+        if (tt.state[s] == SSB_TENTATIVE && h >= d.n_init) tt.state[s] = SSB_CONFIRMED;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// bookkeeping: mark_missed, _initiate_track (ids in unmatched-det order),
+// drop deleted tracks (order preserved), output rows (A.2), counters.
+// Single block; the per-new-track feature copies use all warps.
+// ---------------------------------------------------------------------------
+__global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H, int W,
+                                double *out, int *counts) {
+    __shared__ int s_w[33];
+    __shared__ int s_nnew;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
+    const int T0 = tt.scalars[SC_N_TRACKS];
+    const int n_free = tt.scalars[SC_N_FREE];
+    const int next_id = tt.scalars[SC_NEXT_ID];
+    // unmatched tracks did not see a detection this frame
+    for (int p = tid; p < T0; p += blockDim.x) tt.last_det[tt.order[p]] = -1;
+    __syncthreads();
+    for (int k = tid; k < fs.cnt[FC_N_MATCH]; k += blockDim.x)
+        tt.last_det[tt.order[fs.match_trk[k]]] = fs.match_det[k];
+    // 1. mark_missed
+    for (int k = tid; k < fs.cnt[FC_N_UNTRK]; k += blockDim.x) {
+        const int s = tt.order[fs.untrk[k]];
+        if (tt.state[s] == SSB_TENTATIVE) tt.state[s] = SSB_DELETED;
+        else if (tt.tsu[s] > d.max_age) tt.state[s] = SSB_DELETED;
+    }
+    // 2. new tracks
+    if (tid == 0) {
+        int nn = fs.cnt[FC_N_UNDET];
+        int err = 0;
+        if (nn > n_free) { nn = n_free; err = 1; }
+        if (nn > d.S - T0) { nn = d.S - T0; err = 1; }
+        s_nnew = nn;
+        if (err) tt.scalars[SC_ERROR] = 1;
+    }
+    __syncthreads();
+    const int n_new = s_nnew;
+    for (int k = wid; k < n_new; k += nw) {
+        const int det = fs.undet[k];
+        const int s = tt.free_stack[n_free - 1 - k];
+        if (lane == 0) {
+            tt.order[T0 + k] = s;
+            const float *z = fs.det_xyah + det * 4;
+            const double z0 = z[0], z1 = z[1], z2 = z[2], z3 = z[3];
+            double *m = tt.mean + (size_t)s * 8;
+            m[0] = z0; m[1] = z1; m[2] = z2; m[3] = z3; m[4] = 0; m[5] = 0; m[6] = 0; m[7] = 0;
+            double std[8] = {2 * KF_WP * z0, 2 * KF_WP * z1, 1 * z2, 2 * KF_WP * z3,
+                             10 * KF_WV * z0, 10 * KF_WV * z1, 0.1 * z2, 10 * KF_WV * z3};
+            double *P = tt.cov + (size_t)s * 64;
+            for (int e = 0; e < 64; e++) P[e] = 0.0;
+            for (int i = 0; i < 8; i++) P[i * 9] = std[i] * std[i];
+            tt.track_id[s] = next_id + k;
+            tt.state[s] = SSB_TENTATIVE;
+            tt.hits[s] = 1; tt.age[s] = 1; tt.tsu[s] = 0;
+            tt.cls[s] = (int)fs.det_cls[det];
+            tt.conf[s] = fs.det_conf[det];
+            tt.last_det[s] = det;
+            tt.gal_count[s] = 0; tt.gal_head[s] = 0;
+        }
+        const float nrm = fs.det_norm[det];
+        const float *f = fs.feats + (size_t)det * d.D;
+        float *tf = tt.feat + (size_t)s * d.D;
+        for (int i = lane; i < d.D; i += 32) tf[i] = f[i] / nrm;
+    }
+    __syncthreads();
+    // 3. drop deleted tracks, keep order; recycle their slots
+    const int T1 = T0 + n_new;
+    const int per = (T1 + blockDim.x - 1) / blockDim.x;
+    const int b = tid * per, e = min(T1, b + per);
+    int c = 0;
+    for (int p = b; p < e; p++) c += tt.state[tt.order[p]] != SSB_DELETED;
+    int keep_tot;
+    int off = block_excl_scan(c, s_w, &keep_tot);
+    int offd = b - off;
+    const int free_base = n_free - n_new;
+    for (int p = b; p < e; p++) {
+        const int s = tt.order[p];
+        if (tt.state[s] != SSB_DELETED) tt.order_tmp[off++] = s;
+        else { tt.free_stack[free_base + offd] = s; offd++; tt.gal_count[s] = 0; tt.gal_head[s] = 0; }
+    }
+    __syncthreads();
+    for (int p = tid; p < keep_tot; p += blockDim.x) tt.order[p] = tt.order_tmp[p];
+    __syncthreads();
+    // 4. output rows: confirmed and time_since_update <= 1, list order
+    const int per2 = (keep_tot + blockDim.x - 1) / blockDim.x;
+    const int b2 = tid * per2, e2 = min(keep_tot, b2 + per2);
+    int c2 = 0, cc = 0;
+    for (int p = b2; p < e2; p++) {
+        const int s = tt.order[p];
+        const bool conf = tt.state[s] == SSB_CONFIRMED;
+        cc += conf;
+        c2 += conf && tt.tsu[s] <= 1;
+    }
+    int out_tot;
+    int off2 = block_excl_scan(c2, s_w, &out_tot);
+    int conf_tot;
+    (void)block_excl_scan(cc, s_w, &conf_tot);
+    for (int p = b2; p < e2; p++) {
+        const int s = tt.order[p];
+        if (tt.state[s] != SSB_CONFIRMED || tt.tsu[s] > 1) continue;
+        const double *m = tt.mean + (size_t)s * 8;
+        const double w = m[2] * m[3];
+        const double x = m[0] - w / 2, y = m[1] - m[3] / 2, h = m[3];
+        double *o = out + (size_t)off2 * SSB_OUT_COLS;
+        o[0] = (double)max((int)x, 0);
+        o[1] = (double)max((int)y, 0);
+        o[2] = (double)min((int)(x + w), W - 1);
+        o[3] = (double)min((int)(y + h), H - 1);
+        o[4] = (double)tt.track_id[s];
+        o[5] = (double)tt.cls[s];
+        o[6] = (double)tt.conf[s];
+        o[7] = (double)tt.last_det[s];
+        off2++;
+    }
+    if (tid == 0) {
+        tt.scalars[SC_N_TRACKS] = keep_tot;
+        tt.scalars[SC_NEXT_ID] = next_id + n_new;
+        tt.scalars[SC_N_FREE] = free_base + (T1 - keep_tot);
+        tt.scalars[SC_FRAME] += 1;
+        counts[SSB_CNT_OUT_ROWS] = out_tot;
+        counts[SSB_CNT_TRACKS] = keep_tot;
+        counts[SSB_CNT_CONFIRMED] = conf_tot;
+        counts[SSB_CNT_NEXT_ID] = next_id + n_new;
+        counts[SSB_CNT_MATCHES_A] = fs.cnt[FC_N_MATCH_A];
+        counts[SSB_CNT_MATCHES_B] = fs.cnt[FC_N_MATCH] - fs.cnt[FC_N_MATCH_A];
+        counts[SSB_CNT_NEW] = n_new;
+        counts[SSB_CNT_ERROR] = tt.scalars[SC_ERROR];
+    }
+}
+
+// gallery partial_fit (A.5/A.6): every confirmed track appends its current
+// smoothed feature once per frame; ring of `budget` samples per slot.
+__global__ void gallery_append_kernel(TrackTable tt, SsbDims d) {
+    const int p = blockIdx.x;
+    if (p >= tt.scalars[SC_N_TRACKS]) return;
+    const int s = tt.order[p];
+    if (tt.state[s] != SSB_CONFIRMED) return;
+    const int head = tt.gal_head[s];
+    const float *f = tt.feat + (size_t)s * d.D;
+    float *g = tt.gallery + ((size_t)s * d.B + head) * d.D;
+    for (int i = threadIdx.x; i < d.D; i += blockDim.x) g[i] = f[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        tt.gal_head[s] = (head + 1) % d.B;
+        tt.gal_count[s] = min(tt.gal_count[s] + 1, d.B);
+    }
+}
+
+__global__ void reset_table_kernel(TrackTable tt, SsbDims d) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.S) {
+        tt.free_stack[i] = d.S - 1 - i;   // pop order: slot 0 first
+        tt.state[i] = SSB_DELETED;
+        tt.gal_count[i] = 0; tt.gal_head[i] = 0;
+        tt.order[i] = 0;
+    }
+    if (i == 0) {
+        for (int k = 0; k < SC_COUNT; k++) tt.scalars[k] = 0;
+        tt.scalars[SC_NEXT_ID] = 1;
+        tt.scalars[SC_N_FREE] = d.S;
+    }
+}
+
+__global__ void export_tracks_kernel(TrackTable tt, SsbDims d, int *ids, int *state, int *hits,
+                                     int *age, int *tsu, int *gal, double *mean, double *cov,
+                                     float *feat) {
+    const int p = blockIdx.x;
+    if (p >= tt.scalars[SC_N_TRACKS]) return;
+    const int s = tt.order[p];
+    if (threadIdx.x == 0) {
+        if (ids) ids[p] = tt.track_id[s];
+        if (state) state[p] = tt.state[s];
+        if (hits) hits[p] = tt.hits[s];
+        if (age) age[p] = tt.age[s];
+        if (tsu) tsu[p] = tt.tsu[s];
+        if (gal) gal[p] = tt.gal_count[s];
+    }
+    if (mean) for (int i = threadIdx.x; i < 8; i += blockDim.x) mean[(size_t)p * 8 + i] = tt.mean[(size_t)s * 8 + i];
+    if (cov) for (int i = threadIdx.x; i < 64; i += blockDim.x) cov[(size_t)p * 64 + i] = tt.cov[(size_t)s * 64 + i];
+    if (feat) for (int i = threadIdx.x; i < d.D; i += blockDim.x) feat[(size_t)p * d.D + i] = tt.feat[(size_t)s * d.D + i];
+}
+
+// ---------------------------------------------------------------------------
+// host-side launchers
+// ---------------------------------------------------------------------------
+static int g_lsap_smem_limit = 0;   // bytes of dynamic smem opted in
+
+static int lsap_prepare(int L, size_t *dyn_bytes, size_t *cost_bytes) {
+    if (!g_lsap_smem_limit) {
+        int dev = 0, maxopt = 0;
+        SSB_CHECK_CUDA(cudaGetDevice(&dev));
+        SSB_CHECK_CUDA(cudaDeviceGetAttribute(&maxopt, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        int want = maxopt - 2048;
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(assign_stage_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(assign_stage_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
+        g_lsap_smem_limit = want;
+    }
+    size_t fixed = (size_t)L * (3 * 8 + 4 * 4 + 2) + 64;
+    if (fixed + 1024 > (size_t)g_lsap_smem_limit) {
+        ssb_set_error("LSAP dimension %d exceeds shared memory", L);
+        return -3;
+    }
+    *dyn_bytes = g_lsap_smem_limit;
+    *cost_bytes = (size_t)g_lsap_smem_limit - fixed - 16;
+    return 0;
+}
+
+int ssb_launch_prep(const SsbDims &d, const float *dets, int n, int h, int w, FrameScratch fs,
+                    cudaStream_t st) {
+    if (n > 0) {
+        prep_dets_kernel<<<(n + 127) / 128, 128, 0, st>>>(dets, n, h, w, fs);
+        SSB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+int ssb_launch_track_frame(ssb_tracker *t, int n, int h, int w, const float *feats, double *out,
+                           int *counts, int track_hint, cudaStream_t st) {
+    const SsbDims &d = t->dims;
+    TrackTable tt = t->tt;
+    FrameScratch fs = t->fs;
+    fs.feats = const_cast<float *>(feats);
+    const int Tmax = (track_hint >= 0 && track_hint <= d.S) ? track_hint : d.S;
+    const int L = d.S > d.N ? d.S : d.N;
+    size_t dyn = 0, cost_b = 0;
+    int rc = lsap_prepare(L, &dyn, &cost_b);
+    if (rc) return rc;
+
+    if (n > 0) {
+        det_norm_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(fs.feats, n, d.D, fs.det_norm);
+        SSB_CHECK_LAUNCH();
+    }
+    if (Tmax > 0) {
+        kf_predict_tracks_kernel<<<(Tmax * 32 + 127) / 128, 128, 0, st>>>(tt);
+        SSB_CHECK_LAUNCH();
+    }
+    build_lists_kernel<<<1, 256, 0, st>>>(tt, fs);
+    SSB_CHECK_LAUNCH();
+    if (Tmax > 0 && n > 0) {
+        rc = ssb_launch_appearance(tt.gallery, tt.gal_count, tt.gal_head, fs.conf_list, tt.order,
+                                   fs.cnt + FC_N_CONF, Tmax, d.B, fs.feats, n, d.D, fs.app_cost, n, st);
+        if (rc) return rc;
+        gate_cost_kernel<<<Tmax, 128, 0, st>>>(tt, fs, d, n);
+        SSB_CHECK_LAUNCH();
+    }
+    assign_stage_a_kernel<<<1, 256, dyn, st>>>(tt, fs, d, n, L, cost_b);
+    SSB_CHECK_LAUNCH();
+    if (Tmax > 0 && n > 0) {
+        iou_cost_kernel<<<Tmax, 128, 0, st>>>(tt, fs, d);
+        SSB_CHECK_LAUNCH();
+    }
+    assign_stage_b_kernel<<<1, 256, dyn, st>>>(tt, fs, d, L, cost_b);
+    SSB_CHECK_LAUNCH();
+    const int max_match = Tmax < n ? Tmax : n;
+    if (max_match > 0) {
+        update_matched_kernel<<<max_match, 128, 0, st>>>(tt, fs, d);
+        SSB_CHECK_LAUNCH();
+    }
+    bookkeep_kernel<<<1, 256, 0, st>>>(tt, fs, d, h, w, out, counts);
+    SSB_CHECK_LAUNCH();
+    int Tafter = Tmax + n;
+    if (Tafter > d.S) Tafter = d.S;
+    if (Tafter > 0) {
+        gallery_append_kernel<<<Tafter, 128, 0, st>>>(tt, d);
+        SSB_CHECK_LAUNCH();
+    }
+    return 0;
+}
+
+// ---- stage entry points ----------------------------------------------------
+extern "C" int ssb_crop_boxes(const float *dets_dev, int n, int h, int w, int32_t *boxes_out_dev,
+                              ssb_stream_t stream) {
+    if (n <= 0) return 0;
+    crop_boxes_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(dets_dev, n, h, w, boxes_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ssb_kf_predict(double *mean_dev, double *cov_dev, int n, ssb_stream_t stream) {
+    if (n <= 0) return 0;
+    kf_predict_arrays_kernel<<<(n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, n);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ssb_kf_update(double *mean_dev, double *cov_dev, const float *xyah_dev,
+                             const float *conf_dev, int n, ssb_stream_t stream) {
+    if (n <= 0) return 0;
+    kf_update_arrays_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, xyah_dev, conf_dev, n);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ssb_kf_gating(const double *mean_dev, const double *cov_dev, int n_tracks,
+                             const float *xyah_dev, int n_meas, double *maha_out_dev,
+                             ssb_stream_t stream) {
+    if (n_tracks <= 0 || n_meas <= 0) return 0;
+    kf_gating_arrays_kernel<<<n_tracks, 128, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, n_tracks, xyah_dev, n_meas, maha_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ssb_iou_cost(const double *track_tlwh_dev, int n_tracks, const float *det_tlwh_dev,
+                            int n_dets, double *cost_out_dev, ssb_stream_t stream) {
+    if (n_tracks <= 0 || n_dets <= 0) return 0;
+    iou_cost_arrays_kernel<<<n_tracks, 128, 0, (cudaStream_t)stream>>>(track_tlwh_dev, n_tracks, det_tlwh_dev, n_dets, cost_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int ssb_lsap(const double *cost_dev, int nr, int nc, int32_t *col4row_out_dev,
+                        int32_t *row4col_out_dev, ssb_stream_t stream) {
+    if (nr < 0 || nc < 0) { ssb_set_error("negative LSAP dims"); return -1; }
+    const int L = (nr > nc ? nr : nc) > 1 ? (nr > nc ? nr : nc) : 1;
+    size_t dyn = 0, cost_b = 0;
+    int rc = lsap_prepare(L, &dyn, &cost_b);
+    if (rc) return rc;
+    lsap_kernel<<<1, 256, dyn, (cudaStream_t)stream>>>(cost_dev, nr, nc, L, cost_b, col4row_out_dev, row4col_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+int ssb_launch_reset(ssb_tracker *t, cudaStream_t st) {
+    reset_table_kernel<<<(t->dims.S + 127) / 128, 128, 0, st>>>(t->tt, t->dims);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+int ssb_launch_export(ssb_tracker *t, int *ids, int *state, int *hits, int *age, int *tsu, int *gal,
+                      double *mean, double *cov, float *feat, cudaStream_t st) {
+    export_tracks_kernel<<<t->dims.S, 64, 0, st>>>(t->tt, t->dims, ids, state, hits, age, tsu, gal, mean, cov, feat);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}

@@ -1,0 +1,234 @@
+"""``StrongSORT.update(dets, img)`` -- host-side mirror of the reference's tracker
+seam, driving the sm_100a kernels of libssb.so through the C-ABI (include/ssb.h).
+
+Reference boundary: the tracker call of /root/reference/yolo_multi_model.py:41
+(``model.track(..., persist=True, tracker=...)``) behind which upstream's
+``StrongSORT.update(dets, ori_img)`` sits (the strong_sort/
+package itself is absent from the snapshot).  Same constructor knobs
+(strong_sort.yaml, A.1), same argument meaning, same output rows
+``[x1, y1, x2, y2, track_id, class_id, conf]``.
+
+PyTorch is used for device memory, pinned staging buffers and streams only.
+There is no CPU path: without libssb.so or a CUDA device construction raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib, weights as _weights
+
+CNT_OUT_ROWS, CNT_TRACKS, CNT_CONFIRMED, CNT_NEXT_ID = 0, 1, 2, 3
+CNT_MATCHES_A, CNT_MATCHES_B, CNT_NEW, CNT_ERROR = 4, 5, 6, 7
+_HDR_BYTES = 64          # counts live in front of the output rows
+
+
+class StrongSORT:
+    def __init__(self, model_weights=None, device="cuda:0", fp16=False,
+                 max_dist=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
+                 nn_budget=100, mc_lambda=0.995, ema_alpha=0.9,
+                 max_tracks=1024, max_dets=512):
+        torch = _lib.require_cuda()
+        self._torch = torch
+        self._lib = _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise _lib.SsbError("StrongSORT(device=...) must be a CUDA device")
+        self.fp16 = bool(fp16)   # accepted for signature parity; kernels pick their own precision
+        cfg = _lib.SsbConfig()
+        self._lib.ssb_default_config(C.byref(cfg))
+        cfg.max_tracks, cfg.max_dets = int(max_tracks), int(max_dets)
+        cfg.nn_budget, cfg.n_init, cfg.max_age = int(nn_budget), int(n_init), int(max_age)
+        cfg.max_dist, cfg.max_iou_distance = float(max_dist), float(max_iou_distance)
+        cfg.mc_lambda, cfg.ema_alpha = float(mc_lambda), float(ema_alpha)
+        self.cfg = cfg
+        nbytes = self._lib.ssb_workspace_bytes(C.byref(cfg))
+        if nbytes < 0:
+            _lib.check(-1, "ssb_workspace_bytes")
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+            self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
+            base = (self._ws.data_ptr() + 255) & ~255
+            h = C.c_void_p()
+            _lib.check(self._lib.ssb_create(C.byref(cfg), C.c_void_p(base), nbytes, C.byref(h)),
+                       "ssb_create")
+            self._h = h
+            # ReID weights
+            sd = _weights.load_state_dict(model_weights)
+            blob, sizes = _weights.pack(_weights.fold(sd))
+            self._w_blob = torch.from_numpy(blob).to(self.device)
+            self._w_sizes = (C.c_int64 * len(sizes))(*[int(s) for s in sizes])
+            _lib.check(self._lib.ssb_reid_set_weights(self._h, _lib.ptr(self._w_blob),
+                                                      self._w_sizes, len(sizes)),
+                       "ssb_reid_set_weights")
+            # staging
+            S, N = cfg.max_tracks, cfg.max_dets
+            self._dets_pin = torch.empty((N, 6), dtype=torch.float32).pin_memory()
+            self._dets_dev = torch.empty((N, 6), dtype=torch.float32, device=self.device)
+            self._out_bytes = _HDR_BYTES + S * _lib.SSB_OUT_COLS * 8
+            self._out_dev = torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device)
+            self._out_pin = torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory()
+            self._img_dev = None
+            self._img_pin = None
+            self._feats_dev = torch.empty((N, cfg.feat_dim), dtype=torch.float32, device=self.device)
+        self._out_np = self._out_pin.numpy()
+        self._counts_np = self._out_np[:32].view(np.int32)
+        self._rows_np = self._out_np[_HDR_BYTES:].view(np.float64).reshape(S, _lib.SSB_OUT_COLS)
+        self._track_hint = 0
+        self.last_counts = np.zeros(8, dtype=np.int32)
+        self.last_det_index = np.zeros(0, dtype=np.int64)
+        self.reset()
+
+    # ------------------------------------------------------------------
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self._lib.ssb_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def reset(self):
+        """Forget all tracks (ids restart at 1)."""
+        _lib.check(self._lib.ssb_reset(self._h, C.c_void_p(self.stream.cuda_stream)), "ssb_reset")
+        self.stream.synchronize()
+        self._track_hint = 0
+
+    # ------------------------------------------------------------------
+    def _stage_image(self, img):
+        torch = self._torch
+        if torch.is_tensor(img):
+            if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3:
+                raise ValueError("img tensor must be uint8 [H,W,3]")
+            if img.is_cuda:
+                if img.device != self.device:
+                    img = img.to(self.device)
+                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+                return img.contiguous()
+            src = img.contiguous()
+        else:
+            img = np.asarray(img)
+            if img.dtype != np.uint8 or img.ndim != 3 or img.shape[2] != 3:
+                raise ValueError("img must be a uint8 HxWx3 array (BGR)")
+            src = torch.from_numpy(np.ascontiguousarray(img))
+        if self._img_dev is None or tuple(self._img_dev.shape) != tuple(src.shape):
+            self._img_dev = torch.empty(tuple(src.shape), dtype=torch.uint8, device=self.device)
+        self._img_dev.copy_(src, non_blocking=True)      # on self.stream (set by caller)
+        return self._img_dev
+
+    def update(self, dets, ori_img, features=None):
+        """dets: [N,6] (x1,y1,x2,y2,conf,cls) torch CPU tensor / ndarray (or a
+        CUDA tensor); ori_img: BGR uint8 HxWx3 ndarray (or torch tensor, CPU
+        pinned or CUDA).  Returns float64 ndarray [M,7]; ``[]``-like empty
+        array when there is nothing to report (caller treats as "no ids",
+        yolo_multi_model.py:54).  ``features`` (tests only) bypasses OSNet."""
+        torch = self._torch
+        lib = self._lib
+        if torch.is_tensor(dets):
+            d = dets.detach()
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(np.asarray(dets, dtype=np.float32)))
+        d = d.reshape(-1, 6).to(torch.float32)
+        n = int(d.shape[0])
+        if n > self.cfg.max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self.cfg.max_dets}")
+        H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
+        st = C.c_void_p(self.stream.cuda_stream)
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            if n:
+                if d.is_cuda:
+                    self._dets_dev[:n].copy_(d, non_blocking=True)
+                else:
+                    self._dets_pin[:n].copy_(d)
+                    self._dets_dev[:n].copy_(self._dets_pin[:n], non_blocking=True)
+            feats_ptr = None
+            img_dev = None
+            if features is not None:
+                f = torch.as_tensor(features, dtype=torch.float32).reshape(n, self.cfg.feat_dim)
+                self._feats_dev[:n].copy_(f, non_blocking=False)
+                feats_ptr = _lib.ptr(self._feats_dev)
+            elif n:
+                img_dev = self._stage_image(ori_img)
+            pitch = 3 * W
+            _lib.check(lib.ssb_update(
+                self._h, _lib.ptr(self._dets_dev), n,
+                _lib.ptr(img_dev) if img_dev is not None else None, H, W, pitch,
+                feats_ptr, C.c_void_p(self._out_dev.data_ptr() + _HDR_BYTES),
+                _lib.ptr(self._out_dev), self._track_hint, st), "ssb_update")
+            self._out_pin.copy_(self._out_dev, non_blocking=True)
+        self.stream.synchronize()
+        cnt = self._counts_np
+        self.last_counts = cnt.copy()
+        if cnt[CNT_ERROR]:
+            raise _lib.SsbError("track table overflow: raise max_tracks / max_dets")
+        self._track_hint = int(cnt[CNT_TRACKS])
+        m = int(cnt[CNT_OUT_ROWS])
+        rows = self._rows_np[:m].copy()
+        self.last_det_index = rows[:, 7].astype(np.int64)
+        return rows[:, :7]
+
+    # ------------------------------------------------------------------
+    def extract_features(self, ori_img, boxes_xyxy_int):
+        """OSNet embeddings of integer crop boxes (parity tests / ssb_reid)."""
+        torch = self._torch
+        b = torch.as_tensor(np.asarray(boxes_xyxy_int, dtype=np.int32).reshape(-1, 4))
+        n = int(b.shape[0])
+        H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            img_dev = self._stage_image(ori_img)
+            bd = b.to(self.device)
+            out = torch.empty((n, self.cfg.feat_dim), dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.ssb_reid(self._h, _lib.ptr(img_dev), H, W, 3 * W, _lib.ptr(bd), n,
+                                          _lib.ptr(out), C.c_void_p(self.stream.cuda_stream)),
+                       "ssb_reid")
+        self.stream.synchronize()
+        return out.cpu().numpy()
+
+    def export_tracks(self):
+        """Live track table in list order (== Tracker.tracks of the oracle)."""
+        torch = self._torch
+        T = self._track_hint
+        S, D = self.cfg.max_tracks, self.cfg.feat_dim
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            ints = [torch.zeros(S, dtype=torch.int32, device=self.device) for _ in range(6)]
+            mean = torch.zeros((S, 8), dtype=torch.float64, device=self.device)
+            cov = torch.zeros((S, 8, 8), dtype=torch.float64, device=self.device)
+            feat = torch.zeros((S, D), dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.ssb_export_tracks(
+                self._h, *[_lib.ptr(t) for t in ints], _lib.ptr(mean), _lib.ptr(cov),
+                _lib.ptr(feat), C.c_void_p(self.stream.cuda_stream)), "ssb_export_tracks")
+        self.stream.synchronize()
+        names = ["track_id", "state", "hits", "age", "tsu", "gallery_len"]
+        out = {k: v[:T].cpu().numpy().astype(np.int64) for k, v in zip(names, ints)}
+        out["mean"] = mean[:T].cpu().numpy()
+        out["cov"] = cov[:T].cpu().numpy()
+        out["feat"] = feat[:T].cpu().numpy()
+        return out
+
+    def debug_costs(self):
+        """(cost_a [rows_a, cols_a], cost_b [rows_b, cols_b]) of the last update."""
+        pa, pb, pd = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        _lib.check(self._lib.ssb_debug_cost_ptrs(self._h, C.byref(pa), C.byref(pb), C.byref(pd)),
+                   "ssb_debug_cost_ptrs")
+        self.stream.synchronize()
+        dims = _wrap_device(self._torch, pd.value, (4,), "<i4", self.device).cpu().numpy()
+        ra, ca, rb, cb = [int(x) for x in dims]
+        a = np.zeros((ra, ca), dtype=np.float64)
+        b = np.zeros((rb, cb), dtype=np.float64)
+        if a.size:
+            a = _wrap_device(self._torch, pa.value, (ra, ca), "<f8", self.device).cpu().numpy()
+        if b.size:
+            b = _wrap_device(self._torch, pb.value, (rb, cb), "<f8", self.device).cpu().numpy()
+        return a, b
+
+
+class _DevView:
+    def __init__(self, ptr, shape, typestr):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def _wrap_device(torch, ptr, shape, typestr, device):
+    """View raw device memory (owned by the tracker workspace) as a tensor."""
+    return torch.as_tensor(_DevView(ptr, shape, typestr), device=device)

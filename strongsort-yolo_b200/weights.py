@@ -1,0 +1,112 @@
+"""OSNet-x0.25 checkpoint loading, BatchNorm folding and packing for the device.
+
+Input: a torchreid-style state_dict ({name: array}; .npz, or a torch .pth/.pt
+checkpoint).  Output: one flat float32 blob whose tensor order and layouts are
+the canonical walk of csrc/reid.cu (``reid_tensor_sizes_host``):
+
+  stem  W[ky][kx][ci][co], b      (conv1 7x7 + BN folded)
+  per OSBlock: conv1 W[ci][co], b | 10 x LightConv (pw W[ci][co], dw W[tap][c]
+               with BN scale folded, b) in order a1,b1,b2,c1..c3,d1..d4 |
+               gate fc1 W[c][r], b, fc2 W[r][c], b | conv3 W[ci][co], b |
+               downsample W[ci][co], b (if cin != cout) | transition W, b
+  conv5 W[ci][co], b ; fc W[ci][co] (BN1d folded), b
+Each tensor starts on a 16-byte boundary inside the blob.
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+BN_EPS = 1e-5
+BLOCKS = [(16, 64), (64, 64), (64, 96), (96, 96), (96, 128), (128, 128)]
+DEFAULT_WEIGHTS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "weights",
+                               "osnet_x0_25_synth.npz")
+
+
+def load_state_dict(path=None):
+    path = path or DEFAULT_WEIGHTS
+    if path.endswith(".npz"):
+        return {k: np.asarray(v) for k, v in np.load(path).items()}
+    import torch
+    sd = torch.load(path, map_location="cpu")
+    if isinstance(sd, dict) and "state_dict" in sd:
+        sd = sd["state_dict"]
+    return {k.replace("module.", "", 1): v.detach().cpu().numpy() for k, v in sd.items()
+            if hasattr(v, "detach")}
+
+
+def _bn(sd, prefix):
+    g = sd[prefix + ".weight"].astype(np.float64)
+    b = sd[prefix + ".bias"].astype(np.float64)
+    m = sd[prefix + ".running_mean"].astype(np.float64)
+    v = sd[prefix + ".running_var"].astype(np.float64)
+    scale = g / np.sqrt(v + BN_EPS)
+    return scale, b - m * scale
+
+
+def _fold_conv(sd, conv, bn):
+    """[co,ci,kh,kw] conv + BN -> W[kh][kw][ci][co] (squeezed for 1x1), b[co]."""
+    w = sd[conv + ".weight"].astype(np.float64)
+    scale, shift = _bn(sd, bn)
+    w = w * scale[:, None, None, None]
+    w = np.transpose(w, (2, 3, 1, 0))                     # kh, kw, ci, co
+    if w.shape[0] == 1 and w.shape[1] == 1:
+        w = w[0, 0]                                       # [ci][co]
+    return w, shift
+
+
+def fold(sd):
+    """-> list of (name, float32 ndarray) in canonical order."""
+    out = []
+    w, b = _fold_conv(sd, "conv1.conv", "conv1.bn")
+    out += [("stem.w", w), ("stem.b", b)]
+    stage_of = ["conv2.0", "conv2.1", "conv3.0", "conv3.1", "conv4.0", "conv4.1"]
+    streams = [["conv2a"], ["conv2b.0", "conv2b.1"],
+               ["conv2c.0", "conv2c.1", "conv2c.2"],
+               ["conv2d.0", "conv2d.1", "conv2d.2", "conv2d.3"]]
+    for bi, (cin, cout) in enumerate(BLOCKS):
+        p = stage_of[bi]
+        w, b = _fold_conv(sd, f"{p}.conv1.conv", f"{p}.conv1.bn")
+        out += [(f"{p}.conv1.w", w), (f"{p}.conv1.b", b)]
+        for names in streams:
+            for nm in names:
+                q = f"{p}.{nm}"
+                pw = sd[q + ".conv1.weight"].astype(np.float64)[:, :, 0, 0].T   # [ci][co]
+                scale, shift = _bn(sd, q + ".bn")
+                dw = sd[q + ".conv2.weight"].astype(np.float64)[:, 0]          # [c][3][3]
+                dw = (dw * scale[:, None, None]).reshape(dw.shape[0], 9).T     # [tap][c]
+                out += [(q + ".pw", pw), (q + ".dw", dw), (q + ".b", shift)]
+        g = f"{p}.gate"
+        out += [(g + ".fc1.w", sd[g + ".fc1.weight"].astype(np.float64)[:, :, 0, 0].T),
+                (g + ".fc1.b", sd[g + ".fc1.bias"].astype(np.float64)),
+                (g + ".fc2.w", sd[g + ".fc2.weight"].astype(np.float64)[:, :, 0, 0].T),
+                (g + ".fc2.b", sd[g + ".fc2.bias"].astype(np.float64))]
+        w, b = _fold_conv(sd, f"{p}.conv3.conv", f"{p}.conv3.bn")
+        out += [(f"{p}.conv3.w", w), (f"{p}.conv3.b", b)]
+        if cin != cout:
+            w, b = _fold_conv(sd, f"{p}.downsample.conv", f"{p}.downsample.bn")
+            out += [(f"{p}.down.w", w), (f"{p}.down.b", b)]
+        if bi in (1, 3):
+            t = p.split(".")[0] + ".2.0"
+            w, b = _fold_conv(sd, f"{t}.conv", f"{t}.bn")
+            out += [(f"{t}.w", w), (f"{t}.b", b)]
+    w, b = _fold_conv(sd, "conv5.conv", "conv5.bn")
+    out += [("conv5.w", w), ("conv5.b", b)]
+    scale, shift = _bn(sd, "fc.1")
+    fw = sd["fc.0.weight"].astype(np.float64) * scale[:, None]            # [co][ci]
+    fb = sd["fc.0.bias"].astype(np.float64) * scale + shift
+    out += [("fc.w", fw.T), ("fc.b", fb)]
+    return [(n, np.ascontiguousarray(a, dtype=np.float32)) for n, a in out]
+
+
+def pack(tensors):
+    """-> (blob float32 [total], sizes int64 [n]) with 16-byte aligned tensors."""
+    sizes = np.asarray([a.size for _, a in tensors], dtype=np.int64)
+    padded = (sizes + 3) & ~3
+    blob = np.zeros(int(padded.sum()), dtype=np.float32)
+    off = 0
+    for (_, a), p in zip(tensors, padded):
+        blob[off:off + a.size] = a.reshape(-1)
+        off += int(p)
+    return blob, sizes

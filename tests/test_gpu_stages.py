@@ -1,0 +1,218 @@
+"""GPU parity, stage by stage, through the C-ABI (include/ssb.h) against the
+CPU oracle.  Integer / index results bit-exact; float64 Kalman math to 1e-9
+rel (LAPACK vs. hand-ordered Cholesky); float32 costs to 1e-5 abs."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+import torch
+from scipy.optimize import linear_sum_assignment
+
+from oracle import nms_np, strongsort_np as ss
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from strongsort_yolo_b200 import _lib
+    return _lib.load()
+
+
+def dev(a):
+    return torch.as_tensor(np.ascontiguousarray(a)).cuda()
+
+
+def P(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def ST():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _tracks(rng, n):
+    kf = ss.KalmanFilter()
+    means, covs = [], []
+    for _ in range(n):
+        z = np.array([rng.uniform(50, 1800), rng.uniform(50, 1000), rng.uniform(0.3, 0.5),
+                      rng.uniform(80, 240)], dtype=np.float32)
+        m, Pm = kf.initiate(z)
+        for _ in range(int(rng.integers(0, 4))):
+            m, Pm = kf.predict(m, Pm)
+            zz = (m[:4] + rng.normal(0, 1, 4) * [2, 2, 0.01, 2]).astype(np.float32)
+            m, Pm = kf.update(m, Pm, zz, float(rng.uniform(0.5, 0.95)))
+        means.append(m); covs.append(Pm)
+    return kf, np.asarray(means), np.asarray(covs)
+
+
+def test_kf_predict_update_gating(lib):
+    from strongsort_yolo_b200 import _lib
+    rng = np.random.default_rng(11)
+    kf, means, covs = _tracks(rng, 300)
+    m_d, c_d = dev(means), dev(covs)
+    _lib.check(lib.ssb_kf_predict(P(m_d), P(c_d), 300, ST()))
+    ref = [kf.predict(m, c) for m, c in zip(means, covs)]
+    rm, rc = np.asarray([r[0] for r in ref]), np.asarray([r[1] for r in ref])
+    np.testing.assert_allclose(m_d.cpu().numpy(), rm, rtol=1e-13, atol=0)
+    np.testing.assert_allclose(c_d.cpu().numpy(), rc, rtol=1e-12, atol=1e-18)
+
+    z = (rm[:, :4] + rng.normal(0, 1, (300, 4)) * [3, 3, 0.02, 3]).astype(np.float32)
+    conf = rng.uniform(0.5, 0.95, 300).astype(np.float32)
+    z_d, conf_d = dev(z), dev(conf)
+    # gating first (on predicted state)
+    out = torch.zeros((300, 300), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ssb_kf_gating(P(m_d), P(c_d), 300, P(z_d), 300, P(out), ST()))
+    g_ref = np.asarray([kf.gating_distance(m, c, z) for m, c in zip(rm, rc)])
+    np.testing.assert_allclose(out.cpu().numpy(), g_ref, rtol=1e-9, atol=1e-9)
+    # the threshold decisions agree wherever the oracle is not within 1e-9 of it
+    far = np.abs(g_ref - 9.4877) > 1e-6
+    assert np.array_equal((out.cpu().numpy() > 9.4877)[far], (g_ref > 9.4877)[far])
+    _lib.check(lib.ssb_kf_update(P(m_d), P(c_d), P(z_d), P(conf_d), 300, ST()))
+    ref = [kf.update(m, c, zz, float(cc)) for m, c, zz, cc in zip(rm, rc, z, conf)]
+    np.testing.assert_allclose(m_d.cpu().numpy(), np.asarray([r[0] for r in ref]), rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(c_d.cpu().numpy(), np.asarray([r[1] for r in ref]), rtol=1e-8, atol=1e-10)
+
+
+def test_crop_boxes_bit_exact(lib):
+    from strongsort_yolo_b200 import _lib
+    rng = np.random.default_rng(5)
+    n = 500
+    x1, y1 = rng.uniform(-20, 1900, n), rng.uniform(-20, 1060, n)
+    dets = np.stack([x1, y1, x1 + rng.uniform(4, 200, n), y1 + rng.uniform(4, 300, n),
+                     rng.uniform(0.3, 1, n), np.zeros(n)], 1).astype(np.float32)
+    out = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    _lib.check(lib.ssb_crop_boxes(P(dev(dets)), n, 1080, 1920, P(out), ST()))
+    ref = np.asarray([ss.crop_box_xyxy(b, 1920, 1080) for b in ss.xyxy2xywh(dets[:, :4])])
+    np.testing.assert_array_equal(out.cpu().numpy(), ref)
+
+
+def test_iou_cost(lib):
+    from strongsort_yolo_b200 import _lib
+    rng = np.random.default_rng(2)
+    T, N = 150, 333
+    tl = np.stack([rng.uniform(0, 1800, T), rng.uniform(0, 1000, T), rng.uniform(20, 100, T),
+                   rng.uniform(60, 240, T)], 1)
+    dt = np.stack([rng.uniform(0, 1800, N), rng.uniform(0, 1000, N), rng.uniform(20, 100, N),
+                   rng.uniform(60, 240, N)], 1).astype(np.float32)
+    dt[:T] = (tl + rng.normal(0, 3, (T, 4))).astype(np.float32)[:min(T, N)]
+    out = torch.zeros((T, N), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ssb_iou_cost(P(dev(tl)), T, P(dev(dt)), N, P(out), ST()))
+    ref = np.asarray([1.0 - ss.iou(tl[i], dt) for i in range(T)])
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-14, atol=1e-15)
+
+
+@pytest.mark.parametrize("T,B,N", [(1, 1, 1), (7, 100, 10), (100, 100, 100), (37, 100, 130), (256, 100, 500), (5, 150, 70)])
+def test_appearance_cost(lib, T, B, N):
+    from strongsort_yolo_b200 import _lib
+    rng = np.random.default_rng(T * 1000 + N)
+    D = 512
+    gal = np.maximum(rng.normal(0, 1, (T, B, D)), 0).astype(np.float32)
+    counts = rng.integers(1, B + 1, T).astype(np.int32)
+    counts[0] = B
+    feats = np.maximum(rng.normal(0, 1, (N, D)), 0).astype(np.float32)
+    # make some pairs close
+    for i in range(min(T, N)):
+        feats[i] = gal[i, 0] + 0.1 * rng.normal(0, 1, D).astype(np.float32)
+    out = torch.zeros((T, N), dtype=torch.float32, device="cuda")
+    _lib.check(lib.ssb_appearance_cost(P(dev(gal)), P(dev(counts)), T, B, P(dev(feats)), N, D, P(out), ST()))
+    ref = np.stack([ss._nn_cosine_distance(gal[t, :counts[t]], feats) for t in range(T)])
+    np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
+
+
+def _lsap_cases():
+    rng = np.random.default_rng(8)
+    shapes = [(1, 1), (1, 9), (9, 1), (10, 10), (33, 64), (64, 33), (100, 100), (115, 100),
+              (100, 130), (256, 500), (300, 170), (40, 40)]
+    for (nr, nc) in shapes:
+        for kind in range(5):
+            if kind == 0:
+                c = rng.random((nr, nc))
+            elif kind == 1:
+                c = rng.integers(0, 3, (nr, nc)).astype(float)
+            elif kind == 2:
+                c = np.full((nr, nc), 0.2 + 1e-5)
+            elif kind == 3:
+                c = rng.random((nr, nc)) * 0.3; c[c > 0.2] = 0.2 + 1e-5
+            else:
+                c = np.full((nr, nc), 0.7 + 1e-5)
+                for i in range(min(nr, nc)):
+                    c[i, (i * 7) % nc] = rng.random() * 0.7
+            yield c
+
+
+def test_lsap_matches_scipy(lib):
+    from strongsort_yolo_b200 import _lib
+    for c in _lsap_cases():
+        nr, nc = c.shape
+        c4r = torch.full((nr,), -7, dtype=torch.int32, device="cuda")
+        r4c = torch.full((nc,), -7, dtype=torch.int32, device="cuda")
+        _lib.check(lib.ssb_lsap(P(dev(c)), nr, nc, P(c4r), P(r4c), ST()))
+        rows, cols = linear_sum_assignment(c)
+        want_c4r = -np.ones(nr, dtype=np.int32); want_c4r[rows] = cols
+        want_r4c = -np.ones(nc, dtype=np.int32); want_r4c[cols] = rows
+        np.testing.assert_array_equal(c4r.cpu().numpy(), want_c4r, err_msg=str(c.shape))
+        np.testing.assert_array_equal(r4c.cpu().numpy(), want_r4c, err_msg=str(c.shape))
+
+
+def test_lsap_empty_and_nan(lib):
+    from strongsort_yolo_b200 import _lib
+    c4r = torch.full((4,), -7, dtype=torch.int32, device="cuda")
+    r4c = torch.full((4,), -7, dtype=torch.int32, device="cuda")
+    dummy = torch.zeros(16, dtype=torch.float64, device="cuda")
+    _lib.check(lib.ssb_lsap(P(dummy), 0, 4, P(c4r), P(r4c), ST()))
+    assert (r4c.cpu().numpy() == -1).all()
+    bad = torch.full((4, 4), float("nan"), dtype=torch.float64, device="cuda")
+    _lib.check(lib.ssb_lsap(P(bad), 4, 4, P(c4r), P(r4c), ST()))      # must terminate
+    torch.cuda.synchronize()
+    assert (c4r.cpu().numpy() == -1).all()
+
+
+def test_reid_embeddings_kat(golden_dir):
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    g = np.load(os.path.join(golden_dir, "reid_kat.npz"))
+    trk = StrongSORT(max_tracks=64, max_dets=64)
+    emb = trk.extract_features(g["img"], g["boxes"])
+    ref = g["emb"]
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(emb - ref) / scale) < 1e-3          # north_star: floats within 1e-3 rel
+    cos = (emb * ref).sum(1) / (np.linalg.norm(emb, axis=1) * np.linalg.norm(ref, axis=1))
+    assert np.all(1 - cos < 1e-5)
+
+
+def test_reid_embeddings_live(oracle_extractor):
+    from strongsort_yolo_b200 import synth
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1")
+    fr = st.next_frame()
+    boxes = np.asarray([ss.crop_box_xyxy(b, 640, 640) for b in ss.xyxy2xywh(fr.dets[:, :4])])
+    trk = StrongSORT(max_tracks=64, max_dets=64)
+    emb = trk.extract_features(fr.img, boxes)
+    ref = oracle_extractor(fr.img, boxes)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    assert np.max(np.abs(emb - ref) / scale) < 1e-3
+
+
+@pytest.mark.parametrize("A,nc,extra", [(1200, 80, 0), (8400, 80, 0), (5040, 1, 51), (700, 3, 0)])
+def test_yolo_nms_matches_torchvision(A, nc, extra, golden_dir):
+    from strongsort_yolo_b200 import yolo
+    rng = np.random.default_rng(A + nc)
+    if A == 1200:
+        pred = np.load(os.path.join(golden_dir, "nms_kat.npz"))["pred"]
+    else:
+        n = 120
+        cx, cy = rng.uniform(60, 580, n), rng.uniform(60, 580, n)
+        w, h = rng.uniform(20, 120, n), rng.uniform(30, 160, n)
+        dets = np.stack([cx - w / 2, cy - h / 2, cx + w / 2, cy + h / 2, rng.uniform(0.31, 0.95, n),
+                         rng.integers(0, nc, n)], 1).astype(np.float32)
+        ex = rng.normal(0, 1, (n, extra)).astype(np.float32) if extra else None
+        pred = yolo.synth_head(dets, num_classes=nc, num_anchors=A, rng=rng, extra=ex, jitter=5)
+    nms = yolo.YoloNMS(num_classes=nc, num_extra=extra, max_anchors=A)
+    got = nms.detect(torch.as_tensor(pred).cuda())
+    want = nms_np.yolo_nms(pred, nc, extra, 0.3, 0.4, 1000, False)
+    np.testing.assert_array_equal(got, want)
+    # max_det truncation and the agnostic switch
+    nms2 = yolo.YoloNMS(num_classes=nc, num_extra=extra, max_anchors=A, max_det=7, agnostic=True)
+    np.testing.assert_array_equal(nms2.detect(torch.as_tensor(pred).cuda()),
+                                  nms_np.yolo_nms(pred, nc, extra, 0.3, 0.4, 7, True))

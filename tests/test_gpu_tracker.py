@@ -1,0 +1,148 @@
+"""GPU parity of the whole StrongSORT.update(dets, img) path against the CPU
+oracle on identical seeded frames: assignment indices and track IDs bit-exact,
+integer boxes exact, Kalman state to 1e-9 rel, features to 1e-5."""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import FeatureBank, assert_rows_equal, assert_tables_equal
+from oracle import strongsort_np as ss
+from strongsort_yolo_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _unpack(flat, lens):
+    out, o = [], 0
+    for n in lens:
+        out.append(flat[o:o + n]); o += n
+    return out
+
+
+def _run_tracker_only(cfg, frames, seed, bank_seed, check_tables_every=1, **stream_kw):
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream(cfg, render=False, **stream_kw)
+    st.rng = np.random.default_rng(seed)
+    bank = FeatureBank(seed=bank_seed)
+    ora = ss.StrongSORTOracle(None)
+    ora.trace_enabled = True
+    gpu = StrongSORT(max_tracks=2048 if cfg == "C4" else 1024, max_dets=640)
+    img = np.zeros((st.H, st.W, 3), dtype=np.uint8)
+    for f in range(frames):
+        fr = st.next_frame()
+        feats = bank(fr.gt_ids)
+        want = ora.update(fr.dets, img, features=feats)
+        got = gpu.update(fr.dets, img, features=feats)
+        tr = ora.last_trace
+        assert_rows_equal(got, want)
+        assert int(gpu.last_counts[3]) == ora.tracker._next_id, f"frame {f}: next id"
+        if f % check_tables_every == 0:
+            assert_tables_equal(gpu.export_tracks(), ora.track_table())
+            a, b = gpu.debug_costs()
+            if "A_cost" in tr:
+                np.testing.assert_allclose(a, tr["A_cost"], rtol=0, atol=5e-6)
+            if "B_cost" in tr:
+                np.testing.assert_allclose(b, tr["B_cost"], rtol=1e-12, atol=1e-12)
+    return gpu, ora
+
+
+def test_c2_tracker_only_vs_oracle():
+    _run_tracker_only("C2", 45, seed=123, bank_seed=3)
+
+
+def test_c2_tracker_only_vs_golden(golden_dir):
+    """The committed C2-sized golden run (tools/make_golden.py)."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    g = np.load(os.path.join(golden_dir, "c2_tracker.npz"))
+    rows = _unpack(g["rows"], g["row_lens"])
+    st = synth.make_stream("C2", render=False)
+    bank = FeatureBank(seed=7)
+    gpu = StrongSORT()
+    img = np.zeros((1080, 1920, 3), dtype=np.uint8)
+    for f in range(len(rows)):
+        fr = st.next_frame()
+        got = gpu.update(fr.dets, img, features=bank(fr.gt_ids))
+        np.testing.assert_array_equal(got[:, :6], rows[f][:, :6], err_msg=f"frame {f}")
+    assert int(gpu.last_counts[3]) == int(g["next_id"])
+
+
+def test_c4_crowded_tracker_only():
+    """C4: 4K, 500 dets/frame, 256 persistent + 244 flickers (transposed LSAP,
+    table churn, cost matrices beyond the shared-memory staging size)."""
+    _run_tracker_only("C4", 12, seed=77, bank_seed=5, check_tables_every=3)
+
+
+def test_lifecycle_occlusion_and_deletion():
+    """Objects vanish for > max_age frames and come back: missed/deleted/new-id
+    paths, gallery retention, tentative deletion."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.SyntheticStream(width=1280, height=720, n_persistent=24, seed=99, render=False,
+                               drop_rate=0.1, spurious_rate=0.05)
+    bank = FeatureBank(seed=9)
+    ora = ss.StrongSORTOracle(None, max_age=5)
+    gpu = StrongSORT(max_age=5, max_tracks=256, max_dets=64)
+    img = np.zeros((720, 1280, 3), dtype=np.uint8)
+    for f in range(70):
+        fr = st.next_frame()
+        keep = np.ones(len(fr.dets), bool)
+        if 20 <= f < 30:
+            keep = fr.gt_ids % 3 != 0          # a third of the objects disappear for 10 frames
+        if f in (40, 41):
+            keep[:] = False                    # two empty frames
+        d, ids = fr.dets[keep], fr.gt_ids[keep]
+        feats = bank(ids)
+        want = ora.update(d, img, features=feats)
+        got = gpu.update(d, img, features=feats)
+        assert_rows_equal(got, want)
+        assert_tables_equal(gpu.export_tracks(), ora.track_table())
+    assert ora.tracker._next_id > 25
+
+
+def test_reset_restarts_ids():
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1", render=False)
+    bank = FeatureBank(seed=1)
+    gpu = StrongSORT(max_tracks=64, max_dets=32)
+    img = np.zeros((640, 640, 3), dtype=np.uint8)
+    frames = [st.next_frame() for _ in range(5)]
+    feats = [bank(f.gt_ids) for f in frames]
+    a = [gpu.update(f.dets, img, features=x) for f, x in zip(frames, feats)]
+    gpu.reset()
+    b = [gpu.update(f.dets, img, features=x) for f, x in zip(frames, feats)]
+    for x, y in zip(a, b):
+        np.testing.assert_array_equal(x, y)      # idempotent after reset
+
+
+def test_c1_end_to_end_vs_golden_and_oracle(oracle_extractor, golden_dir):
+    """Config C1 with the CUDA OSNet in the loop: same ids/boxes as the golden
+    run and as the live oracle; embeddings within 1e-3."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    g = np.load(os.path.join(golden_dir, "c1_e2e.npz"))
+    rows = _unpack(g["rows"], g["row_lens"])
+    st = synth.make_stream("C1")
+    gpu = StrongSORT(max_tracks=64, max_dets=32)
+    for f in range(8):
+        fr = st.next_frame()
+        got = gpu.update(fr.dets, fr.img)
+        np.testing.assert_array_equal(got[:, :6], rows[f][:, :6], err_msg=f"frame {f}")
+    assert int(gpu.last_counts[3]) == int(g["next_id"])
+    tab = gpu.export_tracks()
+    np.testing.assert_array_equal(tab["track_id"], g["tab_track_id"])
+    np.testing.assert_allclose(tab["mean"], g["tab_mean"], rtol=1e-6)
+    np.testing.assert_allclose(tab["feat"], g["tab_feat"], rtol=0, atol=1e-3)
+
+
+def test_c2_end_to_end_vs_oracle(oracle_extractor):
+    """Config C2 (1080p, 100 dets/frame), CUDA OSNet vs the fp32 oracle OSNet."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C2")
+    ora = ss.StrongSORTOracle(oracle_extractor)
+    gpu = StrongSORT()
+    for f in range(12):
+        fr = st.next_frame()
+        want = ora.update(fr.dets, fr.img)
+        got = gpu.update(fr.dets, fr.img)
+        assert_rows_equal(got, want)
+    assert int(gpu.last_counts[3]) == ora.tracker._next_id
+    assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-6, feat_tol=1e-3)
