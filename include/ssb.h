@@ -61,6 +61,8 @@ enum {
 #define SSB_OUT_COLS 8 /* x1,y1,x2,y2,track_id,cls,conf,det_index(-1 if none) */
 
 int ssb_version(void);
+/* kernels launched by this library since load (bench.py reports the delta) */
+int64_t ssb_launch_count(void);
 const char *ssb_last_error(void);
 void ssb_default_config(ssb_config *cfg);
 
@@ -144,6 +146,11 @@ int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, int32_t *hit
  * cols_b (device).                                                          */
 int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev, const double **cost_b_dev,
                         const int32_t **dims_dev);
+
+/* ---- diagnostic: one tcgen05 GEMM tile in the operand layout of the ReID kernels
+ * D[128][n] (f32) = A[shift:shift+128][k] (f16) * B[n][k]^T (f16); status!=0: timeout */
+int ssb_tc_probe(const void *a_dev, int a_rows, int shift, const void *b_dev, int n, int k,
+                 float *d_dev, int32_t *status_dev, ssb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -10,12 +10,12 @@ LIB_PATH = os.path.join(HERE, "libssb.so")
 
 # every symbol include/ssb.h declares (tests/test_abi.py checks the export list)
 SYMBOLS = [
-    "ssb_version", "ssb_last_error", "ssb_default_config", "ssb_workspace_bytes",
+    "ssb_version", "ssb_launch_count", "ssb_last_error", "ssb_default_config", "ssb_workspace_bytes",
     "ssb_create", "ssb_destroy", "ssb_reset", "ssb_reid_num_tensors",
     "ssb_reid_tensor_sizes", "ssb_reid_set_weights", "ssb_update", "ssb_reid",
     "ssb_crop_boxes", "ssb_kf_predict", "ssb_kf_update", "ssb_kf_gating",
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
-    "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs",
+    "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
 ]
 
 SSB_CNT_N = 8
@@ -49,6 +49,7 @@ def load():
     lib = C.CDLL(LIB_PATH)
     vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
     lib.ssb_version.restype = i32
+    lib.ssb_launch_count.restype = i64
     lib.ssb_last_error.restype = C.c_char_p
     lib.ssb_default_config.argtypes = [C.POINTER(SsbConfig)]
     lib.ssb_default_config.restype = None
@@ -73,6 +74,7 @@ def load():
     lib.ssb_nms_scratch_bytes.restype = i64
     lib.ssb_yolo_nms.argtypes = [vp, i32, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp]
     lib.ssb_export_tracks.argtypes = [vp] * 11
+    lib.ssb_tc_probe.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.ssb_debug_cost_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in SYMBOLS:
         fn = getattr(lib, name)

@@ -22,7 +22,9 @@ void ssb_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *ssb_last_error(void) { return g_err; }
+long long g_ssb_launches = 0;
 extern "C" int ssb_version(void) { return 100; }
+extern "C" int64_t ssb_launch_count(void) { return (int64_t)g_ssb_launches; }
 
 extern "C" void ssb_default_config(ssb_config *c) {
     c->max_tracks = 1024;

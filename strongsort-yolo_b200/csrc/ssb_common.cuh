@@ -95,7 +95,12 @@ void ssb_set_error(const char *fmt, ...);
             return -2;                                                              \
         }                                                                           \
     } while (0)
-#define SSB_CHECK_LAUNCH()  SSB_CHECK_CUDA(cudaGetLastError())
+extern long long g_ssb_launches;   // kernels launched by this library (bench.py: gpu_launches)
+#define SSB_CHECK_LAUNCH()                         \
+    do {                                           \
+        g_ssb_launches++;                          \
+        SSB_CHECK_CUDA(cudaGetLastError());        \
+    } while (0)
 
 // launchers implemented across the .cu files --------------------------------
 int ssb_launch_prep(const SsbDims &d, const float *dets, int n, int h, int w,

@@ -10,6 +10,11 @@ if ROOT not in sys.path:
 
 
 def pytest_configure(config):
+    try:      # the oracle's small convs get slower with very many threads
+        import torch
+        torch.set_num_threads(min(16, os.cpu_count() or 1))
+    except Exception:
+        pass
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 

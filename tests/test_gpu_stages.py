@@ -83,7 +83,8 @@ def test_crop_boxes_bit_exact(lib):
     dets = np.stack([x1, y1, x1 + rng.uniform(4, 200, n), y1 + rng.uniform(4, 300, n),
                      rng.uniform(0.3, 1, n), np.zeros(n)], 1).astype(np.float32)
     out = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
-    _lib.check(lib.ssb_crop_boxes(P(dev(dets)), n, 1080, 1920, P(out), ST()))
+    dets_d = dev(dets)      # keep device tensors referenced until the kernel has run
+    _lib.check(lib.ssb_crop_boxes(P(dets_d), n, 1080, 1920, P(out), ST()))
     ref = np.asarray([ss.crop_box_xyxy(b, 1920, 1080) for b in ss.xyxy2xywh(dets[:, :4])])
     np.testing.assert_array_equal(out.cpu().numpy(), ref)
 
@@ -98,7 +99,8 @@ def test_iou_cost(lib):
                    rng.uniform(60, 240, N)], 1).astype(np.float32)
     dt[:T] = (tl + rng.normal(0, 3, (T, 4))).astype(np.float32)[:min(T, N)]
     out = torch.zeros((T, N), dtype=torch.float64, device="cuda")
-    _lib.check(lib.ssb_iou_cost(P(dev(tl)), T, P(dev(dt)), N, P(out), ST()))
+    tl_d, dt_d = dev(tl), dev(dt)
+    _lib.check(lib.ssb_iou_cost(P(tl_d), T, P(dt_d), N, P(out), ST()))
     ref = np.asarray([1.0 - ss.iou(tl[i], dt) for i in range(T)])
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=1e-14, atol=1e-15)
 
@@ -116,7 +118,8 @@ def test_appearance_cost(lib, T, B, N):
     for i in range(min(T, N)):
         feats[i] = gal[i, 0] + 0.1 * rng.normal(0, 1, D).astype(np.float32)
     out = torch.zeros((T, N), dtype=torch.float32, device="cuda")
-    _lib.check(lib.ssb_appearance_cost(P(dev(gal)), P(dev(counts)), T, B, P(dev(feats)), N, D, P(out), ST()))
+    gal_d, counts_d, feats_d = dev(gal), dev(counts), dev(feats)
+    _lib.check(lib.ssb_appearance_cost(P(gal_d), P(counts_d), T, B, P(feats_d), N, D, P(out), ST()))
     ref = np.stack([ss._nn_cosine_distance(gal[t, :counts[t]], feats) for t in range(T)])
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
 
@@ -148,7 +151,9 @@ def test_lsap_matches_scipy(lib):
         nr, nc = c.shape
         c4r = torch.full((nr,), -7, dtype=torch.int32, device="cuda")
         r4c = torch.full((nc,), -7, dtype=torch.int32, device="cuda")
-        _lib.check(lib.ssb_lsap(P(dev(c)), nr, nc, P(c4r), P(r4c), ST()))
+        c_d = dev(c)
+        _lib.check(lib.ssb_lsap(P(c_d), nr, nc, P(c4r), P(r4c), ST()))
+        torch.cuda.synchronize()
         rows, cols = linear_sum_assignment(c)
         want_c4r = -np.ones(nr, dtype=np.int32); want_c4r[rows] = cols
         want_r4c = -np.ones(nc, dtype=np.int32); want_r4c[cols] = rows
