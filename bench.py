@@ -203,6 +203,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=20)
+    ap.add_argument("--only-device", action="store_true",
+                    help="profiling aid: run only the device-resident timed loop (for ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -295,6 +297,12 @@ def main():
     ms_per_step = t_steps_ms / K
     value = world * K / (t_steps_ms / 1000.0)
     final_next_id = int(trk.last_counts[3]) if False else int(trk._out_dev[:32].view(torch.int32)[3].item())
+
+    if args.only_device:
+        if rank == 0:
+            print(json.dumps({"only_device": True, "ms_per_step": ms_per_step, "value": value,
+                              "gpu_launches": launches, "steps": K, "warmup": W}), flush=True)
+        return
 
     # ---------------- ReID alone: roofline of the dominant kernels ------------
     i0 = W + K // 2

@@ -81,6 +81,21 @@ int ssb_reid_num_tensors(void);
 int ssb_reid_tensor_sizes(int64_t *sizes);
 int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const int64_t *sizes, int n);
 
+/* tensor-core OSBlocks (csrc/reid_tc.cu): fp16 hi/lo operand blob built by
+ * weights.pack_tc(); block_offsets[6] are byte offsets of the per-block sections
+ * (each >= ssb_reid_tc_weight_bytes(b), 128-byte aligned).  Setting them switches
+ * the OSBlocks of ssb_reid/ssb_update to the tcgen05 path; ssb_reid_use_tc(t,0)
+ * switches back to the fp32 SIMT baseline. */
+int64_t ssb_reid_tc_weight_bytes(int block);
+int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
+                            int n_blocks);
+int ssb_reid_use_tc(ssb_tracker *t, int enable);
+/* one OSBlock on caller arrays (parity tests): x float32 NHWC [n][H][W][cin] */
+int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, float *y_dev, int n, int use_tc,
+                   ssb_stream_t stream);
+/* copies the tensor-core path's device status word (0 = ok) to the host; synchronises */
+int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream);
+
 /* ---- the per-frame hot path: StrongSORT.update(dets, img) ---------------- */
 /* dets_dev  : float32 [n,6] x1,y1,x2,y2,conf,cls
  * img_dev   : uint8 BGR, h rows of `pitch` bytes (pitch >= 3*w)

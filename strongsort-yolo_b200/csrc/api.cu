@@ -63,7 +63,7 @@ struct Carver {
 };
 
 static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratch *fs,
-                    float **reid_ws, int64_t *reid_floats, int **boxes_tmp) {
+                    float **reid_ws, int64_t *reid_floats, int **boxes_tmp, int **tc_status = nullptr) {
     const size_t S = c->max_tracks, N = c->max_dets, B = c->nn_budget, D = c->feat_dim;
     const size_t L = S > N ? S : N;
     Carver k{base, 0};
@@ -99,6 +99,8 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     const int64_t rf = ssb_reid_ws_floats((int)N);
     float *rw = k.take<float>((size_t)rf);
     int *bt = k.take<int>(N * 4);
+    int *tcs = k.take<int>(64);
+    if (tc_status) *tc_status = tcs;
     if (tt) *tt = t;
     if (fs) *fs = f;
     if (reid_ws) *reid_ws = rw;
@@ -127,7 +129,7 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
     t->cfg = *cfg;
     t->ws_base = (char *)workspace_dev;
     t->ws_bytes = workspace_bytes;
-    carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp);
+    carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp, &t->tc_status);
     SsbDims &d = t->dims;
     d.S = cfg->max_tracks; d.N = cfg->max_dets; d.B = cfg->nn_budget; d.D = cfg->feat_dim;
     d.n_init = cfg->n_init; d.max_age = cfg->max_age;

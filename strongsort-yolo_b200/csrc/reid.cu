@@ -390,29 +390,100 @@ static int launch_pw(const float *in, int P, int cin, int cout, const float *w, 
     return -1;
 }
 
+// first weight-tensor index of OSBlock b in the canonical walk
+static int block_tensor_index(int b) {
+    int k = 2;
+    for (int i = 0; i < b; i++) {
+        const int cin = kBlocks[i][0], cout = kBlocks[i][1];
+        k += 2 + 30 + 4 + 2 + (cin != cout ? 2 : 0) + ((i == 1 || i == 3) ? 2 : 0);
+    }
+    return k;
+}
+
+struct ReidBufs { float *DS, *X1, *T0, *T1, *PW, *X2, *GATE; };
+
+static ReidBufs reid_bufs(ssb_tracker *t, int n, float **A, float **Bf) {
+    float *ws = t->reid_ws;
+    const size_t N = (size_t)n;
+    ReidBufs r;
+    *A = ws;      ws += N * REID_BIG;
+    *Bf = ws;     ws += N * REID_BIG;
+    r.DS = ws;    ws += N * REID_BIG;
+    r.X1 = ws;    ws += N * REID_MID;
+    r.T0 = ws;    ws += N * REID_MID;
+    r.T1 = ws;    ws += N * REID_MID;
+    r.PW = ws;    ws += N * REID_MID;
+    r.X2 = ws;    ws += N * REID_MID;
+    r.GATE = ws;
+    return r;
+}
+
+// one OSBlock, fp32 SIMT kernels: cur [n][Hc][Wc][cin] -> nxt [n][Hc][Wc][cout]
+static int reid_block_simt(ssb_tracker *t, int b, const float *cur, float *nxt, int n, int Hc, int Wc,
+                           const ReidBufs &B, cudaStream_t st) {
+    const float *W = t->w_blob;
+    const int64_t *off = t->w_off;
+    int wi = block_tensor_index(b);
+    auto nextw = [&]() { return W + off[wi++]; };
+    const int cin = kBlocks[b][0], cout = kBlocks[b][1], mid = cout / 4;
+    const int r = mid / 16 > 0 ? mid / 16 : 1;
+    const int px = Hc * Wc, P = n * px;
+    int rc;
+    const float *c1w = nextw(), *c1b = nextw();
+    rc = launch_pw(cur, P, cin, mid, c1w, c1b, nullptr, B.X1, 1, st);
+    if (rc) return rc;
+    const float *lw[10][3];
+    for (int l = 0; l < 10; l++) { lw[l][0] = nextw(); lw[l][1] = nextw(); lw[l][2] = nextw(); }
+    const float *g1w = nextw(), *g1b = nextw(), *g2w = nextw(), *g2b = nextw();
+    const float *c3w = nextw(), *c3b = nextw();
+    const float *dw_ = nullptr, *db_ = nullptr;
+    if (cin != cout) { dw_ = nextw(); db_ = nextw(); }
+    int l = 0;
+    const int ew_blocks = (int)(((size_t)P * (mid / 4) + 255) / 256);
+    for (int s = 0; s < 4; s++) {
+        const float *src = B.X1;
+        float *dst = B.T0;
+        for (int k = 0; k <= s; k++, l++) {
+            rc = launch_pw(src, P, mid, mid, lw[l][0], nullptr, nullptr, B.PW, 0, st);
+            if (rc) return rc;
+            dw3x3_kernel<<<ew_blocks, 256, 0, st>>>(B.PW, n, Hc, Wc, mid, lw[l][1], lw[l][2], dst);
+            SSB_CHECK_LAUNCH();
+            src = dst;
+            dst = (dst == B.T0) ? B.T1 : B.T0;
+        }
+        gap_gate_kernel<<<n, 256, 0, st>>>(src, px, mid, g1w, g1b, g2w, g2b, r, B.GATE);
+        SSB_CHECK_LAUNCH();
+        gate_apply_kernel<<<ew_blocks, 256, 0, st>>>(src, B.GATE, n, px, mid, B.X2, s == 0);
+        SSB_CHECK_LAUNCH();
+    }
+    const float *resid = cur;
+    if (cin != cout) {
+        rc = launch_pw(cur, P, cin, cout, dw_, db_, nullptr, B.DS, 0, st);
+        if (rc) return rc;
+        resid = B.DS;
+    }
+    return launch_pw(B.X2, P, mid, cout, c3w, c3b, resid, nxt, 1, st);
+}
+
+static int reid_block(ssb_tracker *t, int b, const float *cur, float *nxt, int n, int Hc, int Wc,
+                      const ReidBufs &B, int use_tc, cudaStream_t st) {
+    if (use_tc) {
+        if (!t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
+        return ssb_reid_tc_block(b, cur, nxt, t->w_tc + t->w_tc_off[b], n, t->tc_status, st);
+    }
+    return reid_block_simt(t, b, cur, nxt, n, Hc, Wc, B, st);
+}
+
 int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch, const int *boxes,
                      int n, float *feats_out, cudaStream_t st) {
     if (n <= 0) return 0;
+    { int rc = reid_init_attrs(); if (rc) return rc; }
     const float *W = t->w_blob;
     const int64_t *off = t->w_off;
-    int wi = 0;
-    auto nextw = [&]() { return W + off[wi++]; };
-    float *ws = t->reid_ws;
-    const size_t N = (size_t)n;
-    float *A = ws;                       ws += N * REID_BIG;
-    float *Bf = ws;                      ws += N * REID_BIG;
-    float *DS = ws;                      ws += N * REID_BIG;
-    float *X1 = ws;                      ws += N * REID_MID;
-    float *T0 = ws;                      ws += N * REID_MID;
-    float *T1 = ws;                      ws += N * REID_MID;
-    float *PW = ws;                      ws += N * REID_MID;
-    float *X2 = ws;                      ws += N * REID_MID;
-    float *GATE = ws;                    ws += N * 1024;
-    { int rc = reid_init_attrs(); if (rc) return rc; }
-
-    // stem
-    {
-        const float *w0 = nextw(), *b0 = nextw();
+    float *A, *Bf;
+    const ReidBufs B = reid_bufs(t, n, &A, &Bf);
+    {   // stem
+        const float *w0 = W + off[0], *b0 = W + off[1];
         const size_t smem = (ST_IN_FLOATS + ST_CONV * ST_CONV * 16 + 147 * 16) * sizeof(float);
         reid_stem_kernel<<<dim3(32, n), 256, smem, st>>>(img, h, w, pitch, boxes, w0, b0, A);
         SSB_CHECK_LAUNCH();
@@ -420,49 +491,14 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
     int Hc = 64, Wc = 32;
     float *cur = A, *nxt = Bf;
     for (int b = 0; b < 6; b++) {
-        const int cin = kBlocks[b][0], cout = kBlocks[b][1], mid = cout / 4;
-        const int r = mid / 16 > 0 ? mid / 16 : 1;
-        const int px = Hc * Wc, P = n * px;
-        int rc;
-        const float *c1w = nextw(), *c1b = nextw();
-        rc = launch_pw(cur, P, cin, mid, c1w, c1b, nullptr, X1, 1, st);
-        if (rc) return rc;
-        const float *lw[10][3];
-        for (int l = 0; l < 10; l++) { lw[l][0] = nextw(); lw[l][1] = nextw(); lw[l][2] = nextw(); }
-        const float *g1w = nextw(), *g1b = nextw(), *g2w = nextw(), *g2b = nextw();
-        const float *c3w = nextw(), *c3b = nextw();
-        const float *dw_ = nullptr, *db_ = nullptr;
-        if (cin != cout) { dw_ = nextw(); db_ = nextw(); }
-        int l = 0;
-        const int ew_blocks = (int)(((size_t)P * (mid / 4) + 255) / 256);
-        for (int s = 0; s < 4; s++) {
-            const float *src = X1;
-            float *dst = T0;
-            for (int k = 0; k <= s; k++, l++) {
-                rc = launch_pw(src, P, mid, mid, lw[l][0], nullptr, nullptr, PW, 0, st);
-                if (rc) return rc;
-                dw3x3_kernel<<<ew_blocks, 256, 0, st>>>(PW, n, Hc, Wc, mid, lw[l][1], lw[l][2], dst);
-                SSB_CHECK_LAUNCH();
-                src = dst;
-                dst = (dst == T0) ? T1 : T0;
-            }
-            gap_gate_kernel<<<n, 256, 0, st>>>(src, px, mid, g1w, g1b, g2w, g2b, r, GATE);
-            SSB_CHECK_LAUNCH();
-            gate_apply_kernel<<<ew_blocks, 256, 0, st>>>(src, GATE, n, px, mid, X2, s == 0);
-            SSB_CHECK_LAUNCH();
-        }
-        const float *resid = cur;
-        if (cin != cout) {
-            rc = launch_pw(cur, P, cin, cout, dw_, db_, nullptr, DS, 0, st);
-            if (rc) return rc;
-            resid = DS;
-        }
-        rc = launch_pw(X2, P, mid, cout, c3w, c3b, resid, nxt, 1, st);
+        const int cout = kBlocks[b][1];
+        int rc = reid_block(t, b, cur, nxt, n, Hc, Wc, B, t->use_tc, st);
         if (rc) return rc;
         { float *tmp = cur; cur = nxt; nxt = tmp; }
         if (b == 1 || b == 3) {
-            const float *tw = nextw(), *tb = nextw();
-            rc = launch_pw(cur, P, cout, cout, tw, tb, nullptr, nxt, 1, st);
+            const int wi = block_tensor_index(b + 1) - 2;
+            const float *tw = W + off[wi], *tb = W + off[wi + 1];
+            rc = launch_pw(cur, n * Hc * Wc, cout, cout, tw, tb, nullptr, nxt, 1, st);
             if (rc) return rc;
             const int blocks = (int)(((size_t)n * (Hc / 2) * (Wc / 2) * (cout / 4) + 255) / 256);
             avgpool2_kernel<<<blocks, 256, 0, st>>>(nxt, n, Hc, Wc, cout, cur);
@@ -471,15 +507,65 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
         }
     }
     {
-        const float *w5 = nextw(), *b5 = nextw();
+        const int wi = block_tensor_index(6);
+        const float *w5 = W + off[wi], *b5 = W + off[wi + 1];
         int rc = launch_pw(cur, n * Hc * Wc, 128, 128, w5, b5, nullptr, nxt, 1, st);
         if (rc) return rc;
-        gap_gate_kernel<<<n, 256, 0, st>>>(nxt, Hc * Wc, 128, nullptr, nullptr, nullptr, nullptr, 0, GATE);
+        gap_gate_kernel<<<n, 256, 0, st>>>(nxt, Hc * Wc, 128, nullptr, nullptr, nullptr, nullptr, 0, B.GATE);
         SSB_CHECK_LAUNCH();
-        const float *fw = nextw(), *fb = nextw();
-        fc_kernel<<<n, 256, 0, st>>>(GATE, fw, fb, feats_out);
+        const float *fw = W + off[wi + 2], *fb = W + off[wi + 3];
+        fc_kernel<<<n, 256, 0, st>>>(B.GATE, fw, fb, feats_out);
         SSB_CHECK_LAUNCH();
+        if (wi + 4 != t->n_w) { ssb_set_error("internal: weight walk ends at %d of %d tensors", wi + 4, t->n_w); return -4; }
     }
-    if (wi != t->n_w) { ssb_set_error("internal: weight walk consumed %d of %d tensors", wi, t->n_w); return -4; }
+    return 0;
+}
+
+// ---- tensor-core weights + single-block entry point (parity tests) ------------
+extern "C" int64_t ssb_reid_tc_weight_bytes(int block) { return ssb_reid_tc_block_bytes(block); }
+
+extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
+                                       int n_blocks) {
+    if (!t || !blob_dev || !block_offsets) { ssb_set_error("null argument"); return -1; }
+    if (n_blocks != 6) { ssb_set_error("expected 6 OSBlock sections, got %d", n_blocks); return -1; }
+    for (int b = 0; b < 6; b++) {
+        if (block_offsets[b] % 128 != 0) { ssb_set_error("block %d offset not 128-byte aligned", b); return -1; }
+        if (b < 5 && block_offsets[b + 1] - block_offsets[b] < ssb_reid_tc_block_bytes(b)) {
+            ssb_set_error("block %d section too small", b);
+            return -1;
+        }
+        t->w_tc_off[b] = block_offsets[b];
+    }
+    if (((uintptr_t)blob_dev & 127) != 0) { ssb_set_error("tc blob must be 128-byte aligned"); return -1; }
+    t->w_tc = (const unsigned char *)blob_dev;
+    t->use_tc = 1;
+    return 0;
+}
+
+extern "C" int ssb_reid_use_tc(ssb_tracker *t, int enable) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    if (enable && !t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
+    t->use_tc = enable ? 1 : 0;
+    return 0;
+}
+
+// y = OSBlock_b(x): x [n][H][W][cin] float32 NHWC, y [n][H][W][cout]; use_tc picks the path.
+// status_out (device int, may be NULL) receives the tensor-core path's timeout flag.
+extern "C" int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, float *y_dev, int n,
+                              int use_tc, ssb_stream_t stream) {
+    if (!t || !x_dev || !y_dev) { ssb_set_error("null argument"); return -1; }
+    if (block < 0 || block > 5 || n < 1 || n > t->dims.N) { ssb_set_error("bad block / n"); return -1; }
+    if (!t->w_blob) { ssb_set_error("ReID weights not set"); return -1; }
+    { int rc = reid_init_attrs(); if (rc) return rc; }
+    float *A, *Bf;
+    const ReidBufs B = reid_bufs(t, n, &A, &Bf);
+    const int Hc = block < 2 ? 64 : (block < 4 ? 32 : 16), Wc = Hc / 2;
+    return reid_block(t, block, x_dev, y_dev, n, Hc, Wc, B, use_tc, (cudaStream_t)stream);
+}
+
+extern "C" int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream) {
+    if (!t || !status_host) { ssb_set_error("null argument"); return -1; }
+    SSB_CHECK_CUDA(cudaMemcpyAsync(status_host, t->tc_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+    SSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }

@@ -83,6 +83,11 @@ struct ssb_tracker {
     float *reid_ws;           // activation workspace (device)
     int64_t reid_ws_floats;
     int *boxes_tmp;           // [N][4]
+    // tensor-core OSBlocks (reid_tc.cu): hi/lo fp16 operand blob, per-block offsets
+    const unsigned char *w_tc;
+    int64_t w_tc_off[6];
+    int use_tc;               // 1: OSBlocks on tcgen05, 0: fp32 SIMT baseline
+    int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
 };
 
 void ssb_set_error(const char *fmt, ...);
@@ -114,3 +119,6 @@ int ssb_launch_appearance(const float *gallery, const int *gal_count, const int 
 int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch,
                      const int *boxes, int n, float *feats_out, cudaStream_t st);
 int64_t ssb_reid_ws_floats(int max_dets);
+int64_t ssb_reid_tc_block_bytes(int b);
+int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
+                      cudaStream_t st);

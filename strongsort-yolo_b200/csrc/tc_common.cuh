@@ -122,21 +122,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
 }
-// bounded spin so that a protocol bug cannot hang the GPU: returns false on timeout
+// bounded wait so that a protocol bug cannot hang the GPU: returns false after
+// ~0.25 s (5e8 SM cycles).  try_wait suspends the thread in hardware for at most
+// the hinted time, so this is not a hot spin.
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
-    for (uint32_t it = 0; it < (1u << 22); it++) {
+    const long long t0 = clock64();
+    while (true) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok)
-            : "r"(a), "r"(parity)
+            : "r"(a), "r"(parity), "r"(2000u)
             : "memory");
         if (ok) return true;
+        if (clock64() - t0 > 500000000LL) return false;
     }
-    return false;
 }
 
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map needed),

@@ -538,40 +538,85 @@ __global__ void lsap_kernel(const double *C, int nr, int nc, int L, size_t cost_
     lsap_block(C, nr, nc, m, cost_smem_bytes, col4row_out, row4col_out);
 }
 
+// Ordered multi-way compaction helper: every thread owns a contiguous chunk of
+// [0, n) and classifies each index into one of NCLS lists (or none, cls < 0);
+// emit(cls, position_in_that_list, index) is called in index order per list.
+template <int NCLS, typename Classify, typename Emit>
+__device__ void block_partition(int n, int *s_w, int *totals, Classify classify, Emit emit) {
+    const int per = (n + blockDim.x - 1) / blockDim.x;
+    const int b = threadIdx.x * per, e = min(n, b + per);
+    int cnt[NCLS];
+#pragma unroll
+    for (int k = 0; k < NCLS; k++) cnt[k] = 0;
+    for (int i = b; i < e; i++) {
+        const int c = classify(i);
+#pragma unroll
+        for (int k = 0; k < NCLS; k++) cnt[k] += (c == k);
+    }
+    int off[NCLS];
+#pragma unroll
+    for (int k = 0; k < NCLS; k++) off[k] = block_excl_scan(cnt[k], s_w, &totals[k]);
+    for (int i = b; i < e; i++) {
+        const int c = classify(i);
+#pragma unroll
+        for (int k = 0; k < NCLS; k++)
+            if (c == k) emit(k, off[k]++, i);
+    }
+}
+
 // Stage A: LSAP over confirmed x dets, then min_cost_matching's list building
-// and the stage-B candidate list (A.6).
+// and the stage-B candidate list (A.6), all lists by ordered block compaction.
 __global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int n, int L,
                                       size_t cost_smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_w[33];
+    __shared__ int s_nu0;
     LsapSmem m;
     lsap_carve(smem, L, m);
     const int rows = fs.cnt[FC_N_CONF], cols = n;
     lsap_block(fs.cost_a, rows, cols, m, cost_smem_bytes, fs.col4row, fs.row4col);
-    if (threadIdx.x == 0) {
-        int nu = 0;
-        for (int c = 0; c < cols; c++)
-            if (fs.row4col[c] < 0) fs.undet_a[nu++] = c;
-        int nm = 0, nb = 0, nk = 0;
-        const int n_unconf = fs.cnt[FC_N_UNCONF];
-        for (int k = 0; k < n_unconf; k++) fs.cand_b[nb++] = fs.unconf_list[k];
-        for (int r = 0; r < rows; r++) {
-            const int pos = fs.conf_list[r];
-            const int c = fs.col4row[r];
-            bool matched = false;
-            if (c >= 0) {
-                if (fs.cost_a[(size_t)r * cols + c] > d.max_dist) fs.undet_a[nu++] = c;
-                else { fs.match_trk[nm] = pos; fs.match_det[nm] = c; nm++; matched = true; }
-            }
-            if (!matched) {
-                if (tt.tsu[tt.order[pos]] == 1) fs.cand_b[nb++] = pos;
-                else fs.untrk_a_keep[nk++] = pos;
-            }
+    const int n_unconf = fs.cnt[FC_N_UNCONF];
+    // unmatched detections, part 1: unassigned columns ascending
+    {
+        int tot[1];
+        block_partition<1>(cols, s_w, tot,
+                           [&](int c) { return fs.row4col[c] < 0 ? 0 : -1; },
+                           [&](int, int pos, int c) { fs.undet_a[pos] = c; });
+        if (threadIdx.x == 0) s_nu0 = tot[0];
+    }
+    for (int k = threadIdx.x; k < n_unconf; k += blockDim.x) fs.cand_b[k] = fs.unconf_list[k];
+    __syncthreads();
+    const int nu0 = s_nu0;
+    // rows in order: 0 = match, 1 = rejected pair (cost > max_dist), then the
+    // unmatched track goes to 2 = stage-B candidate (tsu == 1) or 3 = kept unmatched
+    auto row_class = [&](int r) -> int {          // 0 match, 1 reject+cand, 2 reject+keep, 3 un+cand, 4 un+keep
+        const int c = fs.col4row[r];
+        const bool one = tt.tsu[tt.order[fs.conf_list[r]]] == 1;
+        if (c >= 0) {
+            if (fs.cost_a[(size_t)r * cols + c] > d.max_dist) return one ? 1 : 2;
+            return 0;
         }
-        fs.cnt[FC_N_UNDET_A] = nu;
-        fs.cnt[FC_N_CAND_B] = nb;
-        fs.cnt[FC_N_UNTRK_A_KEEP] = nk;
-        fs.cnt[FC_N_MATCH] = nm;
-        fs.cnt[FC_N_MATCH_A] = nm;
+        return one ? 3 : 4;
+    };
+    int tot3[3];
+    block_partition<3>(rows, s_w, tot3,
+                       [&](int r) { const int k = row_class(r); return k == 0 ? 0 : ((k == 1 || k == 3) ? 1 : 2); },
+                       [&](int cls, int pos, int r) {
+                           const int p = fs.conf_list[r];
+                           if (cls == 0) { fs.match_trk[pos] = p; fs.match_det[pos] = fs.col4row[r]; }
+                           else if (cls == 1) fs.cand_b[n_unconf + pos] = p;
+                           else fs.untrk_a_keep[pos] = p;
+                       });
+    int totr[1];
+    block_partition<1>(rows, s_w, totr,
+                       [&](int r) { const int k = row_class(r); return (k == 1 || k == 2) ? 0 : -1; },
+                       [&](int, int pos, int r) { fs.undet_a[nu0 + pos] = fs.col4row[r]; });
+    if (threadIdx.x == 0) {
+        fs.cnt[FC_N_UNDET_A] = nu0 + totr[0];
+        fs.cnt[FC_N_CAND_B] = n_unconf + tot3[1];
+        fs.cnt[FC_N_UNTRK_A_KEEP] = tot3[2];
+        fs.cnt[FC_N_MATCH] = tot3[0];
+        fs.cnt[FC_N_MATCH_A] = tot3[0];
         fs.cnt[FC_ROWS_A] = rows; fs.cnt[FC_COLS_A] = cols;
     }
 }
@@ -580,30 +625,44 @@ __global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d,
 __global__ void assign_stage_b_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int L,
                                       size_t cost_smem_bytes) {
     extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_w[33];
+    __shared__ int s_nu0;
     LsapSmem m;
     lsap_carve(smem, L, m);
     const int rows = fs.cnt[FC_N_CAND_B], cols = fs.cnt[FC_N_UNDET_A];
+    const int nm0 = fs.cnt[FC_N_MATCH], nk = fs.cnt[FC_N_UNTRK_A_KEEP];
     lsap_block(fs.cost_b, rows, cols, m, cost_smem_bytes, fs.col4row, fs.row4col);
+    for (int k = threadIdx.x; k < nk; k += blockDim.x) fs.untrk[k] = fs.untrk_a_keep[k];
+    {
+        int tot[1];
+        block_partition<1>(cols, s_w, tot,
+                           [&](int c) { return fs.row4col[c] < 0 ? 0 : -1; },
+                           [&](int, int pos, int c) { fs.undet[pos] = fs.undet_a[c]; });
+        if (threadIdx.x == 0) s_nu0 = tot[0];
+    }
+    __syncthreads();
+    const int nu0 = s_nu0;
+    auto row_class = [&](int r) -> int {          // 0 match, 1 rejected pair, 2 unassigned row
+        const int c = fs.col4row[r];
+        if (c < 0) return 2;
+        return fs.cost_b[(size_t)r * cols + c] > d.max_iou ? 1 : 0;
+    };
+    int tot2[2];
+    block_partition<2>(rows, s_w, tot2,
+                       [&](int r) { return row_class(r) == 0 ? 0 : 1; },
+                       [&](int cls, int pos, int r) {
+                           const int p = fs.cand_b[r];
+                           if (cls == 0) { fs.match_trk[nm0 + pos] = p; fs.match_det[nm0 + pos] = fs.undet_a[fs.col4row[r]]; }
+                           else fs.untrk[nk + pos] = p;
+                       });
+    int totr[1];
+    block_partition<1>(rows, s_w, totr,
+                       [&](int r) { return row_class(r) == 1 ? 0 : -1; },
+                       [&](int, int pos, int r) { fs.undet[nu0 + pos] = fs.undet_a[fs.col4row[r]]; });
     if (threadIdx.x == 0) {
-        int nm = fs.cnt[FC_N_MATCH], nu = 0, nt = 0;
-        const int nk = fs.cnt[FC_N_UNTRK_A_KEEP];
-        for (int k = 0; k < nk; k++) fs.untrk[nt++] = fs.untrk_a_keep[k];
-        for (int c = 0; c < cols; c++)
-            if (fs.row4col[c] < 0) fs.undet[nu++] = fs.undet_a[c];
-        for (int r = 0; r < rows; r++) {
-            const int pos = fs.cand_b[r];
-            const int c = fs.col4row[r];
-            if (c < 0) { fs.untrk[nt++] = pos; continue; }
-            if (fs.cost_b[(size_t)r * cols + c] > d.max_iou) {
-                fs.untrk[nt++] = pos;
-                fs.undet[nu++] = fs.undet_a[c];
-            } else {
-                fs.match_trk[nm] = pos; fs.match_det[nm] = fs.undet_a[c]; nm++;
-            }
-        }
-        fs.cnt[FC_N_MATCH] = nm;
-        fs.cnt[FC_N_UNTRK] = nt;
-        fs.cnt[FC_N_UNDET] = nu;
+        fs.cnt[FC_N_MATCH] = nm0 + tot2[0];
+        fs.cnt[FC_N_UNTRK] = nk + tot2[1];
+        fs.cnt[FC_N_UNDET] = nu0 + totr[0];
         fs.cnt[FC_ROWS_B] = rows; fs.cnt[FC_COLS_B] = cols;
     }
 }

@@ -28,7 +28,7 @@ class StrongSORT:
     def __init__(self, model_weights=None, device="cuda:0", fp16=False,
                  max_dist=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
                  nn_budget=100, mc_lambda=0.995, ema_alpha=0.9,
-                 max_tracks=1024, max_dets=512):
+                 max_tracks=1024, max_dets=512, reid_backend="tc"):
         torch = _lib.require_cuda()
         self._torch = torch
         self._lib = _lib.load()
@@ -62,6 +62,13 @@ class StrongSORT:
             _lib.check(self._lib.ssb_reid_set_weights(self._h, _lib.ptr(self._w_blob),
                                                       self._w_sizes, len(sizes)),
                        "ssb_reid_set_weights")
+            # tensor-core OSBlocks: fp16 hi/lo operand blob (csrc/reid_tc.cu)
+            tc_blob, tc_off = _weights.pack_tc(_weights.fold(sd))
+            self._w_tc = torch.from_numpy(tc_blob).to(self.device)
+            self._w_tc_off = (C.c_int64 * 6)(*[int(o) for o in tc_off])
+            _lib.check(self._lib.ssb_reid_set_weights_tc(self._h, _lib.ptr(self._w_tc),
+                                                         self._w_tc_off, 6), "ssb_reid_set_weights_tc")
+            self.set_reid_backend(reid_backend)
             # staging
             S, N = cfg.max_tracks, cfg.max_dets
             self._dets_pin = torch.empty((N, 6), dtype=torch.float32).pin_memory()
@@ -88,6 +95,34 @@ class StrongSORT:
                 self._h = None
         except Exception:
             pass
+
+    def set_reid_backend(self, name):
+        """'tc': OSBlocks on the tcgen05 tensor cores; 'simt': fp32 CUDA-core baseline."""
+        if name not in ("tc", "simt"):
+            raise ValueError("reid_backend must be 'tc' or 'simt'")
+        _lib.check(self._lib.ssb_reid_use_tc(self._h, 1 if name == "tc" else 0), "ssb_reid_use_tc")
+        self.reid_backend = name
+
+    def reid_tc_status(self):
+        """0 when no tensor-core barrier wait ever timed out."""
+        v = C.c_int32(0)
+        _lib.check(self._lib.ssb_reid_tc_status(self._h, C.byref(v), C.c_void_p(self.stream.cuda_stream)),
+                   "ssb_reid_tc_status")
+        return int(v.value)
+
+    def reid_block(self, block, x, use_tc):
+        """One OSBlock on a float32 NHWC array [n,H,W,cin] (parity tests)."""
+        torch = self._torch
+        couts = [64, 64, 96, 96, 128, 128]
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            xd = torch.as_tensor(np.ascontiguousarray(x, dtype=np.float32)).to(self.device)
+            n, H, W, _ = xd.shape
+            yd = torch.zeros((n, H, W, couts[block]), dtype=torch.float32, device=self.device)
+            _lib.check(self._lib.ssb_reid_block(self._h, int(block), _lib.ptr(xd), _lib.ptr(yd), int(n),
+                                                1 if use_tc else 0, C.c_void_p(self.stream.cuda_stream)),
+                       "ssb_reid_block")
+        self.stream.synchronize()
+        return yd.cpu().numpy()
 
     def reset(self):
         """Forget all tracks (ids restart at 1)."""

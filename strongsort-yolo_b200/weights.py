@@ -110,3 +110,79 @@ def pack(tensors):
         blob[off:off + a.size] = a.reshape(-1)
         off += int(p)
     return blob, sizes
+
+
+# ---------------------------------------------------------------------------
+# tensor-core operand blob (csrc/reid_tc.cu: BlkCfg / Par)
+# ---------------------------------------------------------------------------
+#            CIN MID MIDP COUT DOWN
+TC_BLOCKS = [(16, 16, 16, 64, True), (64, 16, 16, 64, False), (64, 24, 32, 96, True),
+             (96, 24, 32, 96, False), (96, 32, 32, 128, True), (128, 32, 32, 128, False)]
+_STAGE = ["conv2.0", "conv2.1", "conv3.0", "conv3.1", "conv4.0", "conv4.1"]
+_LC = ["conv2a", "conv2b.0", "conv2b.1", "conv2c.0", "conv2c.1", "conv2c.2",
+       "conv2d.0", "conv2d.1", "conv2d.2", "conv2d.3"]
+
+
+def _hi_lo(a64):
+    """fp32 value -> (hi, lo) fp16 pair, hi + lo == fp32(a) to ~2^-22."""
+    a32 = np.asarray(a64, dtype=np.float32)
+    hi = a32.astype(np.float16)
+    lo = (a32 - hi.astype(np.float32)).astype(np.float16)
+    return hi, lo
+
+
+def _b_layout(w_kn):
+    """B operand, K-major no-swizzle: W[k][n] -> bytes of [k/8][n][8] hi then lo."""
+    K, N = w_kn.shape
+    assert K % 8 == 0
+    t = np.ascontiguousarray(w_kn.reshape(K // 8, 8, N).transpose(0, 2, 1))   # [kc][n][8]
+    hi, lo = _hi_lo(t)
+    return hi.tobytes() + lo.tobytes()
+
+
+def _pad128(b):
+    return b + b"\0" * ((-len(b)) % 128)
+
+
+def pack_tc(tensors):
+    """tensors: output of fold().  -> (uint8 blob, int64 offsets[6])."""
+    T = dict(tensors)
+    blob, offs = b"", []
+    for bi, (cin, mid, midp, cout, down) in enumerate(TC_BLOCKS):
+        p = _STAGE[bi]
+        sec = b""
+        w = np.zeros((cin, midp)); w[:, :mid] = T[f"{p}.conv1.w"]
+        sec += _b_layout(w)                                                    # C1W
+        if down:
+            sec += _b_layout(T[f"{p}.down.w"].astype(np.float64))              # DNW [cin][cout]
+        for nm in _LC:                                                         # LCW x 10
+            q = f"{p}.{nm}"
+            pw = T[q + ".pw"].astype(np.float64)                               # [ci][c]
+            dw = T[q + ".dw"].astype(np.float64)                               # [tap][c]
+            wd = np.zeros((9, midp, midp))                                     # [tap][ci][c]
+            wd[:, :mid, :mid] = dw[:, None, :] * pw[None, :, :]
+            sec += _b_layout(wd.reshape(9 * midp, midp))
+        par = np.zeros(midp + 10 * midp + cout + 2 * midp + 2 + 2 * midp + midp, dtype=np.float32)
+        o = 0
+        par[o:o + mid] = T[f"{p}.conv1.b"]; o += midp
+        for nm in _LC:
+            par[o:o + mid] = T[f"{p}.{nm}.b"]; o += midp
+        b3 = T[f"{p}.conv3.b"].astype(np.float64)
+        if down:
+            b3 = b3 + T[f"{p}.down.b"].astype(np.float64)
+        par[o:o + cout] = b3; o += cout
+        g1 = T[f"{p}.gate.fc1.w"]                                              # [mid][r]
+        r = g1.shape[1]
+        gw1 = np.zeros((midp, 2), dtype=np.float32); gw1[:mid, :r] = g1
+        par[o:o + 2 * midp] = gw1.reshape(-1); o += 2 * midp
+        par[o:o + r] = T[f"{p}.gate.fc1.b"]; o += 2
+        gw2 = np.zeros((2, midp), dtype=np.float32); gw2[:r, :mid] = T[f"{p}.gate.fc2.w"]
+        par[o:o + 2 * midp] = gw2.reshape(-1); o += 2 * midp
+        par[o:o + mid] = T[f"{p}.gate.fc2.b"]; o += midp
+        assert o == par.size
+        sec = sec + _pad128(par.tobytes())
+        w3 = np.zeros((midp, cout), dtype=np.float32); w3[:mid] = T[f"{p}.conv3.w"]
+        sec += w3.tobytes()
+        offs.append(len(blob))
+        blob += _pad128(sec)
+    return np.frombuffer(blob, dtype=np.uint8).copy(), np.asarray(offs, dtype=np.int64)

@@ -1,0 +1,139 @@
+"""NumPy emulation of csrc/reid_tc.cu's index arithmetic (band split, padded
+linear pixel maps, 9 shifted GEMMs, zero-ring masks, gate-scaled conv3, hi/lo
+operands) driven by the SAME packed blob the kernel reads (weights.pack_tc).
+It pins the host-side packing and every offset formula on the CPU; only the
+PTX-level behaviour is left to the GPU tests."""
+import numpy as np
+
+from strongsort_yolo_b200 import weights
+
+
+class Cfg:
+    def __init__(self, b):
+        cin, mid, midp, cout, down = weights.TC_BLOCKS[b]
+        geo = [(64, 32, 16, 4, 4), (64, 32, 16, 4, 4), (32, 16, 8, 4, 4), (32, 16, 8, 4, 4),
+               (16, 8, 16, 0, 1), (16, 8, 16, 0, 1)][b]
+        self.CIN, self.MID, self.MIDP, self.COUT, self.DOWN = cin, mid, midp, cout, down
+        self.H, self.W, self.R, self.HALO, self.NB = geo
+        self.RH = self.R + 2 * self.HALO
+        self.WP = self.W + 2
+        self.NPX = (self.RH + 2) * self.WP
+        self.NT = (self.NPX + 127) // 128
+        self.GUARD = self.WP + 2
+        self.MAP_PX = self.GUARD + self.NT * 128 + self.GUARD
+        self.MCH = midp // 8
+        self.IN_P0 = (1 + self.HALO) * self.WP
+        self.IN_P1 = (1 + self.HALO + self.R) * self.WP
+        self.IT0 = self.IN_P0 // 128
+        self.IT1 = (self.IN_P1 + 127) // 128
+        self.NIT = self.IT1 - self.IT0
+        self.LCW_B = 2 * 9 * midp * midp * 2
+        self.C1W_B = 2 * cin * midp * 2
+        self.DNW_B = 2 * cin * cout * 2 if down else 0
+        self.NPAR = midp + 10 * midp + cout + 2 * midp + 2 + 2 * midp + midp
+        self.G_LCW = self.C1W_B + self.DNW_B
+        self.G_PAR = self.G_LCW + 10 * self.LCW_B
+        self.G_W3 = self.G_PAR + ((self.NPAR * 4 + 127) // 128) * 128
+
+
+def _b_operand(raw, K, N):
+    """bytes of [K/8][N][8] hi then lo -> float64 W[k][n] (hi + lo)."""
+    half = K * N * 2
+    hi = np.frombuffer(raw[:half], dtype=np.float16).reshape(K // 8, N, 8).astype(np.float64)
+    lo = np.frombuffer(raw[half:2 * half], dtype=np.float16).reshape(K // 8, N, 8).astype(np.float64)
+    return (hi + lo).transpose(0, 2, 1).reshape(K, N)
+
+
+def _hl(v):
+    """operand rounding: fp32 -> fp16 hi + fp16 lo (as float64)."""
+    v32 = np.asarray(v, dtype=np.float32)
+    hi = v32.astype(np.float16)
+    lo = (v32 - hi.astype(np.float32)).astype(np.float16)
+    return hi.astype(np.float64) + lo.astype(np.float64)
+
+
+def osblock_emul(b, x, blob, offs):
+    """x: float32 [n,H,W,cin] -> float32 [n,H,W,cout], band by band like the kernel."""
+    c = Cfg(b)
+    sec = bytes(blob[int(offs[b]):int(offs[b + 1]) if b < 5 else len(blob)])
+    W1 = _b_operand(sec[0:c.C1W_B], c.CIN, c.MIDP)
+    WD = _b_operand(sec[c.C1W_B:c.C1W_B + c.DNW_B], c.CIN, c.COUT) if c.DOWN else None
+    LCW = [_b_operand(sec[c.G_LCW + l * c.LCW_B:c.G_LCW + (l + 1) * c.LCW_B], 9 * c.MIDP, c.MIDP)
+           for l in range(10)]
+    par = np.frombuffer(sec[c.G_PAR:c.G_PAR + c.NPAR * 4], dtype=np.float32).astype(np.float64)
+    o = 0
+    b1 = par[o:o + c.MIDP]; o += c.MIDP
+    blc = par[o:o + 10 * c.MIDP].reshape(10, c.MIDP); o += 10 * c.MIDP
+    b3 = par[o:o + c.COUT]; o += c.COUT
+    gw1 = par[o:o + 2 * c.MIDP].reshape(c.MIDP, 2); o += 2 * c.MIDP
+    gb1 = par[o:o + 2]; o += 2
+    gw2 = par[o:o + 2 * c.MIDP].reshape(2, c.MIDP); o += 2 * c.MIDP
+    gb2 = par[o:o + c.MIDP]; o += c.MIDP
+    W3 = np.frombuffer(sec[c.G_W3:c.G_W3 + c.MIDP * c.COUT * 4], dtype=np.float32).reshape(c.MIDP, c.COUT).astype(np.float64)
+
+    n = x.shape[0]
+    y = np.zeros((n, c.H, c.W, c.COUT), dtype=np.float32)
+    P = np.arange(c.NT * 128)
+    LR, LC_ = P // c.WP, P % c.WP
+    for crop in range(n):
+        bands = []
+        for band in range(c.NB):
+            row0 = band * c.R - c.HALO
+            GR, GC = row0 + LR - 1, LC_ - 1
+            valid = (P < c.NPX) & (LC_ >= 1) & (LC_ <= c.W) & (LR >= 1) & (LR <= c.RH) & (GR >= 0) & (GR < c.H)
+            own = valid & (LR >= 1 + c.HALO) & (LR < 1 + c.HALO + c.R)
+            xt = np.zeros((c.NT * 128, c.CIN))
+            xt[valid] = x[crop, GR[valid], GC[valid]]
+            xt = _hl(xt)                                            # staged operand tiles
+            acc1 = xt @ W1                                          # conv1, every band tile
+            accd = (xt @ WD) if c.DOWN else None                    # downsample (inner tiles used)
+
+            def to_map(acc, bias):
+                f = np.where(valid[:, None], np.maximum(acc + bias, 0.0), 0.0).astype(np.float32)
+                m = np.full((c.MAP_PX, c.MIDP), np.nan)             # guards: garbage
+                m[c.GUARD:c.GUARD + c.NT * 128] = _hl(f)
+                return m, f
+
+            X1, _ = to_map(acc1, b1)
+            bands.append(dict(valid=valid, own=own, GR=GR, GC=GC, X1=X1, accd=accd, streams=[]))
+        # streams: all bands of the crop advance together (cluster)
+        c3 = [np.zeros((c.NT * 128, c.COUT)) + (bd["accd"] if c.DOWN else 0.0) for bd in bands]
+        lc = 0
+        for s in range(4):
+            srcs = [bd["X1"] for bd in bands]
+            fs = None
+            for k in range(s + 1):
+                new_srcs, fs = [], []
+                for bd, src in zip(bands, srcs):
+                    acc = np.zeros((c.NT * 128, c.MIDP))
+                    for tap in range(9):
+                        off = (tap // 3 - 1) * c.WP + (tap % 3 - 1)
+                        a = src[c.GUARD + off:c.GUARD + off + c.NT * 128]
+                        a = np.where(np.isnan(a), 1e30, a)          # guard garbage must never matter
+                        acc += a @ LCW[lc][tap * c.MIDP:(tap + 1) * c.MIDP]
+                    valid = bd["valid"]
+                    f = np.where(valid[:, None], np.maximum(acc + blc[lc], 0.0), 0.0).astype(np.float32)
+                    m = np.full((c.MAP_PX, c.MIDP), np.nan)
+                    m[c.GUARD:c.GUARD + c.NT * 128] = _hl(f)
+                    new_srcs.append(m); fs.append(f)
+                srcs = new_srcs
+                lc += 1
+            tot = sum(f[bd["own"]].astype(np.float64).sum(0) for f, bd in zip(fs, bands))
+            mean = tot / (c.H * c.W)
+            h = np.maximum(gb1 + mean @ gw1, 0.0)
+            g = 1.0 / (1.0 + np.exp(-(gb2 + h @ gw2)))
+            W3g = _hl(W3 * g[:, None])
+            for i, (bd, m) in enumerate(zip(bands, srcs)):
+                a = m[c.GUARD:c.GUARD + c.NT * 128]
+                a = np.where(np.isnan(a), 0.0, a)
+                c3[i] += a @ W3g
+        for bd, acc in zip(bands, c3):
+            own = bd["own"].copy()
+            own[:c.IT0 * 128] = False
+            own[c.IT1 * 128:] = False
+            assert own.sum() == bd["own"].sum(), "inner tiles do not cover the band's own pixels"
+            out = acc[own] + b3
+            if not c.DOWN:
+                out = out + x[crop, bd["GR"][own], bd["GC"][own]]
+            y[crop, bd["GR"][own], bd["GC"][own]] = np.maximum(out, 0.0)
+    return y

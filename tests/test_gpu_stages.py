@@ -174,10 +174,11 @@ def test_lsap_empty_and_nan(lib):
     assert (c4r.cpu().numpy() == -1).all()
 
 
-def test_reid_embeddings_kat(golden_dir):
+@pytest.mark.parametrize("backend", ["tc", "simt"])
+def test_reid_embeddings_kat(golden_dir, backend):
     from strongsort_yolo_b200.strong_sort import StrongSORT
     g = np.load(os.path.join(golden_dir, "reid_kat.npz"))
-    trk = StrongSORT(max_tracks=64, max_dets=64)
+    trk = StrongSORT(max_tracks=64, max_dets=64, reid_backend=backend)
     emb = trk.extract_features(g["img"], g["boxes"])
     ref = g["emb"]
     scale = np.abs(ref).max(axis=1, keepdims=True)
