@@ -82,11 +82,11 @@ int ssb_reid_tensor_sizes(int64_t *sizes);
 int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const int64_t *sizes, int n);
 
 /* tensor-core OSBlocks (csrc/reid_tc.cu): fp16 hi/lo operand blob built by
- * weights.pack_tc(); block_offsets[6] are byte offsets of the per-block sections
- * (each >= ssb_reid_tc_weight_bytes(b), 128-byte aligned).  Setting them switches
+ * weights.pack_tc(); block_offsets[10] are byte offsets of the sections (6 OSBlocks,
+ * 2 transition layers, tail, stem; each >= ssb_reid_tc_weight_bytes(i), 128-byte aligned).  Setting them switches
  * the OSBlocks of ssb_reid/ssb_update to the tcgen05 path; ssb_reid_use_tc(t,0)
  * switches back to the fp32 SIMT baseline. */
-int64_t ssb_reid_tc_weight_bytes(int block);
+int64_t ssb_reid_tc_weight_bytes(int section);
 int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
                             int n_blocks);
 int ssb_reid_use_tc(ssb_tracker *t, int enable);

@@ -482,7 +482,10 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
     const int64_t *off = t->w_off;
     float *A, *Bf;
     const ReidBufs B = reid_bufs(t, n, &A, &Bf);
-    {   // stem
+    if (t->use_tc) {        // stem as 16 shifted GEMMs on the space-to-depth image (reid_tc.cu)
+        int rc = ssb_reid_tc_stem(img, h, w, pitch, boxes, t->w_tc + t->w_tc_off[9], A, n, t->tc_status, st);
+        if (rc) return rc;
+    } else {
         const float *w0 = W + off[0], *b0 = W + off[1];
         const size_t smem = (ST_IN_FLOATS + ST_CONV * ST_CONV * 16 + 147 * 16) * sizeof(float);
         reid_stem_kernel<<<dim3(32, n), 256, smem, st>>>(img, h, w, pitch, boxes, w0, b0, A);
@@ -495,7 +498,13 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
         int rc = reid_block(t, b, cur, nxt, n, Hc, Wc, B, t->use_tc, st);
         if (rc) return rc;
         { float *tmp = cur; cur = nxt; nxt = tmp; }
-        if (b == 1 || b == 3) {
+        if ((b == 1 || b == 3) && t->use_tc) {      // transition conv + ReLU + avgpool, one tcgen05 kernel
+            const int a = b == 1 ? 0 : 1;
+            rc = ssb_reid_tc_aux(a, cur, nxt, t->w_tc + t->w_tc_off[6 + a], n, t->tc_status, st);
+            if (rc) return rc;
+            { float *tmp = cur; cur = nxt; nxt = tmp; }
+            Hc /= 2; Wc /= 2;
+        } else if (b == 1 || b == 3) {
             const int wi = block_tensor_index(b + 1) - 2;
             const float *tw = W + off[wi], *tb = W + off[wi + 1];
             rc = launch_pw(cur, n * Hc * Wc, cout, cout, tw, tb, nullptr, nxt, 1, st);
@@ -506,7 +515,10 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
             Hc /= 2; Wc /= 2;
         }
     }
-    {
+    if (t->use_tc) {        // conv5 + GAP + fc in one tcgen05 kernel
+        int rc = ssb_reid_tc_aux(2, cur, feats_out, t->w_tc + t->w_tc_off[8], n, t->tc_status, st);
+        if (rc) return rc;
+    } else {
         const int wi = block_tensor_index(6);
         const float *w5 = W + off[wi], *b5 = W + off[wi + 1];
         int rc = launch_pw(cur, n * Hc * Wc, 128, 128, w5, b5, nullptr, nxt, 1, st);
@@ -522,16 +534,19 @@ int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch
 }
 
 // ---- tensor-core weights + single-block entry point (parity tests) ------------
-extern "C" int64_t ssb_reid_tc_weight_bytes(int block) { return ssb_reid_tc_block_bytes(block); }
+extern "C" int64_t ssb_reid_tc_weight_bytes(int section) {
+    return section < 6 ? ssb_reid_tc_block_bytes(section) : ssb_reid_tc_aux_bytes(section - 6);
+}
 
 extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
                                        int n_blocks) {
     if (!t || !blob_dev || !block_offsets) { ssb_set_error("null argument"); return -1; }
-    if (n_blocks != 6) { ssb_set_error("expected 6 OSBlock sections, got %d", n_blocks); return -1; }
-    for (int b = 0; b < 6; b++) {
-        if (block_offsets[b] % 128 != 0) { ssb_set_error("block %d offset not 128-byte aligned", b); return -1; }
-        if (b < 5 && block_offsets[b + 1] - block_offsets[b] < ssb_reid_tc_block_bytes(b)) {
-            ssb_set_error("block %d section too small", b);
+    if (n_blocks != 10) { ssb_set_error("expected 10 sections (6 OSBlocks, 2 transitions, tail, stem), got %d", n_blocks); return -1; }
+    for (int b = 0; b < 10; b++) {
+        if (block_offsets[b] % 128 != 0) { ssb_set_error("section %d offset not 128-byte aligned", b); return -1; }
+        const int64_t need = b < 6 ? ssb_reid_tc_block_bytes(b) : ssb_reid_tc_aux_bytes(b - 6);
+        if (b < 9 && block_offsets[b + 1] - block_offsets[b] < need) {
+            ssb_set_error("section %d too small", b);
             return -1;
         }
         t->w_tc_off[b] = block_offsets[b];

@@ -72,7 +72,8 @@ struct BlkCfg {
     static constexpr int OFF_PAR = OFF_C3 + C3W_B;        // fp32 biases + gate params
     static constexpr int OFF_GAP = OFF_PAR + ((NPAR * 4 + 127) / 128) * 128;   // [4][MIDP] floats
     static constexpr int OFF_MISC = OFF_GAP + 4 * MIDP * 4;
-    static constexpr int SMEM_B = OFF_MISC + 1024;
+    static constexpr int SMEM_B = OFF_MISC + 128 + 18 * 32 * 4 + 64;
+    static_assert(NT <= 8, "per-tile barriers");
     static_assert(NSTAGE * STG_B <= 2 * MAP_B, "x staging must fit in the P+Q maps");
     static_assert(TM_COLS <= 512, "TMEM columns");
     static_assert(SMEM_B <= 232448, "shared memory");
@@ -102,8 +103,31 @@ __device__ __forceinline__ void split_hl(float v, __half &h, __half &l) {
     l = __float2half_rn(v - __half2float(h));
 }
 
+// CTA shape of the OSBlock kernel: 16 warps.  Warp w may touch TMEM lanes
+// 32*(w%4)..+31 only, so the 4 warps sharing a lane quadrant split the M tiles
+// (group g = w/4 takes tiles g, g+4, ...).  More resident warps is what hides
+// the ALU/LDTM latency of the epilogues: with 4 warps (one per scheduler) 45 %
+// of the time was dependent-issue stall.
+constexpr int OSB_THREADS = 512;
+constexpr int OSB_GROUPS = OSB_THREADS / 128;
+
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
+
+// The MMA-issuing thread is the critical path (ncu: tensor pipe 8 % busy while every
+// other warp waits on the commit barrier), so descriptors are built ONCE per operand
+// and advanced by adding the offset in 16-byte units to the low word -- the start
+// address field is the low 14 bits and never carries out for valid shared addresses.
+__device__ __forceinline__ uint64_t desc_adv(uint64_t base, int units16) {
+    return base + (uint64_t)(int64_t)units16;
+}
+// one hi/lo product: D (+)= Ah*Bh + Al*Bh + Ah*Bl
+__device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl,
+                                     uint32_t idesc, uint32_t acc) {
+    tc::mma_f16_ss(d, ah, bh, idesc, acc);
+    tc::mma_f16_ss(d, al, bh, idesc, 1);
+    tc::mma_f16_ss(d, ah, bl, idesc, 1);
+}
 
 struct Pipe {           // one mbarrier, bulk-synchronous use: every thread waits every commit
     uint64_t *bar;
@@ -116,13 +140,14 @@ struct Pipe {           // one mbarrier, bulk-synchronous use: every thread wait
 };
 
 template <class C>
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(OSB_THREADS, 1)
 osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                   const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using P = Par<C>;
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, grp = warp >> 2;          // TMEM lane quadrant / tile group
     const int crop = blockIdx.x / C::NB, band = blockIdx.x % C::NB;
     const int row0 = band * C::R - C::HALO;            // image row of local row lr = 1
 
@@ -133,9 +158,11 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     uint64_t *bar_mma = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);
     uint64_t *bar_w = bar_mma + 1;
     uint64_t *bar_stg = bar_mma + 2;                   // [2] one per x-staging buffer
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_mma + 4);
-    float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 64);    // [4][MIDP] warp partials
-    float *s_mean = s_scr + 4 * C::MIDP;                                  // [MIDP]
+    uint64_t *bar_tile = bar_mma + 4;                  // [8] per M tile of the current 3x3 layer
+    uint64_t *bar_c3 = bar_mma + 12;                   // conv3 accumulation of the current stream
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_mma + 13);
+    float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 128);   // [16][MIDP] warp partials
+    float *s_mean = s_scr + 16 * C::MIDP;                                 // [MIDP]
     float *s_gate = s_mean + C::MIDP;                                     // [MIDP]
 
     if (warp == 0) tc::tmem_alloc(s_tmem, 512);
@@ -144,9 +171,11 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         tc::mbar_init(bar_w, 1);
         tc::mbar_init(bar_stg, 1);
         tc::mbar_init(bar_stg + 1, 1);
+        for (int i = 0; i < 8; i++) tc::mbar_init(bar_tile + i, 1);
+        tc::mbar_init(bar_c3, C::NIT < 4 ? C::NIT : 4);
         tc::fence_mbar_init();
     }
-    for (int i = tid; i < C::NPAR; i += 128)
+    for (int i = tid; i < C::NPAR; i += OSB_THREADS)
         sPar[i] = reinterpret_cast<const float *>(wblob + C::G_PAR)[i];
     tc::fence_before_sync();
     __syncthreads();
@@ -188,7 +217,8 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         }
         // stage tile t of x: [CIN/8][128][8] hi, then lo
         constexpr int F4 = C::CIN / 4;
-        for (int idx = tid; idx < 128 * F4; idx += 128) {
+#pragma unroll 4
+        for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
             const int px = idx / F4, f4 = idx - px * F4;
             int gr, gc;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -207,32 +237,23 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         __syncthreads();
         tc::fence_after_sync();
         if (tid == 0) {
-            const uint32_t a_hi = tc::smem_u32(stg), a_lo = a_hi + C::STG_HALF_B;
-            const uint32_t b_hi = tc::smem_u32(sW1), b_lo = b_hi + C::C1W_HALF_B;
-            constexpr uint32_t LBO_B1 = C::MIDP * 16;
-            for (int ks = 0; ks < C::CIN / 16; ks++) {
-                const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
-                const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
-                const uint64_t bh = tc::make_smem_desc(b_hi + ks * 2 * LBO_B1, LBO_B1, 128);
-                const uint64_t bl = tc::make_smem_desc(b_lo + ks * 2 * LBO_B1, LBO_B1, 128);
-                const uint32_t d = tmem + C::TM_LC + t * C::MIDP;
-                tc::mma_f16_ss(d, ah, bh, IDESC_MID, ks > 0);
-                tc::mma_f16_ss(d, al, bh, IDESC_MID, 1);
-                tc::mma_f16_ss(d, ah, bl, IDESC_MID, 1);
-            }
+            const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(stg), 2048, 128);
+            const uint64_t al0 = desc_adv(ah0, C::STG_HALF_B / 16);
+            const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), C::MIDP * 16, 128);
+            const uint64_t bl0 = desc_adv(bh0, C::C1W_HALF_B / 16);
+            const uint32_t d1 = tmem + C::TM_LC + t * C::MIDP;
+#pragma unroll
+            for (int ks = 0; ks < C::CIN / 16; ks++)
+                mma3(d1, desc_adv(ah0, ks * 256), desc_adv(al0, ks * 256), desc_adv(bh0, ks * 2 * C::MIDP),
+                     desc_adv(bl0, ks * 2 * C::MIDP), IDESC_MID, ks > 0);
             if (C::DOWN && t >= C::IT0 && t < C::IT1) {
-                const uint32_t d_hi = tc::smem_u32(sW1) + C::C1W_B, d_lo = d_hi + C::DNW_HALF_B;
-                constexpr uint32_t LBO_BD = C::COUT * 16;
-                for (int ks = 0; ks < C::CIN / 16; ks++) {
-                    const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
-                    const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
-                    const uint64_t bh = tc::make_smem_desc(d_hi + ks * 2 * LBO_BD, LBO_BD, 128);
-                    const uint64_t bl = tc::make_smem_desc(d_lo + ks * 2 * LBO_BD, LBO_BD, 128);
-                    const uint32_t d = tmem + C::TM_C3 + (t - C::IT0) * C::COUT;
-                    tc::mma_f16_ss(d, ah, bh, IDESC_OUT, ks > 0);
-                    tc::mma_f16_ss(d, al, bh, IDESC_OUT, 1);
-                    tc::mma_f16_ss(d, ah, bl, IDESC_OUT, 1);
-                }
+                const uint64_t dh0 = tc::make_smem_desc(tc::smem_u32(sW1) + C::C1W_B, C::COUT * 16, 128);
+                const uint64_t dl0 = desc_adv(dh0, C::DNW_HALF_B / 16);
+                const uint32_t d2 = tmem + C::TM_C3 + (t - C::IT0) * C::COUT;
+#pragma unroll
+                for (int ks = 0; ks < C::CIN / 16; ks++)
+                    mma3(d2, desc_adv(ah0, ks * 256), desc_adv(al0, ks * 256), desc_adv(dh0, ks * 2 * C::COUT),
+                         desc_adv(dl0, ks * 2 * C::COUT), IDESC_OUT, ks > 0);
             }
             tc::mma_commit(bar_stg + sb);
         }
@@ -250,24 +271,31 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
 
     // epilogue: TMEM tile -> (+bias, relu, zero-ring mask) -> hi/lo operand map.
     // GAPACC: also accumulate per-channel sums over the band's own inner pixels.
-    auto drain_to_map = [&](unsigned char *dst, const float *bias, auto gapacc, float *gap) {
+    // tile_bar != nullptr: tile t may be drained as soon as ITS MMAs have completed
+    // (tile_bar[t], parity tile_par), while later tiles are still on the tensor pipe.
+    auto drain_to_map = [&](unsigned char *dst, const float *bias, auto gapacc, float *gap,
+                            uint64_t *tile_bar, uint32_t tile_par) {
         constexpr bool GAPACC = decltype(gapacc)::value;
-        for (int t = 0; t < C::NT; t++) {
-            const int p = t * 128 + warp * 32 + lane;
+        for (int t = grp; t < C::NT; t += OSB_GROUPS) {
+            if (tile_bar) {
+                if (!tc::mbar_wait(tile_bar + t, tile_par)) ok = false;
+                tc::fence_after_sync();
+            }
+            const int p = t * 128 + quad * 32 + lane;
             int gr, gc;
             const bool valid = pixel_valid(p, gr, gc);
             const int lr = p / C::WP;
             const bool own = valid && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R;
             unsigned char *d_hi = dst + (C::GUARD + p) * 16, *d_lo = d_hi + C::MAP_HALF_B;
+            float v[C::MIDP];
+            tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_LC + t * C::MIDP, v);
 #pragma unroll
             for (int c0 = 0; c0 < C::MIDP; c0 += 16) {
-                float v[16];
-                tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + C::TM_LC + t * C::MIDP + c0, v);
                 __align__(16) __half h[16];
                 __align__(16) __half l[16];
 #pragma unroll
                 for (int j = 0; j < 16; j++) {
-                    const float f = valid ? fmaxf(v[j] + bias[c0 + j], 0.f) : 0.f;
+                    const float f = valid ? fmaxf(v[c0 + j] + bias[c0 + j], 0.f) : 0.f;
                     if (GAPACC) { if (own) gap[c0 + j] += f; }
                     split_hl(f, h[j], l[j]);
                 }
@@ -284,13 +312,15 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         tc::fence_after_sync();
     };
 
-    drain_to_map(sX1, sPar + P::B1, FalseT{}, nullptr);
+    drain_to_map(sX1, sPar + P::B1, FalseT{}, nullptr, nullptr, 0);
 
     // ------------------------------------------------------------------
     // phase 2: four streams of dense 3x3 convs + gated conv3 accumulation
     // ------------------------------------------------------------------
     const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);      // [MIDP][COUT]
     int lc = 0;
+    uint32_t lc_par = 0, c3_par = 0;
+    bool c3_pending = false;
     for (int s = 0; s < 4; s++) {
         const unsigned char *src = sX1;
         unsigned char *dst = sP;
@@ -298,48 +328,58 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             if (!tc::mbar_wait(bar_w, w_phase)) ok = false;       // this LightConv's weights landed
             w_phase ^= 1;
             tc::fence_after_sync();
-            if (tid == 0) {
-                const uint32_t a_hi = tc::smem_u32(src) + C::GUARD * 16, a_lo = a_hi + C::MAP_HALF_B;
-                const uint32_t b_hi = tc::smem_u32(sW1), b_lo = b_hi + C::LCW_HALF_B;
-                constexpr uint32_t LBO_B = C::MIDP * 16;
-                for (int t = 0; t < C::NT; t++) {
-                    const uint32_t d = tmem + C::TM_LC + t * C::MIDP;
-                    uint32_t acc = 0;
+            // four issuing threads (one per SM sub-partition), tile t -> warp t % 4; every
+            // tile commits to its own barrier so its drain overlaps the later tiles' MMAs
+            if (warp < 4 && lane == 0) {
+                const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(src) + C::GUARD * 16, C::PLANE_B, 128);
+                const uint64_t al0 = desc_adv(ah0, C::MAP_HALF_B / 16);
+                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), C::MIDP * 16, 128);
+                const uint64_t bl0 = desc_adv(bh0, C::LCW_HALF_B / 16);
 #pragma unroll 1
+                for (int t = warp; t < C::NT; t += 4) {
+                    const uint32_t d = tmem + C::TM_LC + t * C::MIDP;
+                    const uint64_t aht = desc_adv(ah0, t * 128), alt = desc_adv(al0, t * 128);
+#pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
-                        const int off = ((tap / 3 - 1) * C::WP + (tap % 3 - 1) + t * 128) * 16;
+                        const int po = (tap / 3 - 1) * C::WP + (tap % 3 - 1);        // pixels == 16-byte units
 #pragma unroll
                         for (int ks = 0; ks < C::MIDP / 16; ks++) {
-                            const uint32_t ka = ks * 2 * C::PLANE_B;
-                            const uint32_t kb = (tap * C::MCH + ks * 2) * LBO_B;
-                            const uint64_t ah = tc::make_smem_desc(a_hi + off + ka, C::PLANE_B, 128);
-                            const uint64_t al = tc::make_smem_desc(a_lo + off + ka, C::PLANE_B, 128);
-                            const uint64_t bh = tc::make_smem_desc(b_hi + kb, LBO_B, 128);
-                            const uint64_t bl = tc::make_smem_desc(b_lo + kb, LBO_B, 128);
-                            tc::mma_f16_ss(d, ah, bh, IDESC_MID, acc);
-                            tc::mma_f16_ss(d, al, bh, IDESC_MID, 1);
-                            tc::mma_f16_ss(d, ah, bl, IDESC_MID, 1);
-                            acc = 1;
+                            const int ka = ks * 2 * C::MAP_PX;
+                            const int kb = (tap * C::MCH + ks * 2) * C::MIDP;
+                            mma3(d, desc_adv(aht, po + ka), desc_adv(alt, po + ka), desc_adv(bh0, kb),
+                                 desc_adv(bl0, kb), IDESC_MID, (tap | ks) != 0);
                         }
                     }
+                    tc::mma_commit(bar_tile + t);
                 }
-                tc::mma_commit(bar_mma);
             }
-            mma.wait();
-            tc::fence_after_sync();
-            // the weight buffer is free again: prefetch the next LightConv's weights
-            if (tid == 0 && lc + 1 < 10) {
-                tc::mbar_arrive_expect_tx(bar_w, C::LCW_B);
-                tc::bulk_g2s(sW1, wblob + C::G_LCW + (size_t)(lc + 1) * C::LCW_B, C::LCW_B, bar_w);
+            // one otherwise lightly loaded thread waits for the whole layer and then refills
+            // the weight buffer with the next LightConv's weights
+            if (warp == 15 && lane == 0) {
+                for (int t = 0; t < C::NT; t++)
+                    if (!tc::mbar_wait(bar_tile + t, lc_par)) ok = false;
+                if (lc + 1 < 10) {
+                    tc::mbar_arrive_expect_tx(bar_w, C::LCW_B);
+                    tc::bulk_g2s(sW1, wblob + C::G_LCW + (size_t)(lc + 1) * C::LCW_B, C::LCW_B, bar_w);
+                }
+            }
+            // the previous stream's conv3 MMAs read P/Q: they must be done before this
+            // layer's drain overwrites those maps
+            if (c3_pending) {
+                if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
+                c3_par ^= 1;
+                c3_pending = false;
             }
             const bool last = (k == s);
             if (!last) {
-                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, FalseT{}, nullptr);
+                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, FalseT{}, nullptr, bar_tile, lc_par);
+                lc_par ^= 1;
             } else {
                 float gap[C::MIDP];
 #pragma unroll
                 for (int j = 0; j < C::MIDP; j++) gap[j] = 0.f;
-                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, TrueT{}, gap);
+                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, TrueT{}, gap, bar_tile, lc_par);
+                lc_par ^= 1;
                 // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid
 #pragma unroll
                 for (int j = 0; j < C::MIDP; j++) {
@@ -349,9 +389,12 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                     if (lane == 0) s_scr[warp * C::MIDP + j] = vs;
                 }
                 __syncthreads();
-                if (tid < C::MIDP)
-                    sGap[s * C::MIDP + tid] = (s_scr[tid] + s_scr[C::MIDP + tid]) +
-                                              (s_scr[2 * C::MIDP + tid] + s_scr[3 * C::MIDP + tid]);
+                if (tid < C::MIDP) {
+                    float tot = 0.f;
+#pragma unroll
+                    for (int w = 0; w < OSB_THREADS / 32; w++) tot += s_scr[w * C::MIDP + tid];
+                    sGap[s * C::MIDP + tid] = tot;
+                }
                 if (C::NB > 1) cluster.sync(); else __syncthreads();
                 if (tid < C::MIDP) {          // fixed band order: every CTA of the crop gets the same bits
                     float tot = 0.f;
@@ -378,7 +421,7 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                 }
                 __syncthreads();
                 // ---- gate-scaled conv3 weights  B[kc][co][8] = W3[k][co] * g[k]  (hi / lo)
-                for (int u = tid; u < C::COUT * C::MCH; u += 128) {
+                for (int u = tid; u < C::COUT * C::MCH; u += OSB_THREADS) {
                     const int kc = u / C::COUT, co = u - kc * C::COUT;
                     __align__(16) __half h[8];
                     __align__(16) __half l[8];
@@ -394,54 +437,55 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                 tc::fence_before_sync();
                 __syncthreads();
                 tc::fence_after_sync();
-                if (tid == 0) {
-                    const uint32_t a_hi = tc::smem_u32(dst) + C::GUARD * 16, a_lo = a_hi + C::MAP_HALF_B;
-                    const uint32_t b_hi = tc::smem_u32(sC3), b_lo = b_hi + C::C3W_HALF_B;
-                    constexpr uint32_t LBO_B3 = C::COUT * 16;
-                    for (int i = 0; i < C::NIT; i++) {
+                if (warp < 4 && warp < C::NIT && lane == 0) {
+                    const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(dst) + C::GUARD * 16, C::PLANE_B, 128);
+                    const uint64_t al0 = desc_adv(ah0, C::MAP_HALF_B / 16);
+                    const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sC3), C::COUT * 16, 128);
+                    const uint64_t bl0 = desc_adv(bh0, C::C3W_HALF_B / 16);
+                    const uint32_t acc0 = (C::DOWN || s > 0) ? 1u : 0u;
+#pragma unroll 1
+                    for (int i = warp; i < C::NIT; i += 4) {
                         const uint32_t d = tmem + C::TM_C3 + i * C::COUT;
-                        const int off = (C::IT0 + i) * 128 * 16;
 #pragma unroll
                         for (int ks = 0; ks < C::MIDP / 16; ks++) {
-                            const uint32_t ka = ks * 2 * C::PLANE_B, kb = ks * 2 * LBO_B3;
-                            const uint64_t ah = tc::make_smem_desc(a_hi + off + ka, C::PLANE_B, 128);
-                            const uint64_t al = tc::make_smem_desc(a_lo + off + ka, C::PLANE_B, 128);
-                            const uint64_t bh = tc::make_smem_desc(b_hi + kb, LBO_B3, 128);
-                            const uint64_t bl = tc::make_smem_desc(b_lo + kb, LBO_B3, 128);
-                            tc::mma_f16_ss(d, ah, bh, IDESC_OUT, (C::DOWN || s > 0 || ks > 0) ? 1 : 0);
-                            tc::mma_f16_ss(d, al, bh, IDESC_OUT, 1);
-                            tc::mma_f16_ss(d, ah, bl, IDESC_OUT, 1);
+                            const int ka = (C::IT0 + i) * 128 + ks * 2 * C::MAP_PX, kb = ks * 2 * C::COUT;
+                            mma3(d, desc_adv(ah0, ka), desc_adv(al0, ka), desc_adv(bh0, kb), desc_adv(bl0, kb),
+                                 IDESC_OUT, ks > 0 ? 1u : acc0);
                         }
                     }
-                    if (s == 3) tc::mma_commit(bar_mma);
+                    tc::mma_commit(bar_c3);
                 }
+                c3_pending = true;
             }
             src = dst;
             dst = (dst == sP) ? sQ : sP;
         }
     }
-    mma.wait();                       // the last stream's conv3 MMAs
+    if (c3_pending) {                 // the last stream's conv3 MMAs
+        if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
+        c3_par ^= 1;
+    }
     tc::fence_after_sync();
 
     // ------------------------------------------------------------------
     // final epilogue: y = relu(conv3 + bias (+ downsample already in TMEM) (+ x))
     // ------------------------------------------------------------------
     float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
-    for (int i = 0; i < C::NIT; i++) {
-        const int p = (C::IT0 + i) * 128 + warp * 32 + lane;
+    for (int i = grp; i < C::NIT; i += OSB_GROUPS) {
+        const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
         int gr, gc;
         const bool valid = pixel_valid(p, gr, gc);
         const int lr = p / C::WP;
         const bool own = valid && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R;
 #pragma unroll 1
-        for (int c0 = 0; c0 < C::COUT; c0 += 16) {
-            float v[16];
-            tc::tmem_ld16(tmem + ((uint32_t)(warp * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
+        for (int c0 = 0; c0 < C::COUT; c0 += 32) {
+            float v[32];
+            tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
             if (own) {
                 float *o = yout + ((size_t)gr * C::W + gc) * C::COUT + c0;
                 const float *xr = xin + ((size_t)gr * C::W + gc) * C::CIN + c0;
 #pragma unroll
-                for (int j = 0; j < 16; j += 4) {
+                for (int j = 0; j < 32; j += 4) {
                     float4 r;
                     r.x = v[j] + sPar[P::B3 + c0 + j];
                     r.y = v[j + 1] + sPar[P::B3 + c0 + j + 1];
@@ -485,7 +529,7 @@ int launch_block(const float *x, float *y, const unsigned char *w, int n, int *s
     }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n * C::NB);
-    cfg.blockDim = dim3(128);
+    cfg.blockDim = dim3(OSB_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_B;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -497,6 +541,450 @@ int launch_block(const float *x, float *y, const unsigned char *w, int n, int *s
     cfg.numAttrs = 1;
     SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock_tc_kernel<C>, x, y, w, n, status));
     g_ssb_launches++;
+    return 0;
+}
+
+
+// ---------------------------------------------------------------------------
+// 1x1 conv + ReLU (+ 2x2 average pool) on the tensor cores: the two transition
+// layers between the OSNet stages.  Persistent CTAs, 128-pixel M tiles, x tile
+// and TMEM accumulator double-buffered so the MMA of tile i+1 overlaps the
+// epilogue of tile i.  With POOL the 128 tile rows are 32 output pixels x their
+// 4 window positions, so the pool is a 2-step shuffle over adjacent TMEM lanes.
+// ---------------------------------------------------------------------------
+template <int CIN_, int COUT_, int H_, int W_, bool POOL_>
+struct PwCfg {
+    static constexpr int CIN = CIN_, COUT = COUT_, H = H_, W = W_;
+    static constexpr bool POOL = POOL_;
+    static constexpr int STG_HALF_B = (CIN / 8) * 128 * 16, STG_B = 2 * STG_HALF_B;
+    static constexpr int W_HALF_B = CIN * COUT * 2, W_B = 2 * W_HALF_B;
+    static constexpr int OFF_STG = 0;
+    static constexpr int OFF_W = 2 * STG_B;
+    static constexpr int OFF_BIAS = OFF_W + W_B;
+    static constexpr int OFF_MISC = OFF_BIAS + COUT * 4;
+    static constexpr int SMEM_B = OFF_MISC + 128;
+    static constexpr int G_W = 0, G_BIAS = W_B, G_TOTAL = W_B + ((COUT * 4 + 127) / 128) * 128;
+    static_assert(SMEM_B <= 232448, "shared memory");
+    static_assert(2 * COUT <= 512, "TMEM columns");
+};
+
+template <class C>
+__global__ void __launch_bounds__(OSB_THREADS, 1)
+pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
+             const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, grp = warp >> 2;
+    unsigned char *sStg = smem + C::OFF_STG, *sW = smem + C::OFF_W;
+    float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);     // [2] mma, [2]=weights
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 3);
+    constexpr int HO = C::POOL ? C::H / 2 : C::H, WO = C::POOL ? C::W / 2 : C::W;
+    constexpr int OUT_PER_TILE = C::POOL ? 32 : 128;
+    const long long total_out = (long long)n_crops * HO * WO;
+    const int ntiles = (int)((total_out + OUT_PER_TILE - 1) / OUT_PER_TILE);
+
+    if (warp == 0) tc::tmem_alloc(s_tmem, 512);
+    if (tid == 0) {
+        tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::mbar_init(bar + 2, 1);
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < C::COUT; i += OSB_THREADS) sBias[i] = reinterpret_cast<const float *>(wblob + C::G_BIAS)[i];
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(bar + 2, C::W_B);
+        tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 2);
+    }
+    bool ok = true;
+    uint32_t ph[2] = {0, 0};
+    constexpr uint32_t IDESC = tc::make_idesc_f16(128, C::COUT);
+
+    auto epilogue = [&](int tile, int buf) {
+        if (!tc::mbar_wait(bar + buf, ph[buf])) ok = false;
+        ph[buf] ^= 1;
+        tc::fence_after_sync();
+        const int m = quad * 32 + lane;
+        long long o = C::POOL ? (long long)tile * 32 + (m >> 2) : (long long)tile * 128 + m;
+        const bool wr = (o < total_out) && (!C::POOL || (m & 3) == 0);
+#pragma unroll 1
+        for (int c0 = grp * 16; c0 < C::COUT; c0 += 16 * OSB_GROUPS) {
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + buf * C::COUT + c0, v);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float f = fmaxf(v[j] + sBias[c0 + j], 0.f);
+                if (C::POOL) {
+                    f += __shfl_xor_sync(0xffffffffu, f, 1);
+                    f += __shfl_xor_sync(0xffffffffu, f, 2);
+                    f *= 0.25f;
+                }
+                v[j] = f;
+            }
+            if (wr) {
+                float *dst = y + o * C::COUT + c0;
+#pragma unroll
+                for (int j = 0; j < 16; j += 4)
+                    *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+        tc::fence_before_sync();
+    };
+
+    int it = 0, prev_tile = -1;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, it++) {
+        const int buf = it & 1;
+        unsigned char *stg = sStg + buf * C::STG_B;
+        constexpr int F4 = C::CIN / 4;
+#pragma unroll 2
+        for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
+            const int m = idx / F4, f4 = idx - m * F4;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (C::POOL) {
+                const long long o = (long long)tile * 32 + (m >> 2);
+                if (o < total_out) {
+                    const int q = m & 3;
+                    const int n = (int)(o / (HO * WO)), rem = (int)(o - (long long)n * HO * WO);
+                    const int oy = rem / WO, ox = rem - oy * WO;
+                    const int iy = 2 * oy + (q >> 1), ix = 2 * ox + (q & 1);
+                    v = *reinterpret_cast<const float4 *>(x + (((size_t)n * C::H + iy) * C::W + ix) * C::CIN + f4 * 4);
+                }
+            } else {
+                const long long o = (long long)tile * 128 + m;
+                if (o < total_out) v = *reinterpret_cast<const float4 *>(x + (size_t)o * C::CIN + f4 * 4);
+            }
+            __half h[4], l[4];
+            split_hl(v.x, h[0], l[0]); split_hl(v.y, h[1], l[1]);
+            split_hl(v.z, h[2], l[2]); split_hl(v.w, h[3], l[3]);
+            const int off = (f4 >> 1) * 2048 + m * 16 + (f4 & 1) * 8;
+            *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
+            *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
+        }
+        tc::fence_async_smem();
+        if (it == 0) { if (!tc::mbar_wait(bar + 2, 0)) ok = false; }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+            const uint32_t a_hi = tc::smem_u32(stg), a_lo = a_hi + C::STG_HALF_B;
+            const uint32_t b_hi = tc::smem_u32(sW), b_lo = b_hi + C::W_HALF_B;
+            constexpr uint32_t LBO_B = C::COUT * 16;
+            const uint32_t d = tmem + buf * C::COUT;
+#pragma unroll 1
+            for (int ks = 0; ks < C::CIN / 16; ks++) {
+                const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
+                const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
+                const uint64_t bh = tc::make_smem_desc(b_hi + ks * 2 * LBO_B, LBO_B, 128);
+                const uint64_t bl = tc::make_smem_desc(b_lo + ks * 2 * LBO_B, LBO_B, 128);
+                tc::mma_f16_ss(d, ah, bh, IDESC, ks > 0);
+                tc::mma_f16_ss(d, al, bh, IDESC, 1);
+                tc::mma_f16_ss(d, ah, bl, IDESC, 1);
+            }
+            tc::mma_commit(bar + buf);
+        }
+        if (prev_tile >= 0) epilogue(prev_tile, buf ^ 1);     // overlaps the MMAs just issued
+        prev_tile = tile;
+    }
+    if (prev_tile >= 0) epilogue(prev_tile, (it - 1) & 1);
+    if (!ok && tid == 0) atomicExch(status, 2);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------
+// tail: conv5 (1x1, 128->128, ReLU) -> global average pool -> fc 128->512 (+BN1d
+// folded) -> ReLU.  One CTA per crop: the 16x8 map is exactly one 128-row M tile.
+// ---------------------------------------------------------------------------
+struct TailCfg {
+    static constexpr int CIN = 128, COUT = 128, PX = 128, FEAT = 512;      // FEAT == OSB_THREADS
+    static constexpr int STG_HALF_B = (CIN / 8) * 128 * 16, STG_B = 2 * STG_HALF_B;   // 64 KB
+    static constexpr int W_HALF_B = CIN * COUT * 2, W_B = 2 * W_HALF_B;               // 64 KB
+    static constexpr int OFF_STG = 0, OFF_W = STG_B, OFF_BIAS = OFF_W + W_B;
+    static constexpr int OFF_V = OFF_BIAS + COUT * 4, OFF_MISC = OFF_V + COUT * 4;
+    static constexpr int SMEM_B = OFF_MISC + 128;
+    // blob: W5 hi/lo | b5 [128] | fc W [128][512] fp32 | fc b [512]
+    static constexpr int G_W = 0, G_B5 = W_B, G_FCW = G_B5 + 512, G_FCB = G_FCW + 128 * 512 * 4;
+    static constexpr int G_TOTAL = G_FCB + 512 * 4;
+};
+
+__global__ void __launch_bounds__(OSB_THREADS, 1)
+tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
+               const unsigned char *__restrict__ wblob, int *__restrict__ status) {
+    using C = TailCfg;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, grp = warp >> 2;
+    const int crop = blockIdx.x;
+    unsigned char *stg = smem + C::OFF_STG, *sW = smem + C::OFF_W;
+    float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
+    float *sV = reinterpret_cast<float *>(smem + C::OFF_V);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
+    if (warp == 0) tc::tmem_alloc(s_tmem, 128);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
+    if (tid < C::COUT) sBias[tid] = reinterpret_cast<const float *>(wblob + C::G_B5)[tid];
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(bar + 1, C::W_B);
+        tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 1);
+    }
+    const float *xin = x + (size_t)crop * C::PX * C::CIN;
+    constexpr int F4 = C::CIN / 4;
+#pragma unroll 4
+    for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
+        const int m = idx / F4, f4 = idx - m * F4;
+        const float4 v = *reinterpret_cast<const float4 *>(xin + (size_t)m * C::CIN + f4 * 4);
+        __half h[4], l[4];
+        split_hl(v.x, h[0], l[0]); split_hl(v.y, h[1], l[1]);
+        split_hl(v.z, h[2], l[2]); split_hl(v.w, h[3], l[3]);
+        const int off = (f4 >> 1) * 2048 + m * 16 + (f4 & 1) * 8;
+        *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
+        *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
+    }
+    tc::fence_async_smem();
+    bool ok = tc::mbar_wait(bar + 1, 0);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (tid == 0) {
+        constexpr uint32_t IDESC = tc::make_idesc_f16(128, C::COUT);
+        const uint32_t a_hi = tc::smem_u32(stg), a_lo = a_hi + C::STG_HALF_B;
+        const uint32_t b_hi = tc::smem_u32(sW), b_lo = b_hi + C::W_HALF_B;
+        constexpr uint32_t LBO_B = C::COUT * 16;
+#pragma unroll 1
+        for (int ks = 0; ks < C::CIN / 16; ks++) {
+            const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
+            const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
+            const uint64_t bh = tc::make_smem_desc(b_hi + ks * 2 * LBO_B, LBO_B, 128);
+            const uint64_t bl = tc::make_smem_desc(b_lo + ks * 2 * LBO_B, LBO_B, 128);
+            tc::mma_f16_ss(tmem, ah, bh, IDESC, ks > 0);
+            tc::mma_f16_ss(tmem, al, bh, IDESC, 1);
+            tc::mma_f16_ss(tmem, ah, bl, IDESC, 1);
+        }
+        tc::mma_commit(bar);
+    }
+    if (!tc::mbar_wait(bar, 0)) ok = false;
+    tc::fence_after_sync();
+    // relu(conv5) -> [px][129] floats over the (now dead) staging buffer, then column means
+    float *sAct = reinterpret_cast<float *>(stg);
+    const int m = quad * 32 + lane;
+#pragma unroll 1
+    for (int c0 = grp * 16; c0 < C::COUT; c0 += 16 * OSB_GROUPS) {
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + c0, v);
+#pragma unroll
+        for (int j = 0; j < 16; j++) sAct[m * 129 + c0 + j] = fmaxf(v[j] + sBias[c0 + j], 0.f);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (tid < C::COUT) {
+        float s = 0.f;
+        for (int p = 0; p < C::PX; p++) s += sAct[p * 129 + tid];
+        sV[tid] = s / (float)C::PX;
+    }
+    __syncthreads();
+    const float *fw = reinterpret_cast<const float *>(wblob + C::G_FCW);
+    const float *fb = reinterpret_cast<const float *>(wblob + C::G_FCB);
+    {   // one output feature per thread (OSB_THREADS == FEAT == 512)
+        float acc = fb[tid];
+#pragma unroll 8
+        for (int k = 0; k < C::CIN; k++) acc = fmaf(sV[k], fw[(size_t)k * C::FEAT + tid], acc);
+        feats[(size_t)crop * C::FEAT + tid] = fmaxf(acc, 0.f);
+    }
+    if (!ok && tid == 0) atomicExch(status, 3);
+    if (warp == 0) tc::tmem_dealloc(tmem, 128);
+}
+
+// ---------------------------------------------------------------------------
+// stem on the tensor cores: crop + bilinear resize + normalise + conv7x7/2 + ReLU
+// + maxpool3x3/2, one CTA per (crop, band of 8 pooled rows).
+//
+// A stride-2 7x7 conv on 3 channels is a stride-1 4x4 conv on the 2x2
+// space-to-depth image (12 channels, padded to 16):  with ky = 2a+dy, kx = 2b+dx
+//   out[cy][cx] = sum_{a,b<4} sum_{dy,dx,c} W[2a+dy][2b+dx][c] * S[cy+a][cx+b][(dy,dx,c)],
+//   S[Y][X][(dy,dx,c)] = Rpad[2Y+dy][2X+dx][c],  Rpad = resized crop, zero-padded by 3.
+// S is built once per band in the [chunk][pixel][8] operand layout, so the 16
+// taps are 16 shifted GEMMs (K = 16, N = 16) exactly like the 3x3 convs above.
+// ---------------------------------------------------------------------------
+struct StemCfg {
+    static constexpr int PR = 8;                    // pooled rows per CTA
+    static constexpr int NB = 64 / PR;              // bands per crop
+    static constexpr int CROWS = 2 * PR + 1;        // conv rows needed (17)
+    static constexpr int SROWS = CROWS + 3;         // space-to-depth rows (20)
+    static constexpr int WPS = 67;                  // S row pitch (64 conv cols + 3)
+    static constexpr int NPX = CROWS * WPS;         // output pixel index space
+    static constexpr int NT = (NPX + 127) / 128;    // 9 M tiles
+    static constexpr int MAP_PX = 1408;             // >= NT*128 + 3*WPS + 3
+    static constexpr int PLANE_B = MAP_PX * 16;
+    static constexpr int MAP_HALF_B = 2 * PLANE_B, MAP_B = 2 * MAP_HALF_B;
+    static constexpr int W_HALF_B = 16 * 16 * 16 * 2, W_B = 2 * W_HALF_B;     // [tap][2][16][8]
+    static constexpr int CONV_B = CROWS * 64 * 16 * 4;
+    static constexpr int OFF_MAP = 0, OFF_W = MAP_B, OFF_CONV = OFF_W + W_B;
+    static constexpr int OFF_BIAS = OFF_CONV + CONV_B, OFF_MISC = OFF_BIAS + 64;
+    static constexpr int SMEM_B = OFF_MISC + 64;
+    static constexpr int G_W = 0, G_BIAS = W_B, G_TOTAL = W_B + 128;
+    static_assert(NT * 128 + 3 * WPS + 3 <= MAP_PX, "map guard");
+    static_assert(SMEM_B <= 232448, "shared memory");
+};
+
+__global__ void __launch_bounds__(OSB_THREADS, 1)
+stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const int *__restrict__ boxes,
+               const unsigned char *__restrict__ wblob, float *__restrict__ out, int *__restrict__ status) {
+    using C = StemCfg;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, grp = warp >> 2;
+    const int crop = blockIdx.x / C::NB, band = blockIdx.x % C::NB;
+    const int py0 = band * C::PR, cy0 = 2 * py0 - 1;      // first conv row of the band
+    unsigned char *sMap = smem + C::OFF_MAP, *sW = smem + C::OFF_W;
+    float *sConv = reinterpret_cast<float *>(smem + C::OFF_CONV);
+    float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);     // [0] mma, [1] weights
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
+    if (warp == 0) tc::tmem_alloc(s_tmem, 256);
+    if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
+    if (tid < 16) sBias[tid] = reinterpret_cast<const float *>(wblob + C::G_BIAS)[tid];
+    // zero the operand map (padding rows/cols and the 4 pad channels stay zero)
+    for (int i = tid; i < C::MAP_B / 16; i += OSB_THREADS)
+        reinterpret_cast<uint4 *>(sMap)[i] = make_uint4(0u, 0u, 0u, 0u);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(bar + 1, C::W_B);
+        tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 1);
+    }
+    // ---- build S: every resized+normalised pixel of the band lands in exactly one slot
+    const int bx1 = boxes[crop * 4 + 0], by1 = boxes[crop * 4 + 1];
+    const int cw = boxes[crop * 4 + 2] - bx1, ch = boxes[crop * 4 + 3] - by1;
+    const float sc_y = (float)ch / 256.f, sc_x = (float)cw / 128.f;
+    const float mean[3] = {0.485f, 0.456f, 0.406f};
+    const float stdv[3] = {0.229f, 0.224f, 0.225f};
+    const int gy0 = 2 * cy0 - 3;                               // resized row of S row 0, dy = 0
+    for (int i = tid; i < 2 * C::SROWS * 134; i += OSB_THREADS) {
+        const int ry = i / 134, rx = i - ry * 134;            // local resized row / Rpad column
+        const int gy = gy0 + ry, gx = rx - 3;
+        if (gy < 0 || gy >= 256 || gx < 0 || gx >= 128 || cw <= 0 || ch <= 0) continue;
+        float sy = sc_y * ((float)gy + 0.5f) - 0.5f, sx = sc_x * ((float)gx + 0.5f) - 0.5f;
+        if (sy < 0.f) sy = 0.f;
+        if (sx < 0.f) sx = 0.f;
+        const int y0 = (int)sy, x0 = (int)sx;
+        const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
+        const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
+        const uint8_t *r0 = img + (size_t)(by1 + y0) * pitch + (size_t)bx1 * 3;
+        const uint8_t *r1 = img + (size_t)(by1 + y1) * pitch + (size_t)bx1 * 3;
+        const int Y = ry >> 1, dy = ry & 1, X = rx >> 1, dx = rx & 1;
+        const int q = Y * C::WPS + X;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float p00 = r0[x0 * 3 + c], p01 = r0[x1 * 3 + c];
+            const float p10 = r1[x0 * 3 + c], p11 = r1[x1 * 3 + c];
+            const float val = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
+            const float v = (val / 255.0f - mean[c]) / stdv[c];
+            __half h, l;
+            split_hl(v, h, l);
+            const int e = (dy * 2 + dx) * 3 + c;
+            const int off = (e >> 3) * C::PLANE_B + q * 16 + (e & 7) * 2;
+            *reinterpret_cast<__half *>(sMap + off) = h;
+            *reinterpret_cast<__half *>(sMap + C::MAP_HALF_B + off) = l;
+        }
+    }
+    tc::fence_async_smem();
+    bool ok = tc::mbar_wait(bar + 1, 0);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    if (tid == 0) {
+        constexpr uint32_t IDESC = tc::make_idesc_f16(128, 16);
+        const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(sMap), C::PLANE_B, 128);
+        const uint64_t al0 = desc_adv(ah0, C::MAP_HALF_B / 16);
+        const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW), 16 * 16, 128);
+        const uint64_t bl0 = desc_adv(bh0, C::W_HALF_B / 16);
+#pragma unroll 1
+        for (int t = 0; t < C::NT; t++) {
+            const uint32_t d = tmem + t * 16;
+            const uint64_t aht = desc_adv(ah0, t * 128), alt = desc_adv(al0, t * 128);
+#pragma unroll
+            for (int tap = 0; tap < 16; tap++) {
+                const int po = (tap >> 2) * C::WPS + (tap & 3);
+                mma3(d, desc_adv(aht, po), desc_adv(alt, po), desc_adv(bh0, tap * 32), desc_adv(bl0, tap * 32),
+                     IDESC, tap != 0);
+            }
+        }
+        tc::mma_commit(bar);
+    }
+    if (!tc::mbar_wait(bar, 0)) ok = false;
+    tc::fence_after_sync();
+    // ---- epilogue: bias + ReLU -> sConv[lcy][cx][16]; rows outside the conv map = -inf
+    for (int t = grp; t < C::NT; t += OSB_GROUPS) {
+        const int p = t * 128 + quad * 32 + lane;
+        float v[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * 16, v);
+        const int lcy = p / C::WPS, cx = p - lcy * C::WPS;
+        if (lcy < C::CROWS && cx < 64) {
+            const int gcy = cy0 + lcy;
+            const bool inside = gcy >= 0 && gcy < 128;
+            float *o = sConv + ((size_t)lcy * 64 + cx) * 16;
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+                float4 r;
+                r.x = inside ? fmaxf(v[j] + sBias[j], 0.f) : -INFINITY;
+                r.y = inside ? fmaxf(v[j + 1] + sBias[j + 1], 0.f) : -INFINITY;
+                r.z = inside ? fmaxf(v[j + 2] + sBias[j + 2], 0.f) : -INFINITY;
+                r.w = inside ? fmaxf(v[j + 3] + sBias[j + 3], 0.f) : -INFINITY;
+                *reinterpret_cast<float4 *>(o + j) = r;
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    // ---- maxpool 3x3 s2 p1 -> out[crop][py][px][16]
+    for (int o = tid; o < C::PR * 32 * 4; o += OSB_THREADS) {
+        const int c4 = o & 3, px = (o >> 2) & 31, pr = o >> 7;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int dy = 0; dy < 3; dy++) {
+            const int lcy = 2 * pr + dy;
+#pragma unroll
+            for (int dx = 0; dx < 3; dx++) {
+                const int cx = 2 * px - 1 + dx;
+                if (cx < 0 || cx >= 64) continue;
+                const float4 v = *reinterpret_cast<const float4 *>(sConv + ((size_t)lcy * 64 + cx) * 16 + c4 * 4);
+                m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+            }
+        }
+        *reinterpret_cast<float4 *>(out + (((size_t)crop * 64 + py0 + pr) * 32 + px) * 16 + c4 * 4) = m;
+    }
+    if (!ok && tid == 0) atomicExch(status, 4);
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+}
+
+using PwT1 = PwCfg<64, 64, 64, 32, true>;     // after conv2: 64x32x64 -> 32x16x64
+using PwT2 = PwCfg<96, 96, 32, 16, true>;     // after conv3: 32x16x96 -> 16x8x96
+
+template <class C>
+int launch_pw_tc(const float *x, float *y, const unsigned char *w, int n, int *status, int sms, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+        attr = true;
+    }
+    constexpr int HO = C::POOL ? C::H / 2 : C::H, WO = C::POOL ? C::W / 2 : C::W;
+    const long long total = (long long)n * HO * WO;
+    const int per = C::POOL ? 32 : 128;
+    int tiles = (int)((total + per - 1) / per);
+    int grid = tiles < sms ? tiles : sms;
+    pw_tc_kernel<C><<<grid, OSB_THREADS, C::SMEM_B, st>>>(x, y, w, n, status);
+    SSB_CHECK_LAUNCH();
     return 0;
 }
 
@@ -525,5 +1013,59 @@ int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, i
         case 5: return launch_block<Blk5>(x, y, w, n, status, st);
     }
     ssb_set_error("bad OSBlock index %d", b);
+    return -1;
+}
+
+static int g_sms = 0;
+static int num_sms() {
+    if (!g_sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sms <= 0) g_sms = 148;
+    }
+    return g_sms;
+}
+
+// which: 0 = transition after conv2, 1 = transition after conv3, 2 = tail (conv5+GAP+fc)
+int64_t ssb_reid_tc_aux_bytes(int which) {
+    switch (which) {
+        case 0: return PwT1::G_TOTAL;
+        case 1: return PwT2::G_TOTAL;
+        case 2: return TailCfg::G_TOTAL;
+        case 3: return StemCfg::G_TOTAL;
+    }
+    return -1;
+}
+
+int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *boxes, const unsigned char *wsec,
+                     float *out, int n, int *status, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
+        attr = true;
+    }
+    stem_tc_kernel<<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w, int n, int *status,
+                    cudaStream_t st) {
+    switch (which) {
+        case 0: return launch_pw_tc<PwT1>(x, y, w, n, status, num_sms(), st);
+        case 1: return launch_pw_tc<PwT2>(x, y, w, n, status, num_sms(), st);
+        case 2: {
+            static bool attr = false;
+            if (!attr) {
+                SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
+                attr = true;
+            }
+            tail_tc_kernel<<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
+            SSB_CHECK_LAUNCH();
+            return 0;
+        }
+    }
+    ssb_set_error("bad aux kernel index %d", which);
     return -1;
 }

@@ -85,7 +85,7 @@ struct ssb_tracker {
     int *boxes_tmp;           // [N][4]
     // tensor-core OSBlocks (reid_tc.cu): hi/lo fp16 operand blob, per-block offsets
     const unsigned char *w_tc;
-    int64_t w_tc_off[6];
+    int64_t w_tc_off[10];     // 6 OSBlocks, 2 transitions, tail, stem
     int use_tc;               // 1: OSBlocks on tcgen05, 0: fp32 SIMT baseline
     int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
 };
@@ -122,3 +122,8 @@ int64_t ssb_reid_ws_floats(int max_dets);
 int64_t ssb_reid_tc_block_bytes(int b);
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
                       cudaStream_t st);
+int64_t ssb_reid_tc_aux_bytes(int which);
+int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w, int n, int *status,
+                    cudaStream_t st);
+int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *boxes, const unsigned char *wsec,
+                     float *out, int n, int *status, cudaStream_t st);

@@ -98,6 +98,29 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float *v) {
 #pragma unroll
     for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
 }
+// 32 consecutive columns in one instruction (one wait per 32 values)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float *v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+          "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]),
+          "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+template <int N>
+__device__ __forceinline__ void tmem_ldN(uint32_t taddr, float *v) {
+    static_assert(N == 16 || N == 32, "tmem_ldN");
+    if (N == 16) tmem_ld16(taddr, v); else tmem_ld32(taddr, v);
+}
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *v) {
     uint32_t r[8];
     asm volatile(
@@ -123,22 +146,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
                  : "memory");
 }
 // bounded wait so that a protocol bug cannot hang the GPU: returns false after
-// ~0.25 s (5e8 SM cycles).  try_wait suspends the thread in hardware for at most
-// the hinted time, so this is not a hot spin.
+// ~0.25 s.  Plain try_wait blocks in hardware until the phase flips or an
+// implementation time limit passes (SYNCS.PHASECHK.TRYWAIT); a suspend-time
+// hint must NOT be given -- ptxas turns it into a NANOSLEEP of that length and
+// 45 % of the OSBlock kernel's samples sat in it (profiles/r01_tc_v1).
 __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t a = smem_u32(bar);
-    const long long t0 = clock64();
-    while (true) {
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
             "selp.u32 %0, 1, 0, p;\n\t}\n"
             : "=r"(ok)
-            : "r"(a), "r"(parity), "r"(2000u)
+            : "r"(a), "r"(parity)
             : "memory");
         if (ok) return true;
-        if (clock64() - t0 > 500000000LL) return false;
+        if (it == 64) t0 = clock64();
+        if (it > 64 && clock64() - t0 > 500000000LL) return false;
     }
 }
 

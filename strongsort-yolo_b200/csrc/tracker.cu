@@ -408,6 +408,124 @@ __device__ void lsap_carve(unsigned char *base, int L, LsapSmem &m) {
     m.cost = (double *)base;
 }
 
+// Register-resident shortest-augmenting-path core for nc <= 32*CPL columns: lane l
+// owns columns l, l+32, ... (v, shortest-path cost, path, row4col and the column's
+// position in scipy's `remaining[]` all live in registers), so a search step is CPL
+// independent cost loads + three warp REDUX ops instead of a shared-memory walk.
+// scipy's scan-order tie-break is reproduced through `pos` (the column's index in
+// remaining[]): among equal costs an unassigned column with the LARGEST position
+// wins, else the SMALLEST position; swap-removal moves the last column into the
+// freed position.  (tests emulate this against scipy; oracle/lsap.c is the serial twin.)
+__device__ __forceinline__ unsigned long long f64_order_key(double x) {
+    unsigned long long b = (unsigned long long)__double_as_longlong(x);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+template <int CPL>
+__device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr, int nc0, int nr,
+                              int nc, double *u, int *col4row, int *row4col_out, int lane) {
+    double v[CPL], spc[CPL];
+    int pos[CPL], r4c[CPL], path[CPL];
+    unsigned sc = 0;
+#pragma unroll
+    for (int k = 0; k < CPL; k++) { v[k] = 0.0; r4c[k] = -1; path[k] = -1; }
+    for (int curRow = 0; curRow < nr; curRow++) {
+        sc = 0;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            const int j = lane + 32 * k;
+            spc[k] = INFINITY;
+            pos[k] = j < nc ? nc - 1 - j : -1;
+        }
+        double minVal = 0.0;
+        int i = curRow, num_remaining = nc, sink = -1;
+        while (sink == -1) {
+            const double ui = u[i];
+            double bv = INFINITY;
+            unsigned bkey = 0;
+            int bk = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const int j = lane + 32 * k;
+                if (j < nc && !((sc >> k) & 1u)) {
+                    const double cij = staged ? C[(size_t)i * nc + j]
+                                              : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]);
+                    const double r = minVal + cij - ui - v[k];
+                    if (r < spc[k]) { path[k] = i; spc[k] = r; }
+                    const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k])
+                                                      : (unsigned)(nc - pos[k]);
+                    if (spc[k] < bv || (spc[k] == bv && key > bkey)) { bv = spc[k]; bkey = key; bk = k; }
+                }
+            }
+            // warp arg-min: value (two 32-bit REDUX over an order-preserving key), then tie key
+            const unsigned long long ok = f64_order_key(bv);
+            const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
+            const unsigned hmin = __reduce_min_sync(0xffffffffu, bk >= 0 ? hi : 0xffffffffu);
+            const unsigned lmin = __reduce_min_sync(0xffffffffu, (bk >= 0 && hi == hmin) ? lo : 0xffffffffu);
+            const bool vwin = bk >= 0 && hi == hmin && lo == lmin;
+            const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
+            const unsigned wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            if (wmask == 0) return false;
+            const int wl = __ffs(wmask) - 1;
+            minVal = __shfl_sync(0xffffffffu, bv, wl);
+            if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible
+            const int wk = __shfl_sync(0xffffffffu, bk, wl);
+            int my_pos = -1, my_r = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == wk) { my_pos = pos[k]; my_r = r4c[k]; }
+            const int index = __shfl_sync(0xffffffffu, my_pos, wl);
+            const int rj = __shfl_sync(0xffffffffu, my_r, wl);
+            const int jwin = wl + 32 * wk;
+            if (lane == wl) sc |= 1u << wk;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (!((sc >> k) & 1u) && pos[k] == num_remaining - 1) pos[k] = index;
+            num_remaining--;
+            if (rj == -1) sink = jwin; else i = rj;
+        }
+        // dual updates (column-wise: visited column j with row r = row4col[j] gives u[r])
+        if (lane == 0) u[curRow] += minVal;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            if ((sc >> k) & 1u) {
+                const double dlt = minVal - spc[k];
+                if (r4c[k] >= 0) u[r4c[k]] += dlt;
+                v[k] -= dlt;
+            }
+        }
+        __syncwarp();
+        // augment along the path
+        int j = sink;
+        while (true) {
+            const int ow = j & 31, kk = j >> 5;
+            int mine = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == kk) mine = path[k];
+            const int r = __shfl_sync(0xffffffffu, mine, ow);
+            if (lane == ow) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++)
+                    if (k == kk) r4c[k] = r;
+            }
+            const int t = col4row[r];
+            __syncwarp();
+            if (lane == 0) col4row[r] = j;
+            __syncwarp();
+            j = t;
+            if (r == curRow) break;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+        const int j = lane + 32 * k;
+        if (j < nc) row4col_out[j] = r4c[k];
+    }
+    __syncwarp();
+    return true;
+}
+
 // Solve with the whole block staging, warp 0 iterating.  C is [nr0][nc0]
 // row-major (ld = nc0).  Results in ORIGINAL orientation: col4row_out[nr0],
 // row4col_out[nc0] (-1 = unassigned).  Must be called by all threads.
@@ -434,7 +552,17 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     for (int j = tid; j < nc; j += blockDim.x) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
     __syncthreads();
 
-    if (tid < 32) {
+    if (tid < 32 && nc <= 512) {
+        const double *Cw = staged ? m.cost : C;
+        bool okr;
+        if (nc <= 128) okr = lsap_warp_reg<4>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else if (nc <= 256) okr = lsap_warp_reg<8>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else okr = lsap_warp_reg<16>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        if (!okr) {
+            for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
+            for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
+        }
+    } else if (tid < 32) {
         bool failed = false;
         for (int curRow = 0; curRow < nr && !failed; curRow++) {
             for (int j = lane; j < nc; j += 32) {

@@ -65,9 +65,9 @@ class StrongSORT:
             # tensor-core OSBlocks: fp16 hi/lo operand blob (csrc/reid_tc.cu)
             tc_blob, tc_off = _weights.pack_tc(_weights.fold(sd))
             self._w_tc = torch.from_numpy(tc_blob).to(self.device)
-            self._w_tc_off = (C.c_int64 * 6)(*[int(o) for o in tc_off])
+            self._w_tc_off = (C.c_int64 * len(tc_off))(*[int(o) for o in tc_off])
             _lib.check(self._lib.ssb_reid_set_weights_tc(self._h, _lib.ptr(self._w_tc),
-                                                         self._w_tc_off, 6), "ssb_reid_set_weights_tc")
+                                                         self._w_tc_off, len(tc_off)), "ssb_reid_set_weights_tc")
             self.set_reid_backend(reid_backend)
             # staging
             S, N = cfg.max_tracks, cfg.max_dets

@@ -185,4 +185,27 @@ def pack_tc(tensors):
         sec += w3.tobytes()
         offs.append(len(blob))
         blob += _pad128(sec)
+    # transition layers (conv1x1 + ReLU + avgpool): W hi/lo | bias
+    for t in ("conv2.2.0", "conv3.2.0"):
+        offs.append(len(blob))
+        blob += _pad128(_b_layout(T[t + ".w"].astype(np.float64)) + _pad128(T[t + ".b"].astype(np.float32).tobytes()))
+    # tail: conv5 W hi/lo | b5 | fc W [128][512] fp32 | fc b
+    offs.append(len(blob))
+    blob += _pad128(_b_layout(T["conv5.w"].astype(np.float64)) + T["conv5.b"].astype(np.float32).tobytes()
+                    + np.ascontiguousarray(T["fc.w"], dtype=np.float32).tobytes()
+                    + T["fc.b"].astype(np.float32).tobytes())
+    # stem as a 4x4 conv on the 2x2 space-to-depth image: per tap (a,b) a [16 k][16 co] matrix,
+    # k = (dy*2+dx)*3 + c  <-  W[2a+dy][2b+dx][c][co]   (zero where 2a+dy or 2b+dx > 6, k >= 12)
+    sw = T["stem.w"].astype(np.float64)                       # [7][7][3][16]
+    wt = np.zeros((16, 16, 16))
+    for a in range(4):
+        for b in range(4):
+            for dy in range(2):
+                for dx in range(2):
+                    if 2 * a + dy <= 6 and 2 * b + dx <= 6:
+                        e = (dy * 2 + dx) * 3
+                        wt[a * 4 + b, e:e + 3, :] = sw[2 * a + dy, 2 * b + dx]
+    hi, lo = _hi_lo(np.ascontiguousarray(wt.reshape(16, 2, 8, 16).transpose(0, 1, 3, 2)))   # [tap][kc][n][8]
+    offs.append(len(blob))
+    blob += _pad128(hi.tobytes() + lo.tobytes() + _pad128(T["stem.b"].astype(np.float32).tobytes()))
     return np.frombuffer(blob, dtype=np.uint8).copy(), np.asarray(offs, dtype=np.int64)

@@ -55,7 +55,7 @@ def _hl(v):
 def osblock_emul(b, x, blob, offs):
     """x: float32 [n,H,W,cin] -> float32 [n,H,W,cout], band by band like the kernel."""
     c = Cfg(b)
-    sec = bytes(blob[int(offs[b]):int(offs[b + 1]) if b < 5 else len(blob)])
+    sec = bytes(blob[int(offs[b]):int(offs[b + 1])])
     W1 = _b_operand(sec[0:c.C1W_B], c.CIN, c.MIDP)
     WD = _b_operand(sec[c.C1W_B:c.C1W_B + c.DNW_B], c.CIN, c.COUT) if c.DOWN else None
     LCW = [_b_operand(sec[c.G_LCW + l * c.LCW_B:c.G_LCW + (l + 1) * c.LCW_B], 9 * c.MIDP, c.MIDP)

@@ -28,3 +28,34 @@ def test_emulated_tc_block_matches_oracle(state_dict, block):
         ref = getattr(model, stage)[idx](torch.as_tensor(x).permute(0, 3, 1, 2)).permute(0, 2, 3, 1).numpy()
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err < 2e-5, err
+
+
+def test_stem_space_to_depth_packing(state_dict):
+    """Section 9 of the tensor-core blob (stem as 16 shifted GEMMs on the 2x2
+    space-to-depth image, csrc/reid_tc.cu: stem_tc_kernel) reproduces the 7x7/2 conv."""
+    import torch.nn.functional as F
+    tensors = weights.fold(state_dict)
+    blob, offs = weights.pack_tc(tensors)
+    T = dict(tensors)
+    sec = bytes(blob[int(offs[9]):])
+    half = 16 * 16 * 16 * 2
+    hi = np.frombuffer(sec[:half], dtype=np.float16).astype(np.float64)
+    lo = np.frombuffer(sec[half:2 * half], dtype=np.float16).astype(np.float64)
+    wt = (hi + lo).reshape(16, 2, 16, 8).transpose(0, 1, 3, 2).reshape(16, 16, 16)     # [tap][k][co]
+    bias = np.frombuffer(sec[2 * half:2 * half + 64], dtype=np.float32)
+    np.testing.assert_array_equal(bias, T["stem.b"])
+    rng = np.random.default_rng(0)
+    R = rng.normal(0, 1, (256, 128, 3))
+    w = torch.as_tensor(T["stem.w"].astype(np.float64)).permute(3, 2, 0, 1)
+    ref = F.conv2d(torch.as_tensor(R).permute(2, 0, 1)[None], w, stride=2, padding=3)[0].permute(1, 2, 0).numpy()
+    Rpad = np.zeros((264, 136, 3)); Rpad[3:259, 3:131] = R
+    S = np.zeros((131, 67, 16))
+    for dy in range(2):
+        for dx in range(2):
+            e = (dy * 2 + dx) * 3
+            S[:, :, e:e + 3] = Rpad[dy:dy + 262:2, dx:dx + 134:2]
+    out = np.zeros((128, 64, 16))
+    for a in range(4):
+        for b in range(4):
+            out += S[a:a + 128, b:b + 64] @ wt[a * 4 + b]
+    assert np.abs(out - ref).max() < 1e-5 * np.abs(ref).max()
