@@ -272,35 +272,57 @@ def main():
         st.synchronize()
         hint = int(trk._out_dev[:32].view(torch.int32)[1].item())
 
+    # (a) serial reference: one frame at a time, per-step events, L2 flushed between steps
     with torch.cuda.stream(st):
         for i in range(W):
             step_device(i)
             read_hint()
     barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-    l0 = lib.ssb_launch_count()
-    t_wall0 = time.perf_counter()
+    KS = min(K, 30)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KS)]
     with torch.cuda.stream(st):
-        for k in range(K):
+        for k in range(KS):
             flush.fill_(k & 0xFF)                      # L2 flush, outside the timed pair
             ev[k][0].record(st)
             step_device(W + k)
             ev[k][1].record(st)
             read_hint()                                # sizes the next frame's grids (exact)
     barrier()
+    serial_ms = sum(a.elapsed_time(b) for a, b in ev) / KS
+    del trk
+
+    # (b) value: the two-stage pipeline (embedding of frame k on one stream overlaps the
+    # association of frame k-1 on another), device-resident inputs, K frames timed as a whole.
+    # Inputs rotate through W+K distinct frames (>= 5x the 126 MB L2), no flush needed.
+    trk = StrongSORT(device=str(device))
+    st = trk.stream
+    sptr = C.c_void_p(st.cuda_stream)
+    for i in range(W):
+        trk.update_pipelined(dets_dev[i], imgs_dev[i])
+    trk.flush_pipelined()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.ssb_launch_count()
+    e0.record(st)
+    for k in range(K):
+        trk.update_pipelined(dets_dev[W + k], imgs_dev[W + k])
+    trk.flush_pipelined()
+    e1.record(st)
+    barrier()
     launches = int(lib.ssb_launch_count() - l0)
-    t_steps_ms = sum(a.elapsed_time(b) for a, b in ev)
+    t_steps_ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     t_steps_ms = max_over_ranks(t_steps_ms)
     ms_per_step = t_steps_ms / K
     value = world * K / (t_steps_ms / 1000.0)
-    final_next_id = int(trk.last_counts[3]) if False else int(trk._out_dev[:32].view(torch.int32)[3].item())
+    final_next_id = int(trk.last_counts[3])
 
     if args.only_device:
         if rank == 0:
             print(json.dumps({"only_device": True, "ms_per_step": ms_per_step, "value": value,
+                              "serial_flushed_ms_per_step": serial_ms,
                               "gpu_launches": launches, "steps": K, "warmup": W}), flush=True)
         return
 
@@ -372,7 +394,12 @@ def main():
             "vs_baseline": None, "dtype": "f32 (ReID, appearance) + f64 (Kalman, gating, LSAP)",
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "streams": world, "frame": [H, Wd, 3],
-                       "dets_per_frame": float(np.mean(n_per)), "l2": "flushed between steps (256 MiB write)",
+                       "dets_per_frame": float(np.mean(n_per)),
+                       "l2": f"not flushed: inputs rotate through {W + K} distinct frames "
+                             f"({(W + K) * imgs[0].numel() / 1e6:.0f} MB > 126 MB L2)",
+                       "pipeline": "embedding(k) on stream 1 overlaps association(k-1) on stream 2 "
+                                   "(ssb_embed / ssb_associate); results identical to the serial path",
+                       "serial_flushed_ms_per_step": serial_ms,
                        "weights": "seeded random OSNet-x0.25, BN calibrated on synthetic crops",
                        "e2e_ids_equal_device_run": bool(same_ids)},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

@@ -93,6 +93,9 @@ int ssb_reid_use_tc(ssb_tracker *t, int enable);
 /* one OSBlock on caller arrays (parity tests): x float32 NHWC [n][H][W][cin] */
 int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, float *y_dev, int n, int use_tc,
                    ssb_stream_t stream);
+/* diagnostic: CTA 0 of every tensor-core OSBlock launch writes clock64() phase stamps into
+ * buf_dev (int64[64], [0] = count); NULL switches it off (default) */
+int ssb_reid_tc_debug(void *buf_dev);
 /* copies the tensor-core path's device status word (0 = ok) to the host; synchronises */
 int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream);
 
@@ -109,6 +112,17 @@ int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream
 int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_dev,
                int h, int w, int pitch, const float *feats_dev, double *out_dev,
                int32_t *counts_dev, int track_hint, ssb_stream_t stream);
+
+/* The same step split in its two stages, for callers that overlap them on two streams:
+ * ssb_embed (detection prep + OSNet embeddings into slot 0/1; independent of the track
+ * table) for frame t+1 may run while ssb_associate (everything else) runs for frame t.
+ * ssb_update(...) == ssb_embed(slot 0) + ssb_associate(slot 0) on one stream.  The caller
+ * orders the stages with events; img_dev == NULL in ssb_embed skips the OSNet (the caller
+ * then passes feats_dev to ssb_associate). */
+int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n, const uint8_t *img_dev,
+              int h, int w, int pitch, ssb_stream_t stream);
+int ssb_associate(ssb_tracker *t, int slot, int n, int h, int w, const float *feats_dev,
+                  double *out_dev, int32_t *counts_dev, int track_hint, ssb_stream_t stream);
 
 /* ---- stage entry points (parity tests call these one by one) ------------- */
 /* OSNet embeddings of n crops: boxes_dev int32 [n,4] x1,y1,x2,y2 with crop =

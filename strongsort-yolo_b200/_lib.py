@@ -13,7 +13,7 @@ SYMBOLS = [
     "ssb_version", "ssb_launch_count", "ssb_last_error", "ssb_default_config", "ssb_workspace_bytes",
     "ssb_create", "ssb_destroy", "ssb_reset", "ssb_reid_num_tensors",
     "ssb_reid_tensor_sizes", "ssb_reid_set_weights", "ssb_reid_tc_weight_bytes",
-    "ssb_reid_set_weights_tc", "ssb_reid_use_tc", "ssb_reid_block", "ssb_reid_tc_status", "ssb_update", "ssb_reid",
+    "ssb_reid_set_weights_tc", "ssb_reid_use_tc", "ssb_embed", "ssb_associate", "ssb_reid_block", "ssb_reid_tc_status", "ssb_reid_tc_debug", "ssb_update", "ssb_reid",
     "ssb_crop_boxes", "ssb_kf_predict", "ssb_kf_update", "ssb_kf_gating",
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
@@ -67,7 +67,10 @@ def load():
     lib.ssb_reid_set_weights_tc.argtypes = [vp, vp, C.POINTER(i64), i32]
     lib.ssb_reid_use_tc.argtypes = [vp, i32]
     lib.ssb_reid_block.argtypes = [vp, i32, vp, vp, i32, i32, vp]
+    lib.ssb_reid_tc_debug.argtypes = [vp]
     lib.ssb_reid_tc_status.argtypes = [vp, C.POINTER(C.c_int32), vp]
+    lib.ssb_embed.argtypes = [vp, i32, vp, i32, vp, i32, i32, i32, vp]
+    lib.ssb_associate.argtypes = [vp, i32, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.ssb_update.argtypes = [vp, vp, i32, vp, i32, i32, i32, vp, vp, vp, i32, vp]
     lib.ssb_reid.argtypes = [vp, vp, i32, i32, i32, vp, i32, vp, vp]
     lib.ssb_crop_boxes.argtypes = [vp, i32, i32, i32, vp, vp]

@@ -63,7 +63,8 @@ struct Carver {
 };
 
 static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratch *fs,
-                    float **reid_ws, int64_t *reid_floats, int **boxes_tmp, int **tc_status = nullptr) {
+                    float **reid_ws, int64_t *reid_floats, int **boxes_tmp, int **tc_status = nullptr,
+                    DetSlot *slot1 = nullptr) {
     const size_t S = c->max_tracks, N = c->max_dets, B = c->nn_budget, D = c->feat_dim;
     const size_t L = S > N ? S : N;
     Carver k{base, 0};
@@ -101,6 +102,12 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     int *bt = k.take<int>(N * 4);
     int *tcs = k.take<int>(64);
     if (tc_status) *tc_status = tcs;
+    DetSlot s1;
+    s1.det_tlwh = k.take<float>(N * 4); s1.det_xyah = k.take<float>(N * 4);
+    s1.det_box = k.take<int>(N * 4);
+    s1.det_conf = k.take<float>(N); s1.det_cls = k.take<float>(N);
+    s1.feats = k.take<float>(N * D); s1.det_norm = k.take<float>(N);
+    if (slot1) *slot1 = s1;
     if (tt) *tt = t;
     if (fs) *fs = f;
     if (reid_ws) *reid_ws = rw;
@@ -129,7 +136,10 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
     t->cfg = *cfg;
     t->ws_base = (char *)workspace_dev;
     t->ws_bytes = workspace_bytes;
-    carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp, &t->tc_status);
+    carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp, &t->tc_status,
+          &t->slot[1]);
+    t->slot[0] = DetSlot{t->fs.det_tlwh, t->fs.det_xyah, t->fs.det_box, t->fs.det_conf, t->fs.det_cls,
+                         t->fs.feats, t->fs.det_norm};
     SsbDims &d = t->dims;
     d.S = cfg->max_tracks; d.N = cfg->max_dets; d.B = cfg->nn_budget; d.D = cfg->feat_dim;
     d.n_init = cfg->n_init; d.max_age = cfg->max_age;
@@ -154,27 +164,41 @@ extern "C" int ssb_reset(ssb_tracker *t, ssb_stream_t stream) {
     return ssb_launch_reset(t, (cudaStream_t)stream);
 }
 
-extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_dev,
-                          int h, int w, int pitch, const float *feats_dev, double *out_dev,
-                          int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
-    if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
+// stage 1 of a frame: detection prep + OSNet embeddings into slot (0/1).  Independent of
+// the track table, so frame t+1 may be embedded while frame t is still being associated.
+extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n, const uint8_t *img_dev,
+                         int h, int w, int pitch, ssb_stream_t stream) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
     if (n > 0 && !dets_dev) { ssb_set_error("null dets"); return -1; }
     if (h <= 0 || w <= 0) { ssb_set_error("bad image size %dx%d", w, h); return -1; }
     cudaStream_t st = (cudaStream_t)stream;
-    int rc = ssb_launch_prep(t->dims, dets_dev, n, h, w, t->fs, st);
+    FrameScratch fs = ssb_slot_view(t, slot);
+    int rc = ssb_launch_prep(t->dims, dets_dev, n, h, w, fs, st);
+    if (rc || n == 0) return rc;
+    if (!img_dev) return 0;                         // caller supplies embeddings to ssb_associate
+    if (pitch < 3 * w) { ssb_set_error("bad pitch"); return -1; }
+    if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
+    return ssb_reid_forward(t, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
+}
+
+// stage 2: association + track-table update from the detections/embeddings of `slot`
+extern "C" int ssb_associate(ssb_tracker *t, int slot, int n, int h, int w, const float *feats_dev,
+                             double *out_dev, int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
+    if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
+    if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
+    return ssb_launch_track_frame(t, slot, n, h, w, feats_dev, out_dev, counts_dev, track_hint,
+                                  (cudaStream_t)stream);
+}
+
+extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_dev,
+                          int h, int w, int pitch, const float *feats_dev, double *out_dev,
+                          int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
+    if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
+    if (!feats_dev && n > 0 && !img_dev) { ssb_set_error("null image"); return -1; }
+    int rc = ssb_embed(t, 0, dets_dev, n, feats_dev ? nullptr : img_dev, h, w, pitch, stream);
     if (rc) return rc;
-    const float *feats = feats_dev;
-    if (!feats) {
-        if (n > 0) {
-            if (!img_dev || pitch < 3 * w) { ssb_set_error("null image / bad pitch"); return -1; }
-            if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
-            rc = ssb_reid_forward(t, img_dev, h, w, pitch, t->fs.det_box, n, t->fs.feats, st);
-            if (rc) return rc;
-        }
-        feats = t->fs.feats;
-    }
-    return ssb_launch_track_frame(t, n, h, w, feats, out_dev, counts_dev, track_hint, st);
+    return ssb_associate(t, 0, n, h, w, feats_dev, out_dev, counts_dev, track_hint, stream);
 }
 
 extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, int pitch,

@@ -584,3 +584,11 @@ extern "C" int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stre
     SSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     return 0;
 }
+
+// diagnostic: CTA 0 of every tensor-core OSBlock launch writes clock64() phase stamps to
+// buf_dev[0..63] (buf_dev[0] = number of stamps); pass NULL to switch it off.
+extern long long *g_ssb_tc_dbg;
+extern "C" int ssb_reid_tc_debug(void *buf_dev) {
+    g_ssb_tc_dbg = (long long *)buf_dev;
+    return 0;
+}

@@ -79,6 +79,7 @@ struct BlkCfg {
     static_assert(SMEM_B <= 232448, "shared memory");
     static_assert(MIDP % 16 == 0 && COUT % 16 == 0 && CIN % 16 == 0, "MMA shapes");
     static_assert(H % R == 0 && H / R == NB, "bands");
+    static_assert(MID <= MIDP && COUT == 4 * MID, "OSBlock channel plan");
     // global blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
     static constexpr int G_C1W = 0;
     static constexpr int G_LCW = C1W_B + DNW_B;
@@ -111,6 +112,13 @@ __device__ __forceinline__ void split_hl(float v, __half &h, __half &l) {
 constexpr int OSB_THREADS = 512;
 constexpr int OSB_GROUPS = OSB_THREADS / 128;
 
+// two values at once: one packed convert each way (F2FP / HADD2.F32) instead of four scalar ones
+__device__ __forceinline__ void split_hl2(float a, float b, __half2 &h, __half2 &l) {
+    h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    l = __floats2half2_rn(a - hf.x, b - hf.y);
+}
+
 struct TrueT { static constexpr bool value = true; };
 struct FalseT { static constexpr bool value = false; };
 
@@ -142,7 +150,8 @@ struct Pipe {           // one mbarrier, bulk-synchronous use: every thread wait
 template <class C>
 __global__ void __launch_bounds__(OSB_THREADS, 1)
 osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
-                  const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status) {
+                  const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status,
+                  long long *__restrict__ dbg) {
     extern __shared__ __align__(1024) unsigned char smem[];
     using P = Par<C>;
     cg::cluster_group cluster = cg::this_cluster();
@@ -181,6 +190,10 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
+    // optional phase timestamps of CTA 0 (tools/time_stages.py); dbg == nullptr in production
+    int dbg_n = 0;
+    auto stamp = [&]() { if (dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 63) dbg[1 + dbg_n++] = clock64(); };
+    stamp();
     Pipe mma{bar_mma, 0, true};
     uint32_t w_phase = 0;
     bool ok = true;
@@ -198,6 +211,21 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         gc = lc - 1;
         return lc >= 1 && lc <= C::W && lr >= 1 && lr <= C::RH && gr >= 0 && gr < C::H;
     };
+
+    // this thread drains tile rows p = t*128 + quad*32 + lane for t = grp, grp+4: the same
+    // pixels in every layer, so their validity is decided once (bit j: j-th tile of the thread)
+    unsigned valid_m = 0, own_m = 0;
+    {
+        int j = 0;
+        for (int t = grp; t < C::NT; t += OSB_GROUPS, j++) {
+            const int p = t * 128 + quad * 32 + lane;
+            int gr, gc;
+            const bool v = pixel_valid(p, gr, gc);
+            const int lr = p / C::WP;
+            if (v) valid_m |= 1u << j;
+            if (v && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R) own_m |= 1u << j;
+        }
+    }
 
     // ------------------------------------------------------------------
     // phase 1: X1 = relu(conv1(x)) on every band tile; downsample on inner tiles
@@ -224,9 +252,9 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (pixel_valid(t * 128 + px, gr, gc))
                 v = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
-            __half h[4], l[4];
-            split_hl(v.x, h[0], l[0]); split_hl(v.y, h[1], l[1]);
-            split_hl(v.z, h[2], l[2]); split_hl(v.w, h[3], l[3]);
+            __align__(8) __half2 h[2], l[2];
+            split_hl2(v.x, v.y, h[0], l[0]);
+            split_hl2(v.z, v.w, h[1], l[1]);
             const int off = (f4 >> 1) * 2048 + px * 16 + (f4 & 1) * 8;
             *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
             *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
@@ -276,34 +304,34 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     auto drain_to_map = [&](unsigned char *dst, const float *bias, auto gapacc, float *gap,
                             uint64_t *tile_bar, uint32_t tile_par) {
         constexpr bool GAPACC = decltype(gapacc)::value;
-        for (int t = grp; t < C::NT; t += OSB_GROUPS) {
+        int jt = 0;
+        for (int t = grp; t < C::NT; t += OSB_GROUPS, jt++) {
             if (tile_bar) {
                 if (!tc::mbar_wait(tile_bar + t, tile_par)) ok = false;
                 tc::fence_after_sync();
             }
             const int p = t * 128 + quad * 32 + lane;
-            int gr, gc;
-            const bool valid = pixel_valid(p, gr, gc);
-            const int lr = p / C::WP;
-            const bool own = valid && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R;
+            const bool valid = (valid_m >> jt) & 1u;
+            const bool own = (own_m >> jt) & 1u;
             unsigned char *d_hi = dst + (C::GUARD + p) * 16, *d_lo = d_hi + C::MAP_HALF_B;
             float v[C::MIDP];
             tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_LC + t * C::MIDP, v);
 #pragma unroll
             for (int c0 = 0; c0 < C::MIDP; c0 += 16) {
-                __align__(16) __half h[16];
-                __align__(16) __half l[16];
+                __align__(16) __half2 h[8];
+                __align__(16) __half2 l[8];
 #pragma unroll
-                for (int j = 0; j < 16; j++) {
-                    const float f = valid ? fmaxf(v[c0 + j] + bias[c0 + j], 0.f) : 0.f;
-                    if (GAPACC) { if (own) gap[c0 + j] += f; }
-                    split_hl(f, h[j], l[j]);
+                for (int j = 0; j < 16; j += 2) {
+                    const float f0 = valid ? fmaxf(v[c0 + j] + bias[c0 + j], 0.f) : 0.f;
+                    const float f1 = valid ? fmaxf(v[c0 + j + 1] + bias[c0 + j + 1], 0.f) : 0.f;
+                    if (GAPACC) { if (own) { gap[c0 + j] += f0; gap[c0 + j + 1] += f1; } }
+                    split_hl2(f0, f1, h[j >> 1], l[j >> 1]);
                 }
                 const int pl = (c0 >> 3) * C::PLANE_B;
                 *reinterpret_cast<uint4 *>(d_hi + pl) = *reinterpret_cast<uint4 *>(&h[0]);
-                *reinterpret_cast<uint4 *>(d_hi + pl + C::PLANE_B) = *reinterpret_cast<uint4 *>(&h[8]);
+                *reinterpret_cast<uint4 *>(d_hi + pl + C::PLANE_B) = *reinterpret_cast<uint4 *>(&h[4]);
                 *reinterpret_cast<uint4 *>(d_lo + pl) = *reinterpret_cast<uint4 *>(&l[0]);
-                *reinterpret_cast<uint4 *>(d_lo + pl + C::PLANE_B) = *reinterpret_cast<uint4 *>(&l[8]);
+                *reinterpret_cast<uint4 *>(d_lo + pl + C::PLANE_B) = *reinterpret_cast<uint4 *>(&l[4]);
             }
         }
         tc::fence_async_smem();
@@ -312,7 +340,9 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         tc::fence_after_sync();
     };
 
+    stamp();                                   // [1] phase 1 (staging + conv1/down MMAs) done
     drain_to_map(sX1, sPar + P::B1, FalseT{}, nullptr, nullptr, 0);
+    stamp();                                   // [2] X1 drained
 
     // ------------------------------------------------------------------
     // phase 2: four streams of dense 3x3 convs + gated conv3 accumulation
@@ -328,6 +358,7 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             if (!tc::mbar_wait(bar_w, w_phase)) ok = false;       // this LightConv's weights landed
             w_phase ^= 1;
             tc::fence_after_sync();
+            stamp();                           // LC start (weights ready)
             // four issuing threads (one per SM sub-partition), tile t -> warp t % 4; every
             // tile commits to its own barrier so its drain overlaps the later tiles' MMAs
             if (warp < 4 && lane == 0) {
@@ -371,15 +402,18 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                 c3_pending = false;
             }
             const bool last = (k == s);
+            stamp();                           // LC issued (thread 0: its own tiles)
             if (!last) {
                 drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, FalseT{}, nullptr, bar_tile, lc_par);
                 lc_par ^= 1;
+                stamp();                       // LC drained
             } else {
                 float gap[C::MIDP];
 #pragma unroll
                 for (int j = 0; j < C::MIDP; j++) gap[j] = 0.f;
                 drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, TrueT{}, gap, bar_tile, lc_par);
                 lc_par ^= 1;
+                stamp();                       // last LC of the stream drained
                 // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid
 #pragma unroll
                 for (int j = 0; j < C::MIDP; j++) {
@@ -456,6 +490,7 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                     tc::mma_commit(bar_c3);
                 }
                 c3_pending = true;
+                stamp();                       // gate + conv3 issued
             }
             src = dst;
             dst = (dst == sP) ? sQ : sP;
@@ -502,6 +537,8 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             }
         }
     }
+    stamp();                                   // final epilogue done
+    if (dbg && blockIdx.x == 0 && tid == 0) dbg[0] = dbg_n;
     if (!ok || !mma.ok) { if (tid == 0) atomicExch(status, 1); }
     tc::fence_before_sync();
     if (C::NB > 1) cluster.sync(); else __syncthreads();     // remote sGap reads are done
@@ -521,7 +558,8 @@ using Blk4 = BlkCfg<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1>;
 using Blk5 = BlkCfg<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1>;
 
 template <class C>
-int launch_block(const float *x, float *y, const unsigned char *w, int n, int *status, cudaStream_t st) {
+int launch_block(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,
+                 cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         SSB_CHECK_CUDA(cudaFuncSetAttribute(osblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
@@ -539,7 +577,7 @@ int launch_block(const float *x, float *y, const unsigned char *w, int n, int *s
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock_tc_kernel<C>, x, y, w, n, status));
+    SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock_tc_kernel<C>, x, y, w, n, status, dbg));
     g_ssb_launches++;
     return 0;
 }
@@ -655,9 +693,9 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                 const long long o = (long long)tile * 128 + m;
                 if (o < total_out) v = *reinterpret_cast<const float4 *>(x + (size_t)o * C::CIN + f4 * 4);
             }
-            __half h[4], l[4];
-            split_hl(v.x, h[0], l[0]); split_hl(v.y, h[1], l[1]);
-            split_hl(v.z, h[2], l[2]); split_hl(v.w, h[3], l[3]);
+            __align__(8) __half2 h[2], l[2];
+            split_hl2(v.x, v.y, h[0], l[0]);
+            split_hl2(v.z, v.w, h[1], l[1]);
             const int off = (f4 >> 1) * 2048 + m * 16 + (f4 & 1) * 8;
             *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
             *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
@@ -740,9 +778,9 @@ tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
     for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
         const int m = idx / F4, f4 = idx - m * F4;
         const float4 v = *reinterpret_cast<const float4 *>(xin + (size_t)m * C::CIN + f4 * 4);
-        __half h[4], l[4];
-        split_hl(v.x, h[0], l[0]); split_hl(v.y, h[1], l[1]);
-        split_hl(v.z, h[2], l[2]); split_hl(v.w, h[3], l[3]);
+        __align__(8) __half2 h[2], l[2];
+        split_hl2(v.x, v.y, h[0], l[0]);
+        split_hl2(v.z, v.w, h[1], l[1]);
         const int off = (f4 >> 1) * 2048 + m * 16 + (f4 & 1) * 8;
         *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
         *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
@@ -1002,15 +1040,18 @@ int64_t ssb_reid_tc_block_bytes(int b) {
     return -1;
 }
 
+long long *g_ssb_tc_dbg = nullptr;      // device buffer of 64 int64 (ssb_reid_tc_debug), usually null
+
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
                       cudaStream_t st) {
+    long long *dbg = g_ssb_tc_dbg;
     switch (b) {
-        case 0: return launch_block<Blk0>(x, y, w, n, status, st);
-        case 1: return launch_block<Blk1>(x, y, w, n, status, st);
-        case 2: return launch_block<Blk2>(x, y, w, n, status, st);
-        case 3: return launch_block<Blk3>(x, y, w, n, status, st);
-        case 4: return launch_block<Blk4>(x, y, w, n, status, st);
-        case 5: return launch_block<Blk5>(x, y, w, n, status, st);
+        case 0: return launch_block<Blk0>(x, y, w, n, status, dbg, st);
+        case 1: return launch_block<Blk1>(x, y, w, n, status, dbg, st);
+        case 2: return launch_block<Blk2>(x, y, w, n, status, dbg, st);
+        case 3: return launch_block<Blk3>(x, y, w, n, status, dbg, st);
+        case 4: return launch_block<Blk4>(x, y, w, n, status, dbg, st);
+        case 5: return launch_block<Blk5>(x, y, w, n, status, dbg, st);
     }
     ssb_set_error("bad OSBlock index %d", b);
     return -1;

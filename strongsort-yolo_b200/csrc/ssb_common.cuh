@@ -60,6 +60,14 @@ struct FrameScratch {
     double *lsap_ws;   // LSAP global workspace (u, v, spc when not in smem)
 };
 
+// the per-detection buffers of one frame; two slots so that the embedding stage of
+// frame t+1 can run (on another stream) while frame t is being associated
+struct DetSlot {
+    float *det_tlwh, *det_xyah;
+    int *det_box;
+    float *det_conf, *det_cls, *feats, *det_norm;
+};
+
 struct SsbDims {
     int S, N, B, D;
     int n_init, max_age;
@@ -88,6 +96,7 @@ struct ssb_tracker {
     int64_t w_tc_off[10];     // 6 OSBlocks, 2 transitions, tail, stem
     int use_tc;               // 1: OSBlocks on tcgen05, 0: fp32 SIMT baseline
     int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
+    DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
 };
 
 void ssb_set_error(const char *fmt, ...);
@@ -110,8 +119,15 @@ extern long long g_ssb_launches;   // kernels launched by this library (bench.py
 // launchers implemented across the .cu files --------------------------------
 int ssb_launch_prep(const SsbDims &d, const float *dets, int n, int h, int w,
                     FrameScratch fs, cudaStream_t st);
-int ssb_launch_track_frame(ssb_tracker *t, int n, int h, int w, const float *feats,
+int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const float *feats,
                            double *out, int *counts, int track_hint, cudaStream_t st);
+inline FrameScratch ssb_slot_view(const ssb_tracker *t, int slot) {
+    FrameScratch f = t->fs;
+    const DetSlot &d = t->slot[slot & 1];
+    f.det_tlwh = d.det_tlwh; f.det_xyah = d.det_xyah; f.det_box = d.det_box;
+    f.det_conf = d.det_conf; f.det_cls = d.det_cls; f.feats = d.feats; f.det_norm = d.det_norm;
+    return f;
+}
 int ssb_launch_appearance(const float *gallery, const int *gal_count, const int *gal_head,
                           const int *row_slot_list, const int *order, const int *n_rows_dev,
                           int max_rows, int budget, const float *feats, int n_dets, int dim,

@@ -258,11 +258,67 @@ __device__ void kf_update_thread(double *mean, double *cov, const float *xyah, d
         }
 }
 
+// KalmanFilter.update, one warp per track: lanes 0..7 own the rows of the gain K,
+// every lane owns two covariance entries.  Same expression order as the
+// single-thread version (and as the oracle): K = P H^T S^-1 by Cholesky solves,
+// cov - K (S K^T).
+__device__ void kf_update_warp(double *mean, double *cov, const float *xyah, double conf, int lane,
+                               double *s_K /* [32] shared */) {
+    double mu[4], S[4][4], L[4][4];
+    kf_project(mean, cov, conf, mu, S);
+    chol4(S, L);
+    const double m_old = lane < 8 ? mean[lane] : 0.0;
+    double pold[2];
+    pold[0] = cov[lane];
+    pold[1] = cov[lane + 32];
+    if (lane < 8) {
+        double y[4], kr[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            double t = cov[lane * 8 + r];
+#pragma unroll
+            for (int k = 0; k < r; k++) t -= L[r][k] * y[k];
+            y[r] = t / L[r][r];
+        }
+#pragma unroll
+        for (int r = 3; r >= 0; r--) {
+            double t = y[r];
+#pragma unroll
+            for (int k = r + 1; k < 4; k++) t -= L[k][r] * kr[k];
+            kr[r] = t / L[r][r];
+        }
+#pragma unroll
+        for (int r = 0; r < 4; r++) s_K[lane * 4 + r] = kr[r];
+    }
+    __syncwarp();
+    if (lane < 8) {
+        double t = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) t += ((double)xyah[j] - mu[j]) * s_K[lane * 4 + j];
+        mean[lane] = m_old + t;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        const int e = lane + 32 * r, i = e >> 3, j = e & 7;
+        double acc = 0;
+#pragma unroll
+        for (int a = 0; a < 4; a++) {
+            double skt = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++) skt += S[a][b] * s_K[j * 4 + b];
+            acc += s_K[i * 4 + a] * skt;
+        }
+        cov[e] = pold[r] - acc;
+    }
+}
+
 __global__ void kf_update_arrays_kernel(double *mean, double *cov, const float *xyah,
                                         const float *conf, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    kf_update_thread(mean + (size_t)i * 8, cov + (size_t)i * 64, xyah + i * 4, (double)conf[i]);
+    __shared__ double s_K[4][32];
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    kf_update_warp(mean + (size_t)w * 8, cov + (size_t)w * 64, xyah + w * 4, (double)conf[w], lane,
+                   s_K[(threadIdx.x >> 5) & 3]);
 }
 
 // squared Mahalanobis distance of all measurements to one projected track
@@ -813,6 +869,7 @@ __device__ double block_sum_f64(double v, double *s_red) {
 
 __global__ void update_matched_kernel(TrackTable tt, FrameScratch fs, SsbDims d) {
     __shared__ double s_red[32];
+    __shared__ double s_K[32];
     const int k = blockIdx.x;
     if (k >= fs.cnt[FC_N_MATCH]) return;
     const int pos = fs.match_trk[k], det = fs.match_det[k];
@@ -832,9 +889,10 @@ __global__ void update_matched_kernel(TrackTable tt, FrameScratch fs, SsbDims d)
     const double tot = block_sum_f64(acc, s_red);
     const float n2 = (float)sqrt(tot);
     for (int i = threadIdx.x; i < D; i += blockDim.x) tf[i] = tf[i] / n2;
+    if (threadIdx.x < 32)
+        kf_update_warp(tt.mean + (size_t)s * 8, tt.cov + (size_t)s * 64, fs.det_xyah + det * 4,
+                       (double)fs.det_conf[det], threadIdx.x, s_K);
     if (threadIdx.x == 0) {
-        kf_update_thread(tt.mean + (size_t)s * 8, tt.cov + (size_t)s * 64,
-                         fs.det_xyah + det * 4, (double)fs.det_conf[det]);
         tt.conf[s] = fs.det_conf[det];
         tt.cls[s] = (int)fs.det_cls[det];
         tt.last_det[s] = det;
@@ -1060,12 +1118,12 @@ int ssb_launch_prep(const SsbDims &d, const float *dets, int n, int h, int w, Fr
     return 0;
 }
 
-int ssb_launch_track_frame(ssb_tracker *t, int n, int h, int w, const float *feats, double *out,
+int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const float *feats, double *out,
                            int *counts, int track_hint, cudaStream_t st) {
     const SsbDims &d = t->dims;
     TrackTable tt = t->tt;
-    FrameScratch fs = t->fs;
-    fs.feats = const_cast<float *>(feats);
+    FrameScratch fs = ssb_slot_view(t, slot);
+    if (feats) fs.feats = const_cast<float *>(feats);
     const int Tmax = (track_hint >= 0 && track_hint <= d.S) ? track_hint : d.S;
     const int L = d.S > d.N ? d.S : d.N;
     size_t dyn = 0, cost_b = 0;
@@ -1132,7 +1190,7 @@ extern "C" int ssb_kf_predict(double *mean_dev, double *cov_dev, int n, ssb_stre
 extern "C" int ssb_kf_update(double *mean_dev, double *cov_dev, const float *xyah_dev,
                              const float *conf_dev, int n, ssb_stream_t stream) {
     if (n <= 0) return 0;
-    kf_update_arrays_kernel<<<(n + 63) / 64, 64, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, xyah_dev, conf_dev, n);
+    kf_update_arrays_kernel<<<(n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, xyah_dev, conf_dev, n);
     SSB_CHECK_LAUNCH();
     return 0;
 }

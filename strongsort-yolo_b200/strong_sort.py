@@ -220,6 +220,96 @@ class StrongSORT:
         self.stream.synchronize()
         return out.cpu().numpy()
 
+    # ------------------------------------------------------------------
+    # two-stage pipeline: embedding of frame k overlaps the association of frame k-1
+    # ------------------------------------------------------------------
+    def _pipe_init(self):
+        torch = self._torch
+        with torch.cuda.device(self.device):
+            self._pstream = torch.cuda.Stream(device=self.device)          # embedding stage
+            N = self.cfg.max_dets
+            self._p_dets = [torch.empty((N, 6), dtype=torch.float32, device=self.device) for _ in range(2)]
+            self._p_dets_pin = [torch.empty((N, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
+            self._p_img = [None, None]
+            self._p_out = [torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
+            self._p_pin = [torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._p_embed_done = [torch.cuda.Event() for _ in range(2)]
+            self._p_assoc_done = [torch.cuda.Event() for _ in range(2)]
+        self._p_k = 0
+        self._p_meta = [None, None]
+
+    def _pipe_collect(self, slot):
+        """Wait for the association of the frame in `slot`; return its rows."""
+        self._p_assoc_done[slot].synchronize()
+        buf = self._p_pin[slot].numpy()
+        cnt = buf[:32].view(np.int32)
+        self.last_counts = cnt.copy()
+        if cnt[CNT_ERROR]:
+            raise _lib.SsbError("track table overflow: raise max_tracks / max_dets")
+        self._track_hint = int(cnt[CNT_TRACKS])
+        m = int(cnt[CNT_OUT_ROWS])
+        rows = buf[_HDR_BYTES:].view(np.float64).reshape(-1, _lib.SSB_OUT_COLS)[:m].copy()
+        self.last_det_index = rows[:, 7].astype(np.int64)
+        return rows[:, :7]
+
+    def update_pipelined(self, dets, ori_img):
+        """Same arguments as ``update``; returns the rows of the PREVIOUS frame (None on the
+        first call) -- one frame of latency buys the overlap of this frame's OSNet with the
+        previous frame's association on a second stream.  ``flush_pipelined()`` returns the
+        rows of the last submitted frame.  Results are identical to ``update``."""
+        torch = self._torch
+        if not hasattr(self, "_pstream"):
+            self._pipe_init()
+        k, slot = self._p_k, self._p_k & 1
+        if torch.is_tensor(dets):
+            d = dets.detach().reshape(-1, 6).to(torch.float32)
+        else:
+            d = torch.from_numpy(np.ascontiguousarray(np.asarray(dets, dtype=np.float32))).reshape(-1, 6)
+        n = int(d.shape[0])
+        if n > self.cfg.max_dets:
+            raise ValueError(f"{n} detections exceed max_dets={self.cfg.max_dets}")
+        H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
+        with torch.cuda.device(self.device), torch.cuda.stream(self._pstream):
+            self._pstream.wait_event(self._p_assoc_done[slot])       # slot free (frame k-2 associated)
+            if n:
+                if d.is_cuda:
+                    self._p_dets[slot][:n].copy_(d, non_blocking=True)
+                else:
+                    self._p_dets_pin[slot][:n].copy_(d)
+                    self._p_dets[slot][:n].copy_(self._p_dets_pin[slot][:n], non_blocking=True)
+            img_dev = None
+            if n:
+                if torch.is_tensor(ori_img) and ori_img.is_cuda:
+                    self._pstream.wait_stream(torch.cuda.current_stream(self.device))
+                    img_dev = ori_img.contiguous()
+                else:
+                    src = ori_img if torch.is_tensor(ori_img) else torch.from_numpy(np.ascontiguousarray(ori_img))
+                    if self._p_img[slot] is None or tuple(self._p_img[slot].shape) != tuple(src.shape):
+                        self._p_img[slot] = torch.empty(tuple(src.shape), dtype=torch.uint8, device=self.device)
+                    self._p_img[slot].copy_(src, non_blocking=True)
+                    img_dev = self._p_img[slot]
+            _lib.check(self._lib.ssb_embed(self._h, slot, _lib.ptr(self._p_dets[slot]), n,
+                                           _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
+                                           C.c_void_p(self._pstream.cuda_stream)), "ssb_embed")
+            self._p_embed_done[slot].record(self._pstream)
+        # the previous frame finishes while this frame's embeddings are computed
+        prev = self._pipe_collect(slot ^ 1) if k > 0 else None
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self.stream.wait_event(self._p_embed_done[slot])
+            _lib.check(self._lib.ssb_associate(
+                self._h, slot, n, H, W, None, C.c_void_p(self._p_out[slot].data_ptr() + _HDR_BYTES),
+                _lib.ptr(self._p_out[slot]), self._track_hint, C.c_void_p(self.stream.cuda_stream)),
+                "ssb_associate")
+            self._p_pin[slot].copy_(self._p_out[slot], non_blocking=True)
+            self._p_assoc_done[slot].record(self.stream)
+        self._p_k = k + 1
+        return prev
+
+    def flush_pipelined(self):
+        if not hasattr(self, "_pstream") or self._p_k == 0:
+            return None
+        return self._pipe_collect((self._p_k - 1) & 1)
+
     def export_tracks(self):
         """Live track table in list order (== Tracker.tracks of the oracle)."""
         torch = self._torch

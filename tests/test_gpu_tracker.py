@@ -146,3 +146,23 @@ def test_c2_end_to_end_vs_oracle(oracle_extractor):
         assert_rows_equal(got, want)
     assert int(gpu.last_counts[3]) == ora.tracker._next_id
     assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-6, feat_tol=1e-3)
+
+
+def test_pipelined_update_equals_synchronous():
+    """update_pipelined (embedding of frame k overlapped with the association of frame
+    k-1 on a second stream, ssb_embed/ssb_associate) returns exactly what update returns."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1")
+    frames = [st.next_frame() for _ in range(10)]
+    a = StrongSORT(max_tracks=64, max_dets=32)
+    want = [a.update(f.dets, f.img) for f in frames]
+    b = StrongSORT(max_tracks=64, max_dets=32)
+    got = []
+    for f in frames:
+        r = b.update_pipelined(f.dets, f.img)
+        if r is not None:
+            got.append(r)
+    got.append(b.flush_pipelined())
+    assert len(got) == len(want)
+    for x, y in zip(got, want):
+        np.testing.assert_array_equal(x, y)
