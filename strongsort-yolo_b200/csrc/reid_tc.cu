@@ -54,7 +54,25 @@ struct BlkCfg {
     static constexpr int MAP_B = 2 * MAP_HALF_B;      // hi planes then lo planes
     static constexpr int IN_P0 = (1 + HALO) * WP, IN_P1 = (1 + HALO + R) * WP;
     static constexpr int IT0 = IN_P0 / 128, IT1 = (IN_P1 + 127) / 128, NIT = IT1 - IT0;
-    static constexpr int TM_LC = 0, TM_C3 = NT * MIDP;
+    // "trapezoid": a LightConv with r more LightConvs after it in its stream only has to be
+    // right on the rows within r of the band's own rows, so the M tiles wholly outside
+    // [own - r, own + r] are skipped (no MMAs, no drain) -- the halo recompute shrinks as the
+    // stream gets closer to its end.
+    __host__ __device__ static constexpr int tile_lo(int r) {
+        int row = 1 + HALO - r; if (row < 0) row = 0;
+        return (row * WP) / 128;
+    }
+    __host__ __device__ static constexpr int tile_hi(int r) {
+        int row = 1 + HALO + R + r; if (row > RH + 2) row = RH + 2;
+        int t = (row * WP + 127) / 128; return t > NT ? NT : t;
+    }
+    // CAT: the 3x3 / conv1 MMAs are bound by the shared-memory read of the A tile (4 KB per
+    // MMA, ~40 cycles, measured), so where TMEM has room the hi and lo weight rows are
+    // concatenated along N:  D[:, 0:M] += Ah*Bh (+ Al*Bh),  D[:, M:2M] += Ah*Bl  -- two A
+    // reads per product instead of three; the drain adds the two column halves.
+    static constexpr bool CAT = (NT * 2 * MIDP + NIT * COUT) <= 512;
+    static constexpr int LCN = CAT ? 2 * MIDP : MIDP;     // TMEM columns per 3x3 tile
+    static constexpr int TM_LC = 0, TM_C3 = NT * LCN;
     static constexpr int TM_COLS = TM_C3 + NIT * COUT;
     static constexpr int LCW_HALF_B = 9 * MIDP * MIDP * 2, LCW_B = 2 * LCW_HALF_B;
     static constexpr int C1W_HALF_B = CIN * MIDP * 2, C1W_B = 2 * C1W_HALF_B;
@@ -231,11 +249,30 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     // phase 1: X1 = relu(conv1(x)) on every band tile; downsample on inner tiles
     // ------------------------------------------------------------------
     constexpr uint32_t IDESC_MID = tc::make_idesc_f16(128, C::MIDP);
+    constexpr uint32_t IDESC_CAT = tc::make_idesc_f16(128, 2 * C::MIDP);
     constexpr uint32_t IDESC_OUT = tc::make_idesc_f16(128, C::COUT);
     const float *xin = x + (size_t)crop * C::H * C::W * C::CIN;
     // a waiter may lag an mbarrier by at most one phase, so every staging buffer has
     // its own barrier: tile t commits to bar_stg[t % NSTAGE] and is waited before reuse
     uint32_t stg_phase[2] = {0, 0};
+    // software pipeline over the x tiles: the global loads of tile t+1 are issued before the
+    // fence / barrier / MMA issue of tile t, so their latency is off the critical path
+    constexpr int F4 = C::CIN / 4;
+    constexpr int PER = (128 * F4) / OSB_THREADS;            // float4 items per thread per tile
+    static_assert((128 * F4) % OSB_THREADS == 0, "tile items divide the CTA");
+    float4 xr[PER];
+    auto load_tile = [&](int t) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int idx = tid + q * OSB_THREADS;
+            const int px = idx / F4, f4 = idx - px * F4;
+            int gr, gc;
+            xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (pixel_valid(t * 128 + px, gr, gc))
+                xr[q] = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
+        }
+    };
+    load_tile(0);
     for (int t = 0; t < C::NT; t++) {
         const int sb = t % C::NSTAGE;
         unsigned char *stg = sP + sb * C::STG_B;
@@ -244,14 +281,11 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             stg_phase[sb] ^= 1;
         }
         // stage tile t of x: [CIN/8][128][8] hi, then lo
-        constexpr int F4 = C::CIN / 4;
-#pragma unroll 4
-        for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int idx = tid + q * OSB_THREADS;
             const int px = idx / F4, f4 = idx - px * F4;
-            int gr, gc;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (pixel_valid(t * 128 + px, gr, gc))
-                v = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
+            const float4 v = xr[q];
             __align__(8) __half2 h[2], l[2];
             split_hl2(v.x, v.y, h[0], l[0]);
             split_hl2(v.z, v.w, h[1], l[1]);
@@ -259,6 +293,7 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
             *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
         }
+        if (t + 1 < C::NT) load_tile(t + 1);
         tc::fence_async_smem();
         if (t == 0) { if (!tc::mbar_wait(bar_w, w_phase)) ok = false; w_phase ^= 1; }
         tc::fence_before_sync();
@@ -267,13 +302,22 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         if (tid == 0) {
             const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(stg), 2048, 128);
             const uint64_t al0 = desc_adv(ah0, C::STG_HALF_B / 16);
-            const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), C::MIDP * 16, 128);
-            const uint64_t bl0 = desc_adv(bh0, C::C1W_HALF_B / 16);
-            const uint32_t d1 = tmem + C::TM_LC + t * C::MIDP;
+            const uint32_t d1 = tmem + C::TM_LC + t * C::LCN;
+            if (C::CAT) {
+                const uint64_t bc0 = tc::make_smem_desc(tc::smem_u32(sW1), 2 * C::MIDP * 16, 128);
 #pragma unroll
-            for (int ks = 0; ks < C::CIN / 16; ks++)
-                mma3(d1, desc_adv(ah0, ks * 256), desc_adv(al0, ks * 256), desc_adv(bh0, ks * 2 * C::MIDP),
-                     desc_adv(bl0, ks * 2 * C::MIDP), IDESC_MID, ks > 0);
+                for (int ks = 0; ks < C::CIN / 16; ks++) {
+                    tc::mma_f16_ss(d1, desc_adv(ah0, ks * 256), desc_adv(bc0, ks * 4 * C::MIDP), IDESC_CAT, ks > 0);
+                    tc::mma_f16_ss(d1, desc_adv(al0, ks * 256), desc_adv(bc0, ks * 4 * C::MIDP), IDESC_MID, 1);
+                }
+            } else {
+                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), C::MIDP * 16, 128);
+                const uint64_t bl0 = desc_adv(bh0, C::C1W_HALF_B / 16);
+#pragma unroll
+                for (int ks = 0; ks < C::CIN / 16; ks++)
+                    mma3(d1, desc_adv(ah0, ks * 256), desc_adv(al0, ks * 256), desc_adv(bh0, ks * 2 * C::MIDP),
+                         desc_adv(bl0, ks * 2 * C::MIDP), IDESC_MID, ks > 0);
+            }
             if (C::DOWN && t >= C::IT0 && t < C::IT1) {
                 const uint64_t dh0 = tc::make_smem_desc(tc::smem_u32(sW1) + C::C1W_B, C::COUT * 16, 128);
                 const uint64_t dl0 = desc_adv(dh0, C::DNW_HALF_B / 16);
@@ -299,23 +343,34 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
 
     // epilogue: TMEM tile -> (+bias, relu, zero-ring mask) -> hi/lo operand map.
     // GAPACC: also accumulate per-channel sums over the band's own inner pixels.
+    uint32_t tile_par_bits = 0;       // bit t: parity of bar_tile[t] (a barrier only flips in layers that use it)
+    auto tile_par_of = [&](int t) -> uint32_t { return (tile_par_bits >> t) & 1u; };
+    auto tile_used_advance = [&](int lo, int hi) { for (int t = lo; t < hi; t++) tile_par_bits ^= 1u << t; };
     // tile_bar != nullptr: tile t may be drained as soon as ITS MMAs have completed
     // (tile_bar[t], parity tile_par), while later tiles are still on the tensor pipe.
     auto drain_to_map = [&](unsigned char *dst, const float *bias, auto gapacc, float *gap,
-                            uint64_t *tile_bar, uint32_t tile_par) {
+                            uint64_t *tile_bar, uint32_t tile_par, int t_lo, int t_hi) {
         constexpr bool GAPACC = decltype(gapacc)::value;
         int jt = 0;
         for (int t = grp; t < C::NT; t += OSB_GROUPS, jt++) {
+            if (t < t_lo || t >= t_hi) continue;
             if (tile_bar) {
-                if (!tc::mbar_wait(tile_bar + t, tile_par)) ok = false;
+                if (!tc::mbar_wait(tile_bar + t, tile_par_of(t))) ok = false;
                 tc::fence_after_sync();
             }
+            (void)tile_par;
             const int p = t * 128 + quad * 32 + lane;
             const bool valid = (valid_m >> jt) & 1u;
             const bool own = (own_m >> jt) & 1u;
             unsigned char *d_hi = dst + (C::GUARD + p) * 16, *d_lo = d_hi + C::MAP_HALF_B;
             float v[C::MIDP];
-            tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_LC + t * C::MIDP, v);
+            tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_LC + t * C::LCN, v);
+            if (C::CAT) {
+                float w[C::MIDP];
+                tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_LC + t * C::LCN + C::MIDP, w);
+#pragma unroll
+                for (int j = 0; j < C::MIDP; j++) v[j] += w[j];
+            }
 #pragma unroll
             for (int c0 = 0; c0 < C::MIDP; c0 += 16) {
                 __align__(16) __half2 h[8];
@@ -341,7 +396,7 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     };
 
     stamp();                                   // [1] phase 1 (staging + conv1/down MMAs) done
-    drain_to_map(sX1, sPar + P::B1, FalseT{}, nullptr, nullptr, 0);
+    drain_to_map(sX1, sPar + P::B1, FalseT{}, nullptr, nullptr, 0, 0, C::NT);
     stamp();                                   // [2] X1 drained
 
     // ------------------------------------------------------------------
@@ -349,12 +404,15 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     // ------------------------------------------------------------------
     const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);      // [MIDP][COUT]
     int lc = 0;
-    uint32_t lc_par = 0, c3_par = 0;
+    uint32_t c3_par = 0;
     bool c3_pending = false;
     for (int s = 0; s < 4; s++) {
         const unsigned char *src = sX1;
         unsigned char *dst = sP;
         for (int k = 0; k <= s; k++, lc++) {
+            const int rem = s - k;                                // LightConvs after this one in the stream
+            const int t_lo = rem == 0 ? C::tile_lo(0) : rem == 1 ? C::tile_lo(1) : rem == 2 ? C::tile_lo(2) : C::tile_lo(3);
+            const int t_hi = rem == 0 ? C::tile_hi(0) : rem == 1 ? C::tile_hi(1) : rem == 2 ? C::tile_hi(2) : C::tile_hi(3);
             if (!tc::mbar_wait(bar_w, w_phase)) ok = false;       // this LightConv's weights landed
             w_phase ^= 1;
             tc::fence_after_sync();
@@ -364,11 +422,11 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             if (warp < 4 && lane == 0) {
                 const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(src) + C::GUARD * 16, C::PLANE_B, 128);
                 const uint64_t al0 = desc_adv(ah0, C::MAP_HALF_B / 16);
-                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), C::MIDP * 16, 128);
-                const uint64_t bl0 = desc_adv(bh0, C::LCW_HALF_B / 16);
+                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW1), (C::CAT ? 2 : 1) * C::MIDP * 16, 128);
+                const uint64_t bl0 = desc_adv(bh0, C::LCW_HALF_B / 16);       // (unused with CAT)
 #pragma unroll 1
-                for (int t = warp; t < C::NT; t += 4) {
-                    const uint32_t d = tmem + C::TM_LC + t * C::MIDP;
+                for (int t = t_lo + warp; t < t_hi; t += 4) {
+                    const uint32_t d = tmem + C::TM_LC + t * C::LCN;
                     const uint64_t aht = desc_adv(ah0, t * 128), alt = desc_adv(al0, t * 128);
 #pragma unroll
                     for (int tap = 0; tap < 9; tap++) {
@@ -376,9 +434,15 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
 #pragma unroll
                         for (int ks = 0; ks < C::MIDP / 16; ks++) {
                             const int ka = ks * 2 * C::MAP_PX;
-                            const int kb = (tap * C::MCH + ks * 2) * C::MIDP;
-                            mma3(d, desc_adv(aht, po + ka), desc_adv(alt, po + ka), desc_adv(bh0, kb),
-                                 desc_adv(bl0, kb), IDESC_MID, (tap | ks) != 0);
+                            if (C::CAT) {
+                                const int kb = (tap * C::MCH + ks * 2) * 2 * C::MIDP;
+                                tc::mma_f16_ss(d, desc_adv(aht, po + ka), desc_adv(bh0, kb), IDESC_CAT, (tap | ks) != 0);
+                                tc::mma_f16_ss(d, desc_adv(alt, po + ka), desc_adv(bh0, kb), IDESC_MID, 1);
+                            } else {
+                                const int kb = (tap * C::MCH + ks * 2) * C::MIDP;
+                                mma3(d, desc_adv(aht, po + ka), desc_adv(alt, po + ka), desc_adv(bh0, kb),
+                                     desc_adv(bl0, kb), IDESC_MID, (tap | ks) != 0);
+                            }
                         }
                     }
                     tc::mma_commit(bar_tile + t);
@@ -387,8 +451,8 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             // one otherwise lightly loaded thread waits for the whole layer and then refills
             // the weight buffer with the next LightConv's weights
             if (warp == 15 && lane == 0) {
-                for (int t = 0; t < C::NT; t++)
-                    if (!tc::mbar_wait(bar_tile + t, lc_par)) ok = false;
+                for (int t = t_lo; t < t_hi; t++)
+                    if (!tc::mbar_wait(bar_tile + t, tile_par_of(t))) ok = false;
                 if (lc + 1 < 10) {
                     tc::mbar_arrive_expect_tx(bar_w, C::LCW_B);
                     tc::bulk_g2s(sW1, wblob + C::G_LCW + (size_t)(lc + 1) * C::LCW_B, C::LCW_B, bar_w);
@@ -404,23 +468,34 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
             const bool last = (k == s);
             stamp();                           // LC issued (thread 0: its own tiles)
             if (!last) {
-                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, FalseT{}, nullptr, bar_tile, lc_par);
-                lc_par ^= 1;
+                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, FalseT{}, nullptr, bar_tile, 0, t_lo, t_hi);
+                tile_used_advance(t_lo, t_hi);
                 stamp();                       // LC drained
             } else {
                 float gap[C::MIDP];
 #pragma unroll
                 for (int j = 0; j < C::MIDP; j++) gap[j] = 0.f;
-                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, TrueT{}, gap, bar_tile, lc_par);
-                lc_par ^= 1;
+                drain_to_map(dst, sPar + P::BLC + lc * C::MIDP, TrueT{}, gap, bar_tile, 0, t_lo, t_hi);
+                tile_used_advance(t_lo, t_hi);
                 stamp();                       // last LC of the stream drained
                 // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid
+                // transpose-reduce over the warp: 31 (MIDP = 32) / 16 (MIDP = 16) shuffles in
+                // total instead of 5 per channel; lane c (c >> 1 for MIDP = 16) ends with channel c
 #pragma unroll
-                for (int j = 0; j < C::MIDP; j++) {
-                    float vs = gap[j];
+                for (int off = 16, nh = C::MIDP / 2; nh >= 1; off >>= 1, nh >>= 1) {
+                    const bool up = (lane & off) != 0;
 #pragma unroll
-                    for (int o = 16; o; o >>= 1) vs += __shfl_xor_sync(0xffffffffu, vs, o);
-                    if (lane == 0) s_scr[warp * C::MIDP + j] = vs;
+                    for (int j = 0; j < nh; j++) {
+                        const float send = up ? gap[j] : gap[j + nh];
+                        const float recv = __shfl_xor_sync(0xffffffffu, send, off);
+                        gap[j] = (up ? gap[j + nh] : gap[j]) + recv;
+                    }
+                }
+                if (C::MIDP == 16) {
+                    gap[0] += __shfl_xor_sync(0xffffffffu, gap[0], 1);
+                    if (!(lane & 1)) s_scr[warp * C::MIDP + (lane >> 1)] = gap[0];
+                } else {
+                    s_scr[warp * C::MIDP + lane] = gap[0];
                 }
                 __syncthreads();
                 if (tid < C::MIDP) {
@@ -506,34 +581,34 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     // final epilogue: y = relu(conv3 + bias (+ downsample already in TMEM) (+ x))
     // ------------------------------------------------------------------
     float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
-    for (int i = grp; i < C::NIT; i += OSB_GROUPS) {
+    constexpr int CCH = C::COUT / 32;                         // 32-column chunks per tile
+    for (int u = grp; u < C::NIT * CCH; u += OSB_GROUPS) {    // (tile, chunk) units over the 4 groups
+        const int i = u / CCH, c0 = (u - i * CCH) * 32;
         const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
         int gr, gc;
         const bool valid = pixel_valid(p, gr, gc);
         const int lr = p / C::WP;
         const bool own = valid && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R;
-#pragma unroll 1
-        for (int c0 = 0; c0 < C::COUT; c0 += 32) {
-            float v[32];
-            tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
-            if (own) {
-                float *o = yout + ((size_t)gr * C::W + gc) * C::COUT + c0;
-                const float *xr = xin + ((size_t)gr * C::W + gc) * C::CIN + c0;
+        float4 xv[8];
+        if (!C::DOWN && own) {                                // identity residual: issue the loads first
+            const float *xrow = xin + ((size_t)gr * C::W + gc) * C::CIN + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 r;
-                    r.x = v[j] + sPar[P::B3 + c0 + j];
-                    r.y = v[j + 1] + sPar[P::B3 + c0 + j + 1];
-                    r.z = v[j + 2] + sPar[P::B3 + c0 + j + 2];
-                    r.w = v[j + 3] + sPar[P::B3 + c0 + j + 3];
-                    if (!C::DOWN) {
-                        const float4 xv = *reinterpret_cast<const float4 *>(xr + j);
-                        r.x += xv.x; r.y += xv.y; r.z += xv.z; r.w += xv.w;
-                    }
-                    r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
-                    r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-                    *reinterpret_cast<float4 *>(o + j) = r;
+            for (int j = 0; j < 8; j++) xv[j] = *reinterpret_cast<const float4 *>(xrow + 4 * j);
+        }
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
+        if (own) {
+            float *o = yout + ((size_t)gr * C::W + gc) * C::COUT + c0;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 bb = *reinterpret_cast<const float4 *>(sPar + P::B3 + c0 + j);
+                float4 r = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+                if (!C::DOWN) {
+                    r.x += xv[j >> 2].x; r.y += xv[j >> 2].y; r.z += xv[j >> 2].z; r.w += xv[j >> 2].w;
                 }
+                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
+                r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+                *reinterpret_cast<float4 *>(o + j) = r;
             }
         }
     }

@@ -118,6 +118,9 @@ def pack(tensors):
 #            CIN MID MIDP COUT DOWN
 TC_BLOCKS = [(16, 16, 16, 64, True), (64, 16, 16, 64, False), (64, 24, 32, 96, True),
              (96, 24, 32, 96, False), (96, 32, 32, 128, True), (128, 32, 32, 128, False)]
+# BlkCfg::CAT of csrc/reid_tc.cu (TMEM has room for 2*MIDP columns per 3x3 tile): the conv1
+# and LightConv weights are then laid out [k/8][hi rows | lo rows][8] instead of hi block, lo block
+TC_CAT = [False, False, True, True, True, True]
 _STAGE = ["conv2.0", "conv2.1", "conv3.0", "conv3.1", "conv4.0", "conv4.1"]
 _LC = ["conv2a", "conv2b.0", "conv2b.1", "conv2c.0", "conv2c.1", "conv2c.2",
        "conv2d.0", "conv2d.1", "conv2d.2", "conv2d.3"]
@@ -140,6 +143,14 @@ def _b_layout(w_kn):
     return hi.tobytes() + lo.tobytes()
 
 
+def _b_layout_cat(w_kn):
+    """N-concatenated B operand: W[k][n] -> bytes of [k/8][n (hi) then n (lo)][8]."""
+    K, N = w_kn.shape
+    t = np.ascontiguousarray(w_kn.reshape(K // 8, 8, N).transpose(0, 2, 1))   # [kc][n][8]
+    hi, lo = _hi_lo(t)
+    return np.concatenate([hi, lo], axis=1).tobytes()
+
+
 def _pad128(b):
     return b + b"\0" * ((-len(b)) % 128)
 
@@ -151,8 +162,9 @@ def pack_tc(tensors):
     for bi, (cin, mid, midp, cout, down) in enumerate(TC_BLOCKS):
         p = _STAGE[bi]
         sec = b""
+        lay = _b_layout_cat if TC_CAT[bi] else _b_layout
         w = np.zeros((cin, midp)); w[:, :mid] = T[f"{p}.conv1.w"]
-        sec += _b_layout(w)                                                    # C1W
+        sec += lay(w)                                                          # C1W
         if down:
             sec += _b_layout(T[f"{p}.down.w"].astype(np.float64))              # DNW [cin][cout]
         for nm in _LC:                                                         # LCW x 10
@@ -161,7 +173,7 @@ def pack_tc(tensors):
             dw = T[q + ".dw"].astype(np.float64)                               # [tap][c]
             wd = np.zeros((9, midp, midp))                                     # [tap][ci][c]
             wd[:, :mid, :mid] = dw[:, None, :] * pw[None, :, :]
-            sec += _b_layout(wd.reshape(9 * midp, midp))
+            sec += lay(wd.reshape(9 * midp, midp))
         par = np.zeros(midp + 10 * midp + cout + 2 * midp + 2 + 2 * midp + midp, dtype=np.float32)
         o = 0
         par[o:o + mid] = T[f"{p}.conv1.b"]; o += midp

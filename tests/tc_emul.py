@@ -44,6 +44,12 @@ def _b_operand(raw, K, N):
     return (hi + lo).transpose(0, 2, 1).reshape(K, N)
 
 
+def _b_operand_cat(raw, K, N):
+    """bytes of [K/8][N hi rows | N lo rows][8] -> float64 W[k][n]."""
+    a = np.frombuffer(raw[:K * N * 4], dtype=np.float16).reshape(K // 8, 2 * N, 8).astype(np.float64)
+    return (a[:, :N] + a[:, N:]).transpose(0, 2, 1).reshape(K, N)
+
+
 def _hl(v):
     """operand rounding: fp32 -> fp16 hi + fp16 lo (as float64)."""
     v32 = np.asarray(v, dtype=np.float32)
@@ -56,9 +62,10 @@ def osblock_emul(b, x, blob, offs):
     """x: float32 [n,H,W,cin] -> float32 [n,H,W,cout], band by band like the kernel."""
     c = Cfg(b)
     sec = bytes(blob[int(offs[b]):int(offs[b + 1])])
-    W1 = _b_operand(sec[0:c.C1W_B], c.CIN, c.MIDP)
+    bop = _b_operand_cat if weights.TC_CAT[b] else _b_operand
+    W1 = bop(sec[0:c.C1W_B], c.CIN, c.MIDP)
     WD = _b_operand(sec[c.C1W_B:c.C1W_B + c.DNW_B], c.CIN, c.COUT) if c.DOWN else None
-    LCW = [_b_operand(sec[c.G_LCW + l * c.LCW_B:c.G_LCW + (l + 1) * c.LCW_B], 9 * c.MIDP, c.MIDP)
+    LCW = [bop(sec[c.G_LCW + l * c.LCW_B:c.G_LCW + (l + 1) * c.LCW_B], 9 * c.MIDP, c.MIDP)
            for l in range(10)]
     par = np.frombuffer(sec[c.G_PAR:c.G_PAR + c.NPAR * 4], dtype=np.float32).astype(np.float64)
     o = 0
@@ -96,15 +103,30 @@ def osblock_emul(b, x, blob, offs):
 
             X1, _ = to_map(acc1, b1)
             bands.append(dict(valid=valid, own=own, GR=GR, GC=GC, X1=X1, accd=accd, streams=[]))
-        # streams: all bands of the crop advance together (cluster)
+        # streams: all bands of the crop advance together (cluster).  P/Q are persistent
+        # per-band maps; a LightConv with `rem` successors only updates the tiles
+        # [tile_lo(rem), tile_hi(rem)) ("trapezoid"), the rest keeps stale content.
+        def t_lo(r):
+            return (max(0, 1 + c.HALO - r) * c.WP) // 128
+
+        def t_hi(r):
+            row = min(1 + c.HALO + c.R + r, c.RH + 2)
+            return min(c.NT, (row * c.WP + 127) // 128)
+
+        for bd in bands:
+            bd["P"] = np.full((c.MAP_PX, c.MIDP), 7.25)      # stale / uninitialised content
+            bd["Q"] = np.full((c.MAP_PX, c.MIDP), -3.5)
         c3 = [np.zeros((c.NT * 128, c.COUT)) + (bd["accd"] if c.DOWN else 0.0) for bd in bands]
         lc = 0
         for s in range(4):
-            srcs = [bd["X1"] for bd in bands]
+            src_name, dst_name = "X1", "P"
             fs = None
             for k in range(s + 1):
-                new_srcs, fs = [], []
-                for bd, src in zip(bands, srcs):
+                rem = s - k
+                lo, hi = t_lo(rem) * 128, t_hi(rem) * 128
+                fs = []
+                for bd in bands:
+                    src = bd[src_name]
                     acc = np.zeros((c.NT * 128, c.MIDP))
                     for tap in range(9):
                         off = (tap // 3 - 1) * c.WP + (tap % 3 - 1)
@@ -113,19 +135,20 @@ def osblock_emul(b, x, blob, offs):
                         acc += a @ LCW[lc][tap * c.MIDP:(tap + 1) * c.MIDP]
                     valid = bd["valid"]
                     f = np.where(valid[:, None], np.maximum(acc + blc[lc], 0.0), 0.0).astype(np.float32)
-                    m = np.full((c.MAP_PX, c.MIDP), np.nan)
-                    m[c.GUARD:c.GUARD + c.NT * 128] = _hl(f)
-                    new_srcs.append(m); fs.append(f)
-                srcs = new_srcs
+                    bd[dst_name][c.GUARD + lo:c.GUARD + hi] = _hl(f)[lo:hi]
+                    fs.append(f)
+                src_name, dst_name = dst_name, ("Q" if dst_name == "P" else "P")
                 lc += 1
+            srcs = [bd[src_name] for bd in bands]
             tot = sum(f[bd["own"]].astype(np.float64).sum(0) for f, bd in zip(fs, bands))
             mean = tot / (c.H * c.W)
             h = np.maximum(gb1 + mean @ gw1, 0.0)
             g = 1.0 / (1.0 + np.exp(-(gb2 + h @ gw2)))
             W3g = _hl(W3 * g[:, None])
             for i, (bd, m) in enumerate(zip(bands, srcs)):
-                a = m[c.GUARD:c.GUARD + c.NT * 128]
-                a = np.where(np.isnan(a), 0.0, a)
+                a = m[c.GUARD:c.GUARD + c.NT * 128].copy()
+                a[:c.IT0 * 128] = 0.0                                # conv3 only runs on the inner tiles
+                a[c.IT1 * 128:] = 0.0
                 c3[i] += a @ W3g
         for bd, acc in zip(bands, c3):
             own = bd["own"].copy()
