@@ -218,9 +218,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    from strongsort_yolo_b200 import dist as ssb_dist
     if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=device)
+        ssb_dist.init("nccl", device)
     import __graft_entry__ as ge
     if not os.path.exists(os.path.join(ROOT, "strongsort-yolo_b200", "libssb.so")):
         if local_rank == 0:
@@ -246,11 +246,7 @@ def main():
             torch.cuda.synchronize()
 
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device=device)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return ssb_dist.max_over_ranks(x, device)
 
     # ---------------- value: device-resident inputs, per-step events ----------
     trk = StrongSORT(device=str(device))
