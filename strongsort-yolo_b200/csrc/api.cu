@@ -64,7 +64,7 @@ struct Carver {
 
 static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratch *fs,
                     float **reid_ws, int64_t *reid_floats, int **boxes_tmp, int **tc_status = nullptr,
-                    DetSlot *slot1 = nullptr) {
+                    DetSlot *slot1 = nullptr, float **reid_ws1 = nullptr) {
     const size_t S = c->max_tracks, N = c->max_dets, B = c->nn_budget, D = c->feat_dim;
     const size_t L = S > N ? S : N;
     Carver k{base, 0};
@@ -99,6 +99,8 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     f.lsap_ws = k.take<double>(16);
     const int64_t rf = ssb_reid_ws_floats((int)N);
     float *rw = k.take<float>((size_t)rf);
+    float *rw1 = k.take<float>((size_t)rf);
+    if (reid_ws1) *reid_ws1 = rw1;
     int *bt = k.take<int>(N * 4);
     int *tcs = k.take<int>(64);
     if (tc_status) *tc_status = tcs;
@@ -137,7 +139,7 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
     t->ws_base = (char *)workspace_dev;
     t->ws_bytes = workspace_bytes;
     carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp, &t->tc_status,
-          &t->slot[1]);
+          &t->slot[1], &t->reid_ws1);
     t->slot[0] = DetSlot{t->fs.det_tlwh, t->fs.det_xyah, t->fs.det_box, t->fs.det_conf, t->fs.det_cls,
                          t->fs.feats, t->fs.det_norm};
     SsbDims &d = t->dims;
@@ -179,7 +181,7 @@ extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n,
     if (!img_dev) return 0;                         // caller supplies embeddings to ssb_associate
     if (pitch < 3 * w) { ssb_set_error("bad pitch"); return -1; }
     if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
-    return ssb_reid_forward(t, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
+    return ssb_reid_forward(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
 }
 
 // stage 2: association + track-table update from the detections/embeddings of `slot`
@@ -207,7 +209,7 @@ extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, in
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
     if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
     if (n == 0) return 0;
-    return ssb_reid_forward(t, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
+    return ssb_reid_forward(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
 }
 
 extern "C" int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, int32_t *hits,

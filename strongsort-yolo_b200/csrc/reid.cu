@@ -402,8 +402,8 @@ static int block_tensor_index(int b) {
 
 struct ReidBufs { float *DS, *X1, *T0, *T1, *PW, *X2, *GATE; };
 
-static ReidBufs reid_bufs(ssb_tracker *t, int n, float **A, float **Bf) {
-    float *ws = t->reid_ws;
+static ReidBufs reid_bufs(ssb_tracker *t, int slot, int n, float **A, float **Bf) {
+    float *ws = (slot & 1) ? t->reid_ws1 : t->reid_ws;
     const size_t N = (size_t)n;
     ReidBufs r;
     *A = ws;      ws += N * REID_BIG;
@@ -474,14 +474,14 @@ static int reid_block(ssb_tracker *t, int b, const float *cur, float *nxt, int n
     return reid_block_simt(t, b, cur, nxt, n, Hc, Wc, B, st);
 }
 
-int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
                      int n, float *feats_out, cudaStream_t st) {
     if (n <= 0) return 0;
     { int rc = reid_init_attrs(); if (rc) return rc; }
     const float *W = t->w_blob;
     const int64_t *off = t->w_off;
     float *A, *Bf;
-    const ReidBufs B = reid_bufs(t, n, &A, &Bf);
+    const ReidBufs B = reid_bufs(t, slot, n, &A, &Bf);
     if (t->use_tc) {        // stem as 16 shifted GEMMs on the space-to-depth image (reid_tc.cu)
         int rc = ssb_reid_tc_stem(img, h, w, pitch, boxes, t->w_tc + t->w_tc_off[9], A, n, t->tc_status, st);
         if (rc) return rc;
@@ -573,7 +573,7 @@ extern "C" int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, flo
     if (!t->w_blob) { ssb_set_error("ReID weights not set"); return -1; }
     { int rc = reid_init_attrs(); if (rc) return rc; }
     float *A, *Bf;
-    const ReidBufs B = reid_bufs(t, n, &A, &Bf);
+    const ReidBufs B = reid_bufs(t, 0, n, &A, &Bf);
     const int Hc = block < 2 ? 64 : (block < 4 ? 32 : 16), Wc = Hc / 2;
     return reid_block(t, block, x_dev, y_dev, n, Hc, Wc, B, use_tc, (cudaStream_t)stream);
 }

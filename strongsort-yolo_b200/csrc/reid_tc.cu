@@ -580,8 +580,15 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     // ------------------------------------------------------------------
     // final epilogue: y = relu(conv3 + bias (+ downsample already in TMEM) (+ x))
     // ------------------------------------------------------------------
+    // Every thread owns one pixel row of 32 channels (128 B); written straight from the
+    // registers that is 32 different cache lines per store instruction (the epilogue was
+    // LSU-wavefront bound: 3.8 K cycles per unit).  Rows are therefore transposed through a
+    // warp-private staging tile in the (now dead) map area so that 8 lanes cover one row:
+    // 4 full lines per instruction, for the residual loads as well as for the stores.
     float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
     constexpr int CCH = C::COUT / 32;                         // 32-column chunks per tile
+    float *stage = reinterpret_cast<float *>(sX1) + warp * (32 * 36);
+    static_assert(16 * 32 * 36 * 4 <= 3 * C::MAP_B, "staging tiles fit in the dead maps");
     for (int u = grp; u < C::NIT * CCH; u += OSB_GROUPS) {    // (tile, chunk) units over the 4 groups
         const int i = u / CCH, c0 = (u - i * CCH) * 32;
         const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
@@ -589,28 +596,42 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         const bool valid = pixel_valid(p, gr, gc);
         const int lr = p / C::WP;
         const bool own = valid && lr >= 1 + C::HALO && lr < 1 + C::HALO + C::R;
-        float4 xv[8];
-        if (!C::DOWN && own) {                                // identity residual: issue the loads first
-            const float *xrow = xin + ((size_t)gr * C::W + gc) * C::CIN + c0;
+        const int rowoff = own ? gr * C::W + gc : -1;
+        if (!C::DOWN) {                                       // identity residual, coalesced
 #pragma unroll
-            for (int j = 0; j < 8; j++) xv[j] = *reinterpret_cast<const float4 *>(xrow + 4 * j);
+            for (int it = 0; it < 8; it++) {
+                const int row = it * 4 + (lane >> 3);
+                const int ro = __shfl_sync(0xffffffffu, rowoff, row);
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ro >= 0) x4 = *reinterpret_cast<const float4 *>(xin + (size_t)ro * C::CIN + c0 + (lane & 7) * 4);
+                *reinterpret_cast<float4 *>(stage + row * 36 + (lane & 7) * 4) = x4;
+            }
         }
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
-        if (own) {
-            float *o = yout + ((size_t)gr * C::W + gc) * C::COUT + c0;
+        __syncwarp();
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 bb = *reinterpret_cast<const float4 *>(sPar + P::B3 + c0 + j);
-                float4 r = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
-                if (!C::DOWN) {
-                    r.x += xv[j >> 2].x; r.y += xv[j >> 2].y; r.z += xv[j >> 2].z; r.w += xv[j >> 2].w;
-                }
-                r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
-                r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
-                *reinterpret_cast<float4 *>(o + j) = r;
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4 *>(sPar + P::B3 + c0 + j);
+            float4 r = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+            if (!C::DOWN) {
+                const float4 xv = *reinterpret_cast<const float4 *>(stage + lane * 36 + j);
+                r.x += xv.x; r.y += xv.y; r.z += xv.z; r.w += xv.w;
             }
+            r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
+            r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+            *reinterpret_cast<float4 *>(stage + lane * 36 + j) = r;      // own row only: no hazard
         }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int row = it * 4 + (lane >> 3);
+            const int ro = __shfl_sync(0xffffffffu, rowoff, row);
+            if (ro >= 0)
+                *reinterpret_cast<float4 *>(yout + (size_t)ro * C::COUT + c0 + (lane & 7) * 4) =
+                    *reinterpret_cast<const float4 *>(stage + row * 36 + (lane & 7) * 4);
+        }
+        __syncwarp();
     }
     stamp();                                   // final epilogue done
     if (dbg && blockIdx.x == 0 && tid == 0) dbg[0] = dbg_n;

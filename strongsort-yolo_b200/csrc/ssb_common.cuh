@@ -88,7 +88,8 @@ struct ssb_tracker {
     const float *w_blob;      // folded weights (device, caller-owned)
     int64_t *w_off;           // host: offsets per tensor
     int n_w;
-    float *reid_ws;           // activation workspace (device)
+    float *reid_ws;           // activation workspace of slot 0 (device)
+    float *reid_ws1;          // second activation workspace: embeddings of two frames may be in flight
     int64_t reid_ws_floats;
     int *boxes_tmp;           // [N][4]
     // tensor-core OSBlocks (reid_tc.cu): hi/lo fp16 operand blob, per-block offsets
@@ -132,7 +133,7 @@ int ssb_launch_appearance(const float *gallery, const int *gal_count, const int 
                           const int *row_slot_list, const int *order, const int *n_rows_dev,
                           int max_rows, int budget, const float *feats, int n_dets, int dim,
                           float *cost, int ld, cudaStream_t st);
-int ssb_reid_forward(ssb_tracker *t, const uint8_t *img, int h, int w, int pitch,
+int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch,
                      const int *boxes, int n, float *feats_out, cudaStream_t st);
 int64_t ssb_reid_ws_floats(int max_dets);
 int64_t ssb_reid_tc_block_bytes(int b);

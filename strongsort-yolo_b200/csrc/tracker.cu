@@ -519,9 +519,12 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
             const unsigned hmin = __reduce_min_sync(0xffffffffu, bk >= 0 ? hi : 0xffffffffu);
             const unsigned lmin = __reduce_min_sync(0xffffffffu, (bk >= 0 && hi == hmin) ? lo : 0xffffffffu);
             const bool vwin = bk >= 0 && hi == hmin && lo == lmin;
-            const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
-            const unsigned wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            unsigned wmask = __ballot_sync(0xffffffffu, vwin);
             if (wmask == 0) return false;
+            if (wmask & (wmask - 1)) {              // several lanes tie on the value: scipy's scan-order rule
+                const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
+                wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            }
             const int wl = __ffs(wmask) - 1;
             minVal = __shfl_sync(0xffffffffu, bv, wl);
             if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible

@@ -226,7 +226,10 @@ class StrongSORT:
     def _pipe_init(self):
         torch = self._torch
         with torch.cuda.device(self.device):
-            self._pstream = torch.cuda.Stream(device=self.device)          # embedding stage
+            # one embedding stream per slot: the OSNet launches of two consecutive frames may
+            # interleave on the GPU and fill each other's partial waves
+            self._pstreams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            self._pstream = self._pstreams[0]
             N = self.cfg.max_dets
             self._p_dets = [torch.empty((N, 6), dtype=torch.float32, device=self.device) for _ in range(2)]
             self._p_dets_pin = [torch.empty((N, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -269,8 +272,9 @@ class StrongSORT:
         if n > self.cfg.max_dets:
             raise ValueError(f"{n} detections exceed max_dets={self.cfg.max_dets}")
         H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
-        with torch.cuda.device(self.device), torch.cuda.stream(self._pstream):
-            self._pstream.wait_event(self._p_assoc_done[slot])       # slot free (frame k-2 associated)
+        pst = self._pstreams[slot]
+        with torch.cuda.device(self.device), torch.cuda.stream(pst):
+            pst.wait_event(self._p_assoc_done[slot])                  # slot free (frame k-2 associated)
             if n:
                 if d.is_cuda:
                     self._p_dets[slot][:n].copy_(d, non_blocking=True)
@@ -280,7 +284,7 @@ class StrongSORT:
             img_dev = None
             if n:
                 if torch.is_tensor(ori_img) and ori_img.is_cuda:
-                    self._pstream.wait_stream(torch.cuda.current_stream(self.device))
+                    pst.wait_stream(torch.cuda.current_stream(self.device))
                     img_dev = ori_img.contiguous()
                 else:
                     src = ori_img if torch.is_tensor(ori_img) else torch.from_numpy(np.ascontiguousarray(ori_img))
@@ -290,8 +294,8 @@ class StrongSORT:
                     img_dev = self._p_img[slot]
             _lib.check(self._lib.ssb_embed(self._h, slot, _lib.ptr(self._p_dets[slot]), n,
                                            _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
-                                           C.c_void_p(self._pstream.cuda_stream)), "ssb_embed")
-            self._p_embed_done[slot].record(self._pstream)
+                                           C.c_void_p(pst.cuda_stream)), "ssb_embed")
+            self._p_embed_done[slot].record(pst)
         # the previous frame finishes while this frame's embeddings are computed
         prev = self._pipe_collect(slot ^ 1) if k > 0 else None
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
