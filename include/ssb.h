@@ -81,11 +81,14 @@ int ssb_reid_num_tensors(void);
 int ssb_reid_tensor_sizes(int64_t *sizes);
 int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const int64_t *sizes, int n);
 
-/* tensor-core OSBlocks (csrc/reid_tc.cu): fp16 hi/lo operand blob built by
- * weights.pack_tc(); block_offsets[10] are byte offsets of the sections (6 OSBlocks,
- * 2 transition layers, tail, stem; each >= ssb_reid_tc_weight_bytes(i), 128-byte aligned).  Setting them switches
- * the OSBlocks of ssb_reid/ssb_update to the tcgen05 path; ssb_reid_use_tc(t,0)
- * switches back to the fp32 SIMT baseline. */
+/* tensor-core ReID (csrc/reid_tc.cu, csrc/reid_tc3.cu): fp16 hi/lo operand blob built by
+ * weights.pack_tc(); block_offsets[n_blocks] are byte offsets of the sections, each
+ * >= ssb_reid_tc_weight_bytes(i) bytes and 128-byte aligned: 0..5 OSBlocks with the LightConvs
+ * as 9 shifted GEMMs, 6..7 transition layers, 8 tail, 9 stem, and (n_blocks == 16) 10..15 the
+ * OSBlocks with pointwise-GEMM + fp32-depthwise LightConvs.  Setting them switches
+ * ssb_reid/ssb_update to the tcgen05 path (mode 2 when sections 10..15 are present, else 1);
+ * ssb_reid_use_tc(t, mode): 0 = fp32 SIMT baseline, 1 = 9-tap OSBlocks, 2 = pointwise/depthwise
+ * OSBlocks.  ssb_reid_block's use_tc takes the same mode values. */
 int64_t ssb_reid_tc_weight_bytes(int section);
 int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
                             int n_blocks);

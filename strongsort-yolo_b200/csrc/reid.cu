@@ -469,6 +469,10 @@ static int reid_block(ssb_tracker *t, int b, const float *cur, float *nxt, int n
                       const ReidBufs &B, int use_tc, cudaStream_t st) {
     if (use_tc) {
         if (!t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
+        if (use_tc == 2) {
+            if (!t->have_tc3) { ssb_set_error("pointwise/depthwise tensor-core weights (sections 10..15) not set"); return -1; }
+            return ssb_reid_tc3_block(b, cur, nxt, t->w_tc + t->w_tc_off[10 + b], n, t->tc_status, st);
+        }
         return ssb_reid_tc_block(b, cur, nxt, t->w_tc + t->w_tc_off[b], n, t->tc_status, st);
     }
     return reid_block_simt(t, b, cur, nxt, n, Hc, Wc, B, st);
@@ -535,17 +539,21 @@ int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w,
 
 // ---- tensor-core weights + single-block entry point (parity tests) ------------
 extern "C" int64_t ssb_reid_tc_weight_bytes(int section) {
+    if (section >= 10) return ssb_reid_tc3_block_bytes(section - 10);
     return section < 6 ? ssb_reid_tc_block_bytes(section) : ssb_reid_tc_aux_bytes(section - 6);
 }
 
 extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
                                        int n_blocks) {
     if (!t || !blob_dev || !block_offsets) { ssb_set_error("null argument"); return -1; }
-    if (n_blocks != 10) { ssb_set_error("expected 10 sections (6 OSBlocks, 2 transitions, tail, stem), got %d", n_blocks); return -1; }
-    for (int b = 0; b < 10; b++) {
+    if (n_blocks != 10 && n_blocks != 16) {
+        ssb_set_error("expected 10 sections (6 OSBlocks, 2 transitions, tail, stem) or 16 (+ 6 pointwise/depthwise OSBlocks), got %d", n_blocks);
+        return -1;
+    }
+    for (int b = 0; b < n_blocks; b++) {
         if (block_offsets[b] % 128 != 0) { ssb_set_error("section %d offset not 128-byte aligned", b); return -1; }
-        const int64_t need = b < 6 ? ssb_reid_tc_block_bytes(b) : ssb_reid_tc_aux_bytes(b - 6);
-        if (b < 9 && block_offsets[b + 1] - block_offsets[b] < need) {
+        const int64_t need = ssb_reid_tc_weight_bytes(b);
+        if (b < n_blocks - 1 && block_offsets[b + 1] - block_offsets[b] < need) {
             ssb_set_error("section %d too small", b);
             return -1;
         }
@@ -553,14 +561,17 @@ extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, con
     }
     if (((uintptr_t)blob_dev & 127) != 0) { ssb_set_error("tc blob must be 128-byte aligned"); return -1; }
     t->w_tc = (const unsigned char *)blob_dev;
-    t->use_tc = 1;
+    t->have_tc3 = n_blocks == 16;
+    t->use_tc = t->have_tc3 ? 2 : 1;
     return 0;
 }
 
 extern "C" int ssb_reid_use_tc(ssb_tracker *t, int enable) {
     if (!t) { ssb_set_error("null handle"); return -1; }
     if (enable && !t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
-    t->use_tc = enable ? 1 : 0;
+    if (enable < 0 || enable > 2) { ssb_set_error("ReID mode must be 0 (simt), 1 (tc, 9-tap) or 2 (tc, pointwise + depthwise)"); return -1; }
+    if (enable == 2 && !t->have_tc3) { ssb_set_error("pointwise/depthwise tensor-core weights (sections 10..15) not set"); return -1; }
+    t->use_tc = enable;
     return 0;
 }
 

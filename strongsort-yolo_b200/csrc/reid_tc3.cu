@@ -1,0 +1,639 @@
+// OSNet OSBlock, fused, second tensor-core formulation ("pwdw"), sm_100a.
+//
+// reid_tc.cu runs a LightConv3x3 (1x1 conv, then depthwise 3x3) as ONE dense 3x3 conv = 9
+// shifted tcgen05 GEMMs.  Measured (profiles/r01_tc_phases.md): every M=128, K=16 MMA costs
+// ~40 cycles whatever N is, because it is bound by the 4 KB shared-memory read of its A tile
+// -- so the 9 taps x (hi, lo) operand reads made the LightConv layers 55 % of the kernel.
+// Here the LightConv is split the way it is defined:
+//   * the pointwise 1x1 (the only real contraction) stays on the tensor cores: ONE tap,
+//     2 A-tile reads per tile and K step (hi/lo operands, N-concatenated weights);
+//   * the depthwise 3x3 runs on the CUDA cores in exact fp32 on the GEMM result: the TMEM
+//     accumulator is drained to a zero-ringed fp32 map T[c/4][row][col][4] in shared memory,
+//     a sliding 3-row register window per thread (2 columns x 4 channels) makes 2 float4
+//     loads per output float4, and the result (bias, ReLU, hi/lo split) is written straight
+//     into the next layer's K-major operand map.
+// Because no operand is shifted any more the maps need no zero ring / guard pixels:
+// pixel p = row * W + col, a band is a whole number of 128-row M tiles, the band's own
+// rows start on a tile boundary in stage 2, and all 10 LightConv weight sets (1-4 KB each
+// now) stay resident in shared memory after one bulk copy.
+//
+// Everything else follows reid_tc.cu: band of R rows (+HALO recomputed rows each side) of one
+// crop per CTA, the bands of a crop form a cluster (DSMEM reduction of the ChannelGate's
+// global average pool), gate folded into per-stream scaled copies of conv3's weights,
+// conv3 + downsample accumulated in TMEM, residual + ReLU in the final epilogue.
+#include <cooperative_groups.h>
+
+#include "ssb_common.cuh"
+#include "tc_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int K3_THREADS = 512;
+constexpr int K3_GROUPS = K3_THREADS / 128;
+
+__host__ __device__ constexpr int cmax(int a, int b) { return a > b ? a : b; }
+__host__ __device__ constexpr int rup128(int a) { return (a + 127) / 128 * 128; }
+
+template <int CIN_, int MID_, int MIDP_, int COUT_, int H_, int W_, int R_, int HALO_, int NB_,
+          bool DOWN_, int NSTAGE_, int SEG_>
+struct B3 {
+    static constexpr int CIN = CIN_, MID = MID_, MIDP = MIDP_, COUT = COUT_, H = H_, W = W_, R = R_;
+    static constexpr int HALO = HALO_, NB = NB_, NSTAGE = NSTAGE_, SEG = SEG_;
+    static constexpr bool DOWN = DOWN_;
+    static constexpr int RH = R + 2 * HALO;               // band rows kept (with halo)
+    static constexpr int NPX = RH * W;                    // band pixels, p = lr * W + col
+    static constexpr int NT = NPX / 128;                  // M tiles
+    static constexpr int OWN_P0 = HALO * W, OWN_P1 = (HALO + R) * W;
+    static constexpr int IT0 = OWN_P0 / 128, IT1 = (OWN_P1 + 127) / 128, NIT = IT1 - IT0;
+    static constexpr int MCH = MIDP / 8;                  // 16-byte K chunks per pixel
+    static constexpr int CG = MID / 4;                    // real float4 channel groups
+    static constexpr int XP = W / 2;                      // column pairs of the depthwise pass
+    static constexpr int PLANE_B = NPX * 16;              // LBO of a map operand
+    static constexpr int MAP_HALF_B = MCH * PLANE_B, MAP_B = 2 * MAP_HALF_B;   // hi planes, lo planes
+    static constexpr int TW = W + 2, TH = RH + 2, TPX = TW * TH;
+    static constexpr int T_B = CG * TPX * 16;             // fp32 pointwise result with zero ring
+    static constexpr int STG_HALF_B = (CIN / 8) * 128 * 16, STG_B = 2 * STG_HALF_B;
+    static constexpr int A_B = rup128(cmax(MAP_B + T_B, NSTAGE * STG_B));      // P map + T | x staging
+    static constexpr int LCN = 2 * MIDP;                  // TMEM columns of a pointwise tile (hi | lo weights)
+    static constexpr int TM_C3 = NT * LCN, TM_COLS = TM_C3 + NIT * COUT;
+    static constexpr int C1W_B = CIN * MIDP * 4;
+    static constexpr int DNW_HALF_B = DOWN ? CIN * COUT * 2 : 0, DNW_B = 2 * DNW_HALF_B;
+    static constexpr int LCW_B = MIDP * MIDP * 4;
+    static constexpr int WALL_B = C1W_B + DNW_B + 10 * LCW_B;
+    static constexpr int C3W_HALF_B = MIDP * COUT * 2, C3W_B = 2 * C3W_HALF_B;
+    // PAR (floats): B1[MIDP] | 10 x { DW[9][MIDP], B[MIDP] } | B3[COUT] | GW1[MIDP][2] | GB1[2] |
+    //               GW2[2][MIDP] | GB2[MIDP]
+    static constexpr int P_B1 = 0, P_LC = MIDP, P_B3 = P_LC + 100 * MIDP, P_GW1 = P_B3 + COUT;
+    static constexpr int P_GB1 = P_GW1 + 2 * MIDP, P_GW2 = P_GB1 + 2, P_GB2 = P_GW2 + 2 * MIDP;
+    static constexpr int NPAR = P_GB2 + MIDP;
+    // shared-memory carve-up (bytes)
+    static constexpr int OFF_X1 = 0;
+    static constexpr int OFF_A = OFF_X1 + MAP_B;
+    static constexpr int OFF_W = OFF_A + A_B;
+    static constexpr int OFF_C3 = OFF_W + rup128(WALL_B);
+    static constexpr int OFF_PAR = OFF_C3 + C3W_B;
+    static constexpr int OFF_GAP = OFF_PAR + rup128(NPAR * 4);       // [4][MIDP] floats
+    static constexpr int OFF_MISC = OFF_GAP + 4 * MIDP * 4;
+    static constexpr int SCR_FLOATS = SEG * CG * 4;
+    static constexpr int SMEM_B = OFF_MISC + 128 + (SCR_FLOATS + 2 * MIDP) * 4 + 64;
+    static_assert(NPX % 128 == 0, "band = whole M tiles");
+    static_assert((W & (W - 1)) == 0, "W power of two");
+    static_assert(NT <= 8, "per-tile barriers");
+    static_assert(TM_COLS <= 512, "TMEM columns");
+    static_assert(SMEM_B <= 232448, "shared memory");
+    static_assert(MIDP % 16 == 0 && COUT % 16 == 0 && CIN % 16 == 0 && MID % 4 == 0, "MMA shapes");
+    static_assert(H % R == 0 && H / R == NB, "bands");
+    static_assert(MID <= MIDP && COUT == 4 * MID, "OSBlock channel plan");
+    static_assert(SEG * CG * XP <= K3_THREADS, "depthwise tasks fit the CTA");
+    static_assert(16 * 32 * 36 * 4 <= OFF_C3, "final-epilogue staging fits in the dead maps/weights");
+    // global blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
+    static constexpr int G_PAR = rup128(WALL_B);
+    static constexpr int G_W3 = G_PAR + rup128(NPAR * 4);
+    static constexpr int G_TOTAL = G_W3 + MIDP * COUT * 4;
+};
+
+__device__ __forceinline__ void split2(float a, float b, __half2 &h, __half2 &l) {
+    h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    l = __floats2half2_rn(a - hf.x, b - hf.y);
+}
+__device__ __forceinline__ void split1(float v, __half &h, __half &l) {
+    h = __float2half_rn(v);
+    l = __float2half_rn(v - __half2float(h));
+}
+__device__ __forceinline__ uint64_t dadv(uint64_t base, int units16) {
+    return base + (uint64_t)(int64_t)units16;
+}
+__device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl,
+                                     uint32_t idesc, uint32_t acc) {
+    tc::mma_f16_ss(d, ah, bh, idesc, acc);
+    tc::mma_f16_ss(d, al, bh, idesc, 1);
+    tc::mma_f16_ss(d, ah, bl, idesc, 1);
+}
+// 4 consecutive TMEM columns of this warp's 32 lanes, no wait (pair with tmem_wait_ld)
+__device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void fma4(float4 &o, const float4 &w, const float4 &v) {
+    o.x = fmaf(w.x, v.x, o.x); o.y = fmaf(w.y, v.y, o.y);
+    o.z = fmaf(w.z, v.z, o.z); o.w = fmaf(w.w, v.w, o.w);
+}
+
+template <class C>
+__global__ void __launch_bounds__(K3_THREADS, 1)
+osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
+                const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status,
+                long long *__restrict__ dbg) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int quad = warp & 3, grp = warp >> 2;          // TMEM lane quadrant / work group
+    const int crop = blockIdx.x / C::NB, band = blockIdx.x % C::NB;
+    const int row0 = band * C::R - C::HALO;              // image row of band-local row 0
+
+    unsigned char *sX1 = smem + C::OFF_X1, *sP = smem + C::OFF_A;
+    float4 *sT = reinterpret_cast<float4 *>(sP + C::MAP_B);
+    unsigned char *sW = smem + C::OFF_W, *sC3 = smem + C::OFF_C3;
+    float *sPar = reinterpret_cast<float *>(smem + C::OFF_PAR);
+    float *sGap = reinterpret_cast<float *>(smem + C::OFF_GAP);      // [4][MIDP] band-partial sums
+    uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);
+    uint64_t *bar_stg = bar_w + 1;                     // [2] one per x-staging buffer
+    uint64_t *bar_tile = bar_w + 3;                    // [8] per M tile of the current pointwise conv
+    uint64_t *bar_c3 = bar_w + 11;                     // conv3 accumulation of the current stream
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_w + 12);
+    float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 128);   // [SEG][CG][4] partial sums
+    float *s_mean = s_scr + C::SCR_FLOATS;                                // [MIDP]
+    float *s_gate = s_mean + C::MIDP;                                     // [MIDP]
+
+    if (warp == 0) tc::tmem_alloc(s_tmem, 512);
+    if (tid == 0) {
+        tc::mbar_init(bar_w, 1);
+        tc::mbar_init(bar_stg, 1);
+        tc::mbar_init(bar_stg + 1, 1);
+        for (int i = 0; i < 8; i++) tc::mbar_init(bar_tile + i, 1);
+        tc::mbar_init(bar_c3, 1);
+        tc::fence_mbar_init();
+    }
+    for (int i = tid; i < C::NPAR; i += K3_THREADS)
+        sPar[i] = reinterpret_cast<const float *>(wblob + C::G_PAR)[i];
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = *s_tmem;
+    int dbg_n = 0;
+    auto stamp = [&]() { if (dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 63) dbg[1 + dbg_n++] = clock64(); };
+    stamp();
+    bool ok = true;
+
+    // every weight operand of the block (conv1, downsample, 10 pointwise sets) in one go
+    if (tid == 0) {
+        tc::mbar_arrive_expect_tx(bar_w, C::WALL_B);
+        for (int o = 0; o < C::WALL_B; o += 32768) {
+            const int nb = C::WALL_B - o < 32768 ? C::WALL_B - o : 32768;
+            tc::bulk_g2s(sW + o, wblob + o, nb, bar_w);
+        }
+    }
+
+    constexpr uint32_t IDESC_MID = tc::make_idesc_f16(128, C::MIDP);
+    constexpr uint32_t IDESC_CAT = tc::make_idesc_f16(128, 2 * C::MIDP);
+    constexpr uint32_t IDESC_OUT = tc::make_idesc_f16(128, C::COUT);
+
+    // ------------------------------------------------------------------
+    // phase 1: X1 = relu(conv1(x)) on every band tile; downsample on the own tiles
+    // ------------------------------------------------------------------
+    const float *xin = x + (size_t)crop * C::H * C::W * C::CIN;
+    uint32_t stg_phase[2] = {0, 0};
+    constexpr int F4 = C::CIN / 4;
+    constexpr int PER = (128 * F4) / K3_THREADS;             // float4 items per thread per tile
+    static_assert((128 * F4) % K3_THREADS == 0, "tile items divide the CTA");
+    float4 xr[PER];
+    auto load_tile = [&](int t) {
+#pragma unroll
+        for (int q = 0; q < PER; q++) {
+            const int idx = tid + q * K3_THREADS;
+            const int px = idx / F4, f4 = idx - px * F4;
+            const int p = t * 128 + px;
+            const int gr = row0 + p / C::W, gc = p % C::W;
+            xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr >= 0 && gr < C::H)
+                xr[q] = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
+        }
+    };
+    load_tile(0);
+    for (int t = 0; t < C::NT; t++) {
+        const int sb = t % C::NSTAGE;
+        unsigned char *stg = sP + sb * C::STG_B;
+        if (t >= C::NSTAGE) {                                // MMAs that read this buffer are done
+            if (!tc::mbar_wait(bar_stg + sb, stg_phase[sb])) ok = false;
+            stg_phase[sb] ^= 1;
+        }
+#pragma unroll
+        for (int q = 0; q < PER; q++) {                      // stage tile t of x: [CIN/8][128][8] hi, then lo
+            const int idx = tid + q * K3_THREADS;
+            const int px = idx / F4, f4 = idx - px * F4;
+            const float4 v = xr[q];
+            __align__(8) __half2 h[2], l[2];
+            split2(v.x, v.y, h[0], l[0]);
+            split2(v.z, v.w, h[1], l[1]);
+            const int off = (f4 >> 1) * 2048 + px * 16 + (f4 & 1) * 8;
+            *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
+            *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
+        }
+        if (t + 1 < C::NT) load_tile(t + 1);
+        tc::fence_async_smem();
+        if (t == 0) { if (!tc::mbar_wait(bar_w, 0)) ok = false; }
+        tc::fence_before_sync();
+        __syncthreads();
+        tc::fence_after_sync();
+        if (tid == 0) {
+            const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(stg), 2048, 128);
+            const uint64_t al0 = dadv(ah0, C::STG_HALF_B / 16);
+            const uint64_t bc0 = tc::make_smem_desc(tc::smem_u32(sW), 2 * C::MIDP * 16, 128);
+            const uint32_t d1 = tmem + t * C::LCN;
+#pragma unroll
+            for (int ks = 0; ks < C::CIN / 16; ks++) {
+                tc::mma_f16_ss(d1, dadv(ah0, ks * 256), dadv(bc0, ks * 4 * C::MIDP), IDESC_CAT, ks > 0);
+                tc::mma_f16_ss(d1, dadv(al0, ks * 256), dadv(bc0, ks * 4 * C::MIDP), IDESC_MID, 1);
+            }
+            if (C::DOWN && t >= C::IT0 && t < C::IT1) {
+                const uint64_t dh0 = tc::make_smem_desc(tc::smem_u32(sW) + C::C1W_B, C::COUT * 16, 128);
+                const uint64_t dl0 = dadv(dh0, C::DNW_HALF_B / 16);
+                const uint32_t d2 = tmem + C::TM_C3 + (t - C::IT0) * C::COUT;
+#pragma unroll
+                for (int ks = 0; ks < C::CIN / 16; ks++)
+                    mma3(d2, dadv(ah0, ks * 256), dadv(al0, ks * 256), dadv(dh0, ks * 2 * C::COUT),
+                         dadv(dl0, ks * 2 * C::COUT), IDESC_OUT, ks > 0);
+            }
+            tc::mma_commit(bar_stg + sb);
+        }
+    }
+    for (int sb = 0; sb < C::NSTAGE && sb < C::NT; sb++) {    // the last commit of every buffer
+        if (!tc::mbar_wait(bar_stg + sb, stg_phase[sb])) ok = false;
+        stg_phase[sb] ^= 1;
+    }
+    tc::fence_after_sync();
+    stamp();                                   // [1] phase 1 (staging + conv1/down MMAs) done
+
+    // the staging area becomes the P map (its pad-channel planes must read as zero) and T (zero ring)
+    for (int i = tid; i < (C::MAP_B + C::T_B) / 16; i += K3_THREADS)
+        reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // X1 epilogue: TMEM tile -> (+bias, relu, out-of-image mask) -> hi/lo operand map
+    for (int t = grp; t < C::NT; t += K3_GROUPS) {
+        const int p = t * 128 + quad * 32 + lane;
+        const int gr = row0 + p / C::W;
+        const bool valid = gr >= 0 && gr < C::H;
+        unsigned char *d_hi = sX1 + p * 16, *d_lo = d_hi + C::MAP_HALF_B;
+        float v[C::MIDP], w[C::MIDP];
+        tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN, v);
+        tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + C::MIDP, w);
+        const float *bias = sPar + C::P_B1;
+#pragma unroll
+        for (int c0 = 0; c0 < C::MIDP; c0 += 8) {
+            __align__(16) __half2 h[4];
+            __align__(16) __half2 l[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                const float f0 = valid ? fmaxf(v[c0 + j] + w[c0 + j] + bias[c0 + j], 0.f) : 0.f;
+                const float f1 = valid ? fmaxf(v[c0 + j + 1] + w[c0 + j + 1] + bias[c0 + j + 1], 0.f) : 0.f;
+                split2(f0, f1, h[j >> 1], l[j >> 1]);
+            }
+            *reinterpret_cast<uint4 *>(d_hi + (c0 >> 3) * C::PLANE_B) = *reinterpret_cast<uint4 *>(h);
+            *reinterpret_cast<uint4 *>(d_lo + (c0 >> 3) * C::PLANE_B) = *reinterpret_cast<uint4 *>(l);
+        }
+    }
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    stamp();                                   // [2] X1 drained
+
+    // ------------------------------------------------------------------
+    // phase 2: four streams of LightConvs (pointwise on tcgen05, depthwise on the CUDA cores)
+    //          + gated conv3 accumulation
+    // ------------------------------------------------------------------
+    auto issue_pw = [&](const unsigned char *src, int layer) {      // one thread
+        const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(src), C::PLANE_B, 128);
+        const uint64_t al0 = dadv(ah0, C::MAP_HALF_B / 16);
+        const uint64_t b0 = tc::make_smem_desc(tc::smem_u32(sW) + C::C1W_B + C::DNW_B + layer * C::LCW_B,
+                                               2 * C::MIDP * 16, 128);
+#pragma unroll
+        for (int t = 0; t < C::NT; t++) {
+            const uint32_t d = tmem + t * C::LCN;
+#pragma unroll
+            for (int ks = 0; ks < C::MIDP / 16; ks++) {
+                tc::mma_f16_ss(d, dadv(ah0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_CAT, ks > 0);
+                tc::mma_f16_ss(d, dadv(al0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_MID, 1);
+            }
+            tc::mma_commit(bar_tile + t);
+        }
+    };
+    const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);      // [MIDP][COUT]
+    // depthwise task of this thread: column pair xp, channel group cgi, row segment seg
+    const int dw_xp = tid % C::XP, dw_cg = (tid / C::XP) % C::CG, dw_seg = tid / (C::XP * C::CG);
+    int lc = 0;
+    uint32_t tile_par = 0, c3_par = 0;
+    bool c3_pending = false;
+    if (tid == 0) issue_pw(sX1, 0);
+    for (int s = 0; s < 4; s++) {
+        for (int k = 0; k <= s; k++, lc++) {
+            const int rem = s - k;                                // LightConvs after this one in the stream
+            const bool last = (k == s);
+            // ---- pointwise result: TMEM -> fp32 T (zero ring untouched), units (tile, channel group)
+            for (int u = grp; u < C::NT * C::CG; u += K3_GROUPS) {
+                const int t = u / C::CG, cgi = u - t * C::CG;
+                if (!tc::mbar_wait(bar_tile + t, tile_par)) ok = false;
+                tc::fence_after_sync();
+                const int p = t * 128 + quad * 32 + lane;
+                const int lr = p / C::W, col = p % C::W;
+                uint32_t a[4], b[4];
+                const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + cgi * 4;
+                tmem_ld4_nw(ta, a);
+                tmem_ld4_nw(ta + C::MIDP, b);
+                tmem_wait_ld();
+                sT[cgi * C::TPX + (lr + 1) * C::TW + col + 1] =
+                    make_float4(__uint_as_float(a[0]) + __uint_as_float(b[0]), __uint_as_float(a[1]) + __uint_as_float(b[1]),
+                                __uint_as_float(a[2]) + __uint_as_float(b[2]), __uint_as_float(a[3]) + __uint_as_float(b[3]));
+            }
+            tile_par ^= 1;
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+            stamp();                           // T ready
+            // the next stream starts from X1: its pointwise conv runs under this depthwise pass
+            if (last && s < 3 && tid == 0) issue_pw(sX1, lc + 1);
+            // the previous stream's conv3 MMAs read P: done before this stream overwrites it
+            if (k == 0 && c3_pending) {
+                if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
+                c3_par ^= 1;
+                c3_pending = false;
+                tc::fence_after_sync();
+            }
+            // ---- depthwise 3x3 + bias + ReLU -> hi/lo operand map P (in place: the pointwise
+            //      MMAs that read P have completed); rows [ra, rb) are the "trapezoid" this
+            //      layer has to get right for the rem layers after it
+            float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
+            {
+                const int ra = C::HALO - rem > 0 ? C::HALO - rem : 0;
+                const int rb = C::HALO + C::R + rem < C::RH ? C::HALO + C::R + rem : C::RH;
+                const int per = (rb - ra + C::SEG - 1) / C::SEG;
+                const int r0 = ra + dw_seg * per;
+                int r1 = r0 + per < rb ? r0 + per : rb;
+                if (dw_seg >= C::SEG) r1 = r0;
+                if (r0 < r1) {
+                    const float4 *Tp = sT + dw_cg * C::TPX + 2 * dw_xp;
+                    const float *wl = sPar + C::P_LC + lc * (10 * C::MIDP) + dw_cg * 4;
+                    float4 wd[9];
+#pragma unroll
+                    for (int tap = 0; tap < 9; tap++) wd[tap] = *reinterpret_cast<const float4 *>(wl + tap * C::MIDP);
+                    const float4 bs = *reinterpret_cast<const float4 *>(wl + 9 * C::MIDP);
+                    float4 w0[4], w1[4], w2[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        w0[j] = Tp[r0 * C::TW + j];
+                        w1[j] = Tp[(r0 + 1) * C::TW + j];
+                    }
+                    unsigned char *dbase = sP + (dw_cg >> 1) * C::PLANE_B + (dw_cg & 1) * 8;
+                    for (int lr = r0; lr < r1; lr++) {
+#pragma unroll
+                        for (int j = 0; j < 4; j++) w2[j] = Tp[(lr + 2) * C::TW + j];
+                        float4 o0 = bs, o1 = bs;
+#pragma unroll
+                        for (int dx = 0; dx < 3; dx++) {
+                            fma4(o0, wd[dx], w0[dx]);     fma4(o1, wd[dx], w0[dx + 1]);
+                            fma4(o0, wd[3 + dx], w1[dx]); fma4(o1, wd[3 + dx], w1[dx + 1]);
+                            fma4(o0, wd[6 + dx], w2[dx]); fma4(o1, wd[6 + dx], w2[dx + 1]);
+                        }
+                        const int gr = row0 + lr;
+                        const bool in_img = gr >= 0 && gr < C::H;
+                        o0.x = in_img ? fmaxf(o0.x, 0.f) : 0.f; o0.y = in_img ? fmaxf(o0.y, 0.f) : 0.f;
+                        o0.z = in_img ? fmaxf(o0.z, 0.f) : 0.f; o0.w = in_img ? fmaxf(o0.w, 0.f) : 0.f;
+                        o1.x = in_img ? fmaxf(o1.x, 0.f) : 0.f; o1.y = in_img ? fmaxf(o1.y, 0.f) : 0.f;
+                        o1.z = in_img ? fmaxf(o1.z, 0.f) : 0.f; o1.w = in_img ? fmaxf(o1.w, 0.f) : 0.f;
+                        if (last) {            // rows [ra, rb) == the band's own rows when rem == 0
+                            gacc.x += o0.x + o1.x; gacc.y += o0.y + o1.y;
+                            gacc.z += o0.z + o1.z; gacc.w += o0.w + o1.w;
+                        }
+                        __align__(8) __half2 h[2], l[2];
+                        unsigned char *d = dbase + (lr * C::W + 2 * dw_xp) * 16;
+                        split2(o0.x, o0.y, h[0], l[0]);
+                        split2(o0.z, o0.w, h[1], l[1]);
+                        *reinterpret_cast<uint2 *>(d) = *reinterpret_cast<uint2 *>(h);
+                        *reinterpret_cast<uint2 *>(d + C::MAP_HALF_B) = *reinterpret_cast<uint2 *>(l);
+                        split2(o1.x, o1.y, h[0], l[0]);
+                        split2(o1.z, o1.w, h[1], l[1]);
+                        *reinterpret_cast<uint2 *>(d + 16) = *reinterpret_cast<uint2 *>(h);
+                        *reinterpret_cast<uint2 *>(d + 16 + C::MAP_HALF_B) = *reinterpret_cast<uint2 *>(l);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) { w0[j] = w1[j]; w1[j] = w2[j]; }
+                    }
+                }
+            }
+            if (last) {                        // column-pair lanes of a (segment, channel group) are adjacent
+#pragma unroll
+                for (int off = C::XP / 2; off >= 1; off >>= 1) {
+                    gacc.x += __shfl_xor_sync(0xffffffffu, gacc.x, off);
+                    gacc.y += __shfl_xor_sync(0xffffffffu, gacc.y, off);
+                    gacc.z += __shfl_xor_sync(0xffffffffu, gacc.z, off);
+                    gacc.w += __shfl_xor_sync(0xffffffffu, gacc.w, off);
+                }
+                if (dw_seg < C::SEG && dw_xp == 0)
+                    *reinterpret_cast<float4 *>(s_scr + (dw_seg * C::CG + dw_cg) * 4) = gacc;
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+            stamp();                           // depthwise done
+            if (!last) {
+                if (tid == 0) issue_pw(sP, lc + 1);
+                continue;
+            }
+            // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid
+            if (tid < C::MIDP) {
+                float tot = 0.f;
+                if (tid < C::MID)
+                    for (int g = 0; g < C::SEG; g++) tot += s_scr[(g * C::CG + (tid >> 2)) * 4 + (tid & 3)];
+                sGap[s * C::MIDP + tid] = tot;
+            }
+            if (C::NB > 1) cluster.sync(); else __syncthreads();
+            if (tid < C::MIDP) {          // fixed band order: every CTA of the crop gets the same bits
+                float tot = 0.f;
+                for (int b = 0; b < C::NB; b++) {
+                    const float *rg = (C::NB > 1) ? cluster.map_shared_rank(sGap, b) : sGap;
+                    tot += rg[s * C::MIDP + tid];
+                }
+                s_mean[tid] = tot / (float)(C::H * C::W);
+            }
+            __syncthreads();
+            if (tid < C::MIDP) {
+                float h0 = sPar[C::P_GB1 + 0], h1 = sPar[C::P_GB1 + 1];
+                for (int q = 0; q < C::MIDP; q++) {
+                    const float m = s_mean[q];
+                    h0 = fmaf(m, sPar[C::P_GW1 + q * 2 + 0], h0);
+                    h1 = fmaf(m, sPar[C::P_GW1 + q * 2 + 1], h1);
+                }
+                h0 = fmaxf(h0, 0.f);
+                h1 = fmaxf(h1, 0.f);
+                float g = sPar[C::P_GB2 + tid];
+                g = fmaf(h0, sPar[C::P_GW2 + tid], g);
+                g = fmaf(h1, sPar[C::P_GW2 + C::MIDP + tid], g);
+                s_gate[tid] = 1.f / (1.f + expf(-g));
+            }
+            __syncthreads();
+            // ---- gate-scaled conv3 weights  B[kc][co][8] = W3[k][co] * g[k]  (hi / lo)
+            for (int u = tid; u < C::COUT * C::MCH; u += K3_THREADS) {
+                const int kc = u / C::COUT, co = u - kc * C::COUT;
+                __align__(16) __half h[8];
+                __align__(16) __half l[8];
+#pragma unroll
+                for (int j = 0; j < 8; j++) {
+                    const int kk = kc * 8 + j;
+                    split1(w3[kk * C::COUT + co] * s_gate[kk], h[j], l[j]);
+                }
+                *reinterpret_cast<uint4 *>(sC3 + (size_t)u * 16) = *reinterpret_cast<uint4 *>(h);
+                *reinterpret_cast<uint4 *>(sC3 + C::C3W_HALF_B + (size_t)u * 16) = *reinterpret_cast<uint4 *>(l);
+            }
+            tc::fence_async_smem();
+            tc::fence_before_sync();
+            __syncthreads();
+            tc::fence_after_sync();
+            if (tid == 0) {
+                const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(sP), C::PLANE_B, 128);
+                const uint64_t al0 = dadv(ah0, C::MAP_HALF_B / 16);
+                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sC3), C::COUT * 16, 128);
+                const uint64_t bl0 = dadv(bh0, C::C3W_HALF_B / 16);
+                const uint32_t acc0 = (C::DOWN || s > 0) ? 1u : 0u;
+#pragma unroll
+                for (int i = 0; i < C::NIT; i++) {
+                    const uint32_t d = tmem + C::TM_C3 + i * C::COUT;
+#pragma unroll
+                    for (int ks = 0; ks < C::MIDP / 16; ks++) {
+                        const int ka = (C::IT0 + i) * 128 + ks * 2 * C::NPX, kb = ks * 2 * C::COUT;
+                        mma3(d, dadv(ah0, ka), dadv(al0, ka), dadv(bh0, kb), dadv(bl0, kb), IDESC_OUT,
+                             ks > 0 ? 1u : acc0);
+                    }
+                }
+                tc::mma_commit(bar_c3);
+            }
+            c3_pending = true;
+            stamp();                           // gate + conv3 issued
+        }
+    }
+    if (c3_pending) {                 // the last stream's conv3 MMAs
+        if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
+        c3_par ^= 1;
+    }
+    tc::fence_after_sync();
+    __syncthreads();                  // every thread is past its last read of the maps / weights
+
+    // ------------------------------------------------------------------
+    // final epilogue: y = relu(conv3 + bias (+ downsample already in TMEM) (+ x)), rows transposed
+    // through a warp-private staging tile so that 8 lanes cover one 128-byte pixel row
+    // ------------------------------------------------------------------
+    float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
+    constexpr int CCH = C::COUT / 32;                         // 32-column chunks per tile
+    float *stage = reinterpret_cast<float *>(smem) + warp * (32 * 36);
+    for (int u = grp; u < C::NIT * CCH; u += K3_GROUPS) {     // (tile, chunk) units over the 4 groups
+        const int i = u / CCH, c0 = (u - i * CCH) * 32;
+        const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
+        const bool own = p >= C::OWN_P0 && p < C::OWN_P1;
+        const int rowoff = own ? band * C::R * C::W + (p - C::OWN_P0) : -1;   // pixel index inside the crop
+        if (!C::DOWN) {                                       // identity residual, coalesced
+#pragma unroll
+            for (int it = 0; it < 8; it++) {
+                const int row = it * 4 + (lane >> 3);
+                const int ro = __shfl_sync(0xffffffffu, rowoff, row);
+                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ro >= 0) x4 = *reinterpret_cast<const float4 *>(xin + (size_t)ro * C::CIN + c0 + (lane & 7) * 4);
+                *reinterpret_cast<float4 *>(stage + row * 36 + (lane & 7) * 4) = x4;
+            }
+        }
+        float v[32];
+        tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 bb = *reinterpret_cast<const float4 *>(sPar + C::P_B3 + c0 + j);
+            float4 r = make_float4(v[j] + bb.x, v[j + 1] + bb.y, v[j + 2] + bb.z, v[j + 3] + bb.w);
+            if (!C::DOWN) {
+                const float4 xv = *reinterpret_cast<const float4 *>(stage + lane * 36 + j);
+                r.x += xv.x; r.y += xv.y; r.z += xv.z; r.w += xv.w;
+            }
+            r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f);
+            r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f);
+            *reinterpret_cast<float4 *>(stage + lane * 36 + j) = r;      // own row only: no hazard
+        }
+        __syncwarp();
+#pragma unroll
+        for (int it = 0; it < 8; it++) {
+            const int row = it * 4 + (lane >> 3);
+            const int ro = __shfl_sync(0xffffffffu, rowoff, row);
+            if (ro >= 0)
+                *reinterpret_cast<float4 *>(yout + (size_t)ro * C::COUT + c0 + (lane & 7) * 4) =
+                    *reinterpret_cast<const float4 *>(stage + row * 36 + (lane & 7) * 4);
+        }
+        __syncwarp();
+    }
+    stamp();                                   // final epilogue done
+    if (dbg && blockIdx.x == 0 && tid == 0) dbg[0] = dbg_n;
+    if (!ok) { if (tid == 0) atomicExch(status, 5); }
+    tc::fence_before_sync();
+    if (C::NB > 1) cluster.sync(); else __syncthreads();     // remote sGap reads are done
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    (void)n_crops;
+}
+
+// ---------------------------------------------------------------------------
+// the six OSBlocks of osnet_x0_25 (stage 2: 64x32, stage 3: 32x16, stage 4: 16x8)
+// ---------------------------------------------------------------------------
+//            CIN MID MIDP COUT  H   W   R HALO NB DOWN NSTAGE SEG
+using K0 = B3<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2, 8>;
+using K1 = B3<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2, 8>;
+using K2 = B3<64, 24, 32, 96, 32, 16, 8, 4, 4, true, 2, 5>;
+using K3 = B3<96, 24, 32, 96, 32, 16, 8, 4, 4, false, 2, 5>;
+using K4 = B3<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1, 8>;
+using K5 = B3<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1, 8>;
+
+template <class C>
+int launch3(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,
+            cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(osblock3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+        attr = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n * C::NB);
+    cfg.blockDim = dim3(K3_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_B;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C::NB;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock3_kernel<C>, x, y, w, n, status, dbg));
+    g_ssb_launches++;
+    return 0;
+}
+
+}  // namespace
+
+int64_t ssb_reid_tc3_block_bytes(int b) {
+    switch (b) {
+        case 0: return K0::G_TOTAL;
+        case 1: return K1::G_TOTAL;
+        case 2: return K2::G_TOTAL;
+        case 3: return K3::G_TOTAL;
+        case 4: return K4::G_TOTAL;
+        case 5: return K5::G_TOTAL;
+    }
+    return -1;
+}
+
+extern long long *g_ssb_tc_dbg;
+
+int ssb_reid_tc3_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
+                       cudaStream_t st) {
+    long long *dbg = g_ssb_tc_dbg;
+    switch (b) {
+        case 0: return launch3<K0>(x, y, w, n, status, dbg, st);
+        case 1: return launch3<K1>(x, y, w, n, status, dbg, st);
+        case 2: return launch3<K2>(x, y, w, n, status, dbg, st);
+        case 3: return launch3<K3>(x, y, w, n, status, dbg, st);
+        case 4: return launch3<K4>(x, y, w, n, status, dbg, st);
+        case 5: return launch3<K5>(x, y, w, n, status, dbg, st);
+    }
+    ssb_set_error("bad OSBlock index %d", b);
+    return -1;
+}

@@ -94,8 +94,10 @@ struct ssb_tracker {
     int *boxes_tmp;           // [N][4]
     // tensor-core OSBlocks (reid_tc.cu): hi/lo fp16 operand blob, per-block offsets
     const unsigned char *w_tc;
-    int64_t w_tc_off[10];     // 6 OSBlocks, 2 transitions, tail, stem
-    int use_tc;               // 1: OSBlocks on tcgen05, 0: fp32 SIMT baseline
+    int64_t w_tc_off[16];     // 6 OSBlocks (9-tap), 2 transitions, tail, stem, 6 OSBlocks (pointwise + SIMT depthwise)
+    int have_tc3;             // sections 10..15 present
+    int use_tc;               // 0: fp32 SIMT baseline, 1: tcgen05 OSBlocks with 9 shifted GEMMs per LightConv (reid_tc.cu),
+                              // 2: tcgen05 pointwise + fp32 CUDA-core depthwise (reid_tc3.cu)
     int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
     DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
 };
@@ -139,6 +141,9 @@ int64_t ssb_reid_ws_floats(int max_dets);
 int64_t ssb_reid_tc_block_bytes(int b);
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
                       cudaStream_t st);
+int64_t ssb_reid_tc3_block_bytes(int b);
+int ssb_reid_tc3_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
+                       cudaStream_t st);
 int64_t ssb_reid_tc_aux_bytes(int which);
 int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w, int n, int *status,
                     cudaStream_t st);

@@ -97,10 +97,13 @@ class StrongSORT:
             pass
 
     def set_reid_backend(self, name):
-        """'tc': OSBlocks on the tcgen05 tensor cores; 'simt': fp32 CUDA-core baseline."""
-        if name not in ("tc", "simt"):
-            raise ValueError("reid_backend must be 'tc' or 'simt'")
-        _lib.check(self._lib.ssb_reid_use_tc(self._h, 1 if name == "tc" else 0), "ssb_reid_use_tc")
+        """'tc': OSBlocks on the tcgen05 tensor cores, LightConv = pointwise GEMM + fp32 depthwise
+        (csrc/reid_tc3.cu); 'tc9': LightConv as 9 shifted tcgen05 GEMMs (csrc/reid_tc.cu);
+        'simt': fp32 CUDA-core baseline."""
+        modes = {"simt": 0, "tc9": 1, "tc": 2}
+        if name not in modes:
+            raise ValueError("reid_backend must be 'tc', 'tc9' or 'simt'")
+        _lib.check(self._lib.ssb_reid_use_tc(self._h, modes[name]), "ssb_reid_use_tc")
         self.reid_backend = name
 
     def reid_tc_status(self):
@@ -111,7 +114,9 @@ class StrongSORT:
         return int(v.value)
 
     def reid_block(self, block, x, use_tc):
-        """One OSBlock on a float32 NHWC array [n,H,W,cin] (parity tests)."""
+        """One OSBlock on a float32 NHWC array [n,H,W,cin] (parity tests); use_tc: False/0 simt,
+        1 'tc9' kernel, True/2 'tc' kernel."""
+        use_tc = 2 if use_tc is True else int(use_tc)
         torch = self._torch
         couts = [64, 64, 96, 96, 128, 128]
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
@@ -119,7 +124,7 @@ class StrongSORT:
             n, H, W, _ = xd.shape
             yd = torch.zeros((n, H, W, couts[block]), dtype=torch.float32, device=self.device)
             _lib.check(self._lib.ssb_reid_block(self._h, int(block), _lib.ptr(xd), _lib.ptr(yd), int(n),
-                                                1 if use_tc else 0, C.c_void_p(self.stream.cuda_stream)),
+                                                use_tc, C.c_void_p(self.stream.cuda_stream)),
                        "ssb_reid_block")
         self.stream.synchronize()
         return yd.cpu().numpy()

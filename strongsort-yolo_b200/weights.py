@@ -155,8 +155,48 @@ def _pad128(b):
     return b + b"\0" * ((-len(b)) % 128)
 
 
+def _pack_tc3_block(T, bi):
+    """One OSBlock section of csrc/reid_tc3.cu (B3::G_*): pointwise weights as N-concatenated
+    hi/lo tensor-core operands, depthwise taps + biases in fp32."""
+    cin, mid, midp, cout, down = TC_BLOCKS[bi]
+    p = _STAGE[bi]
+    w = np.zeros((cin, midp)); w[:, :mid] = T[f"{p}.conv1.w"]
+    sec = _b_layout_cat(w)                                                     # C1W
+    if down:
+        sec += _b_layout(T[f"{p}.down.w"].astype(np.float64))                  # DNW [cin][cout]
+    for nm in _LC:                                                             # LCW x 10 (pointwise)
+        pw = np.zeros((midp, midp)); pw[:mid, :mid] = T[f"{p}.{nm}.pw"]
+        sec += _b_layout_cat(pw)
+    sec = _pad128(sec)
+    par = np.zeros(midp + 100 * midp + cout + 2 * midp + 2 + 2 * midp + midp, dtype=np.float32)
+    o = 0
+    par[o:o + mid] = T[f"{p}.conv1.b"]; o += midp
+    for nm in _LC:
+        dw = np.zeros((9, midp), dtype=np.float32); dw[:, :mid] = T[f"{p}.{nm}.dw"]     # [tap][c]
+        par[o:o + 9 * midp] = dw.reshape(-1); o += 9 * midp
+        par[o:o + mid] = T[f"{p}.{nm}.b"]; o += midp
+    b3 = T[f"{p}.conv3.b"].astype(np.float64)
+    if down:
+        b3 = b3 + T[f"{p}.down.b"].astype(np.float64)
+    par[o:o + cout] = b3; o += cout
+    g1 = T[f"{p}.gate.fc1.w"]                                                  # [mid][r]
+    r = g1.shape[1]
+    gw1 = np.zeros((midp, 2), dtype=np.float32); gw1[:mid, :r] = g1
+    par[o:o + 2 * midp] = gw1.reshape(-1); o += 2 * midp
+    par[o:o + r] = T[f"{p}.gate.fc1.b"]; o += 2
+    gw2 = np.zeros((2, midp), dtype=np.float32); gw2[:r, :mid] = T[f"{p}.gate.fc2.w"]
+    par[o:o + 2 * midp] = gw2.reshape(-1); o += 2 * midp
+    par[o:o + mid] = T[f"{p}.gate.fc2.b"]; o += midp
+    assert o == par.size
+    sec += _pad128(par.tobytes())
+    w3 = np.zeros((midp, cout), dtype=np.float32); w3[:mid] = T[f"{p}.conv3.w"]
+    return sec + w3.tobytes()
+
+
 def pack_tc(tensors):
-    """tensors: output of fold().  -> (uint8 blob, int64 offsets[6])."""
+    """tensors: output of fold().  -> (uint8 blob, int64 offsets[16]): sections 0..5 OSBlocks
+    for reid_tc.cu (9 shifted GEMMs per LightConv), 6..7 transitions, 8 tail, 9 stem,
+    10..15 OSBlocks for reid_tc3.cu (pointwise on tcgen05 + fp32 depthwise)."""
     T = dict(tensors)
     blob, offs = b"", []
     for bi, (cin, mid, midp, cout, down) in enumerate(TC_BLOCKS):
@@ -220,4 +260,7 @@ def pack_tc(tensors):
     hi, lo = _hi_lo(np.ascontiguousarray(wt.reshape(16, 2, 8, 16).transpose(0, 1, 3, 2)))   # [tap][kc][n][8]
     offs.append(len(blob))
     blob += _pad128(hi.tobytes() + lo.tobytes() + _pad128(T["stem.b"].astype(np.float32).tobytes()))
+    for bi in range(6):
+        offs.append(len(blob))
+        blob += _pad128(_pack_tc3_block(T, bi))
     return np.frombuffer(blob, dtype=np.uint8).copy(), np.asarray(offs, dtype=np.int64)

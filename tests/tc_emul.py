@@ -160,3 +160,117 @@ def osblock_emul(b, x, blob, offs):
                 out = out + x[crop, bd["GR"][own], bd["GC"][own]]
             y[crop, bd["GR"][own], bd["GC"][own]] = np.maximum(out, 0.0)
     return y
+
+
+# ---------------------------------------------------------------------------
+# csrc/reid_tc3.cu: pointwise on the tensor cores (hi/lo operands), depthwise in fp32
+# ---------------------------------------------------------------------------
+class Cfg3:
+    GEO = [(64, 32, 16, 4, 4, 8), (64, 32, 16, 4, 4, 8), (32, 16, 8, 4, 4, 5), (32, 16, 8, 4, 4, 5),
+           (16, 8, 16, 0, 1, 8), (16, 8, 16, 0, 1, 8)]
+
+    def __init__(self, b):
+        cin, mid, midp, cout, down = weights.TC_BLOCKS[b]
+        self.CIN, self.MID, self.MIDP, self.COUT, self.DOWN = cin, mid, midp, cout, down
+        self.H, self.W, self.R, self.HALO, self.NB, self.SEG = self.GEO[b]
+        self.RH = self.R + 2 * self.HALO
+        self.NPX = self.RH * self.W
+        assert self.NPX % 128 == 0
+        self.NT = self.NPX // 128
+        self.OWN_P0, self.OWN_P1 = self.HALO * self.W, (self.HALO + self.R) * self.W
+        self.IT0, self.IT1 = self.OWN_P0 // 128, (self.OWN_P1 + 127) // 128
+        self.C1W_B = cin * midp * 4
+        self.DNW_B = cin * cout * 4 if down else 0
+        self.LCW_B = midp * midp * 4
+        self.WALL_B = self.C1W_B + self.DNW_B + 10 * self.LCW_B
+        self.NPAR = midp + 100 * midp + cout + 2 * midp + 2 + 2 * midp + midp
+        self.G_PAR = (self.WALL_B + 127) // 128 * 128
+        self.G_W3 = self.G_PAR + (self.NPAR * 4 + 127) // 128 * 128
+        self.G_TOTAL = self.G_W3 + midp * cout * 4
+
+
+def osblock3_emul(b, x, blob, offs):
+    """x: float32 [n,H,W,cin] -> float32 [n,H,W,cout]; band by band, in-place P map with stale
+    rows outside each layer's trapezoid, exactly the kernel's index arithmetic."""
+    c = Cfg3(b)
+    end = int(offs[11 + b]) if 11 + b < len(offs) else len(blob)
+    sec = bytes(blob[int(offs[10 + b]):end])
+    assert len(sec) >= c.G_TOTAL
+    W1 = _b_operand_cat(sec[0:c.C1W_B], c.CIN, c.MIDP)
+    WD = _b_operand(sec[c.C1W_B:c.C1W_B + c.DNW_B], c.CIN, c.COUT) if c.DOWN else None
+    o0 = c.C1W_B + c.DNW_B
+    PW = [_b_operand_cat(sec[o0 + l * c.LCW_B:o0 + (l + 1) * c.LCW_B], c.MIDP, c.MIDP) for l in range(10)]
+    par = np.frombuffer(sec[c.G_PAR:c.G_PAR + c.NPAR * 4], dtype=np.float32)
+    o = 0
+    b1 = par[o:o + c.MIDP].astype(np.float64); o += c.MIDP
+    DW, BL = [], []
+    for _ in range(10):
+        DW.append(par[o:o + 9 * c.MIDP].reshape(9, c.MIDP)); o += 9 * c.MIDP
+        BL.append(par[o:o + c.MIDP]); o += c.MIDP
+    b3 = par[o:o + c.COUT].astype(np.float64); o += c.COUT
+    gw1 = par[o:o + 2 * c.MIDP].reshape(c.MIDP, 2).astype(np.float64); o += 2 * c.MIDP
+    gb1 = par[o:o + 2].astype(np.float64); o += 2
+    gw2 = par[o:o + 2 * c.MIDP].reshape(2, c.MIDP).astype(np.float64); o += 2 * c.MIDP
+    gb2 = par[o:o + c.MIDP].astype(np.float64); o += c.MIDP
+    assert o == c.NPAR
+    W3 = np.frombuffer(sec[c.G_W3:c.G_W3 + c.MIDP * c.COUT * 4], dtype=np.float32).reshape(c.MIDP, c.COUT).astype(np.float64)
+
+    n = x.shape[0]
+    y = np.zeros((n, c.H, c.W, c.COUT), dtype=np.float32)
+    Pix = np.arange(c.NPX)
+    LR, COL = Pix // c.W, Pix % c.W
+    for crop in range(n):
+        bands = []
+        for band in range(c.NB):
+            row0 = band * c.R - c.HALO
+            GR = row0 + LR
+            valid = (GR >= 0) & (GR < c.H)
+            xt = np.zeros((c.NPX, c.CIN))
+            xt[valid] = x[crop, GR[valid], COL[valid]]
+            xt = _hl(xt)
+            X1 = _hl(np.where(valid[:, None], np.maximum(xt @ W1 + b1, 0.0), 0.0).astype(np.float32))
+            accd = (xt @ WD) if c.DOWN else np.zeros((c.NPX, c.COUT))
+            Pm = np.zeros((c.NPX, c.MIDP))                        # zeroed after phase 1
+            bands.append(dict(row0=row0, valid=valid, GR=GR, X1=X1, P=Pm, c3=accd.copy()))
+        lc = 0
+        for s in range(4):
+            for k in range(s + 1):
+                rem = s - k
+                ra, rb = max(c.HALO - rem, 0), min(c.HALO + c.R + rem, c.RH)
+                fs = []
+                for bd in bands:
+                    src = bd["X1"] if k == 0 else bd["P"]
+                    T = np.zeros((c.RH + 2, c.W + 2, c.MIDP), dtype=np.float32)       # zero ring
+                    T[1:-1, 1:-1] = (src @ PW[lc]).astype(np.float32).reshape(c.RH, c.W, c.MIDP)
+                    out = np.zeros((c.RH, c.W, c.MIDP), dtype=np.float32)
+                    out[:] = BL[lc]
+                    for dy in range(3):
+                        for dx in range(3):
+                            out += DW[lc][dy * 3 + dx] * T[dy:dy + c.RH, dx:dx + c.W]
+                    rows_in = ((bd["row0"] + np.arange(c.RH)) >= 0) & ((bd["row0"] + np.arange(c.RH)) < c.H)
+                    out = np.where(rows_in[:, None, None], np.maximum(out, 0.0), 0.0).astype(np.float32)
+                    newP = bd["P"].reshape(c.RH, c.W, c.MIDP).copy()
+                    newP[ra:rb, :, :c.MID] = _hl(out[ra:rb, :, :c.MID])    # only the trapezoid rows, real channels
+                    bd["P"] = newP.reshape(c.NPX, c.MIDP)
+                    fs.append(out)
+                lc += 1
+            tot = sum(f[c.HALO:c.HALO + c.R, :, :].astype(np.float64).sum((0, 1)) for f in fs)
+            tot[c.MID:] = 0.0
+            mean = tot / (c.H * c.W)
+            h = np.maximum(gb1 + mean @ gw1, 0.0)
+            g = 1.0 / (1.0 + np.exp(-(gb2 + h @ gw2)))
+            W3g = _hl((W3 * g[:, None]).astype(np.float32))
+            for bd in bands:
+                a = bd["P"].copy()
+                a[:c.IT0 * 128] = 0.0
+                a[c.IT1 * 128:] = 0.0
+                bd["c3"] += a @ W3g
+        for band, bd in enumerate(bands):
+            own = (Pix >= c.OWN_P0) & (Pix < c.OWN_P1)
+            assert own[c.IT0 * 128:c.IT1 * 128].sum() == own.sum()
+            out = bd["c3"][own] + b3
+            gr, gc = bd["GR"][own], COL[own]
+            if not c.DOWN:
+                out = out + x[crop, gr, gc]
+            y[crop, gr, gc] = np.maximum(out, 0.0)
+    return y

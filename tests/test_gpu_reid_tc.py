@@ -20,22 +20,24 @@ def trk():
     return StrongSORT(max_tracks=64, max_dets=64, reid_backend="simt")
 
 
+@pytest.mark.parametrize("mode", [2, 1], ids=["pwdw", "tap9"])
 @pytest.mark.parametrize("block", [0, 1, 2, 3, 4, 5])
-def test_osblock_tc_matches_simt(trk, block):
+def test_osblock_tc_matches_simt(trk, block, mode):
     H, W, cin = SHAPES[block]
     rng = np.random.default_rng(100 + block)
     x = np.maximum(rng.normal(0.5, 1.0, (5, H, W, cin)), 0).astype(np.float32)
     ref = trk.reid_block(block, x, use_tc=False)
-    got = trk.reid_block(block, x, use_tc=True)
+    got = trk.reid_block(block, x, use_tc=mode)
     assert trk.reid_tc_status() == 0, "a tensor-core barrier wait timed out"
     assert np.isfinite(got).all()
     err = np.abs(got - ref).max() / np.abs(ref).max()
     assert err < 1e-4, f"block {block}: max error {err:.3e} of the activation scale"
 
 
-def test_embeddings_tc_vs_oracle(trk, golden_dir, oracle_extractor):
+@pytest.mark.parametrize("backend", ["tc", "tc9"])
+def test_embeddings_tc_vs_oracle(trk, golden_dir, oracle_extractor, backend):
     g = np.load(os.path.join(golden_dir, "reid_kat.npz"))
-    trk.set_reid_backend("tc")
+    trk.set_reid_backend(backend)
     emb = trk.extract_features(g["img"], g["boxes"])
     trk.set_reid_backend("simt")
     assert trk.reid_tc_status() == 0
@@ -46,13 +48,14 @@ def test_embeddings_tc_vs_oracle(trk, golden_dir, oracle_extractor):
     assert rel.max() < 1e-3
 
 
-def test_c2_frame_tc_vs_simt_embeddings(trk):
+@pytest.mark.parametrize("backend", ["tc", "tc9"])
+def test_c2_frame_tc_vs_simt_embeddings(trk, backend):
     from strongsort_yolo_b200 import synth
     st = synth.make_stream("C1")
     fr = st.next_frame()
     boxes = np.asarray([ss.crop_box_xyxy(b, 640, 640) for b in ss.xyxy2xywh(fr.dets[:, :4])])
     a = trk.extract_features(fr.img, boxes)
-    trk.set_reid_backend("tc")
+    trk.set_reid_backend(backend)
     b = trk.extract_features(fr.img, boxes)
     trk.set_reid_backend("simt")
     assert trk.reid_tc_status() == 0

@@ -49,7 +49,7 @@ def main():
     boxes = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
     feats = torch.zeros((n, 512), dtype=torch.float32, device="cuda")
     _lib.check(lib.ssb_crop_boxes(P(dets), n, 1080, 1920, P(boxes), ST()))
-    for backend in ("tc", "simt"):
+    for backend in ("tc", "tc9", "simt"):
         trk.set_reid_backend(backend)
         out[f"reid_{backend}_n{n}"] = timeit(lambda: _lib.check(lib.ssb_reid(
             trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST())))
@@ -59,14 +59,15 @@ def main():
     shapes = [(64, 32, 16), (64, 32, 64), (32, 16, 64), (32, 16, 96), (16, 8, 96), (16, 8, 128)]
     for b, (hh, ww, cin) in enumerate(shapes):
         x = np.maximum(np.random.default_rng(b).normal(0.5, 1, (n, hh, ww, cin)), 0).astype(np.float32)
-        trk.reid_block(b, x, True)
-        lib.ssb_reid_tc_debug(P(dbg))
-        trk.reid_block(b, x, True)
-        lib.ssb_reid_tc_debug(None)
-        torch.cuda.synchronize()
-        d = dbg.cpu().numpy()
-        k = int(d[0])
-        out[f"osblock{b}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
+        for mode, tag in ((2, ""), (1, "_tap9")):
+            trk.reid_block(b, x, mode)
+            lib.ssb_reid_tc_debug(P(dbg))
+            trk.reid_block(b, x, mode)
+            lib.ssb_reid_tc_debug(None)
+            torch.cuda.synchronize()
+            d = dbg.cpu().numpy()
+            k = int(d[0])
+            out[f"osblock{b}{tag}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
     # stage-A-like clamped cost matrices from the live tracker
     a, b = trk.debug_costs()
     for name, m in (("lsap_stageA", a), ("lsap_stageB", b)):
