@@ -9,9 +9,11 @@
 //     2 A-tile reads per tile and K step (hi/lo operands, N-concatenated weights);
 //   * the depthwise 3x3 runs on the CUDA cores in exact fp32 on the GEMM result: the TMEM
 //     accumulator is drained to a zero-ringed fp32 map T[c/4][row][col][4] in shared memory,
-//     a sliding 3-row register window per thread (2 columns x 4 channels) makes 2 float4
-//     loads per output float4, and the result (bias, ReLU, hi/lo split) is written straight
-//     into the next layer's K-major operand map.
+//     a sliding 3-row register window per thread (1 column x 4 channels; lanes = adjacent
+//     columns, so every shared-memory access is conflict-free) makes 3 float4 loads per output
+//     float4, and the result (bias, ReLU, hi/lo split) is written straight into the next
+//     layer's K-major operand map -- the two lanes holding the halves of an 8-channel K chunk
+//     swap hi/lo words by shuffle so that each writes one full 16-byte operand row.
 // Because no operand is shifted any more the maps need no zero ring / guard pixels:
 // pixel p = row * W + col, a band is a whole number of 128-row M tiles, the band's own
 // rows start on a tile boundary in stage 2, and all 10 LightConv weight sets (1-4 KB each
@@ -49,7 +51,13 @@ struct B3 {
     static constexpr int IT0 = OWN_P0 / 128, IT1 = (OWN_P1 + 127) / 128, NIT = IT1 - IT0;
     static constexpr int MCH = MIDP / 8;                  // 16-byte K chunks per pixel
     static constexpr int CG = MID / 4;                    // real float4 channel groups
-    static constexpr int XP = W / 2;                      // column pairs of the depthwise pass
+    // depthwise pass: a warp = XL adjacent columns x 2 channel groups of one 8-channel K chunk
+    // (x CPW chunk pairs when the map is narrower than 16), walking down a row segment
+    static constexpr int XL = W < 16 ? W : 16;            // column lanes
+    static constexpr int CPW = 16 / XL;                   // channel-group pairs per warp
+    static constexpr int NCB = W / XL;                    // column blocks
+    static constexpr int NCGW = (CG / 2) / CPW;           // channel-group-pair groups
+    static constexpr int TPS = NCB * NCGW;                // warp tasks per row segment
     static constexpr int PLANE_B = NPX * 16;              // LBO of a map operand
     static constexpr int MAP_HALF_B = MCH * PLANE_B, MAP_B = 2 * MAP_HALF_B;   // hi planes, lo planes
     static constexpr int TW = W + 2, TH = RH + 2, TPX = TW * TH;
@@ -76,7 +84,7 @@ struct B3 {
     static constexpr int OFF_PAR = OFF_C3 + C3W_B;
     static constexpr int OFF_GAP = OFF_PAR + rup128(NPAR * 4);       // [4][MIDP] floats
     static constexpr int OFF_MISC = OFF_GAP + 4 * MIDP * 4;
-    static constexpr int SCR_FLOATS = SEG * CG * 4;
+    static constexpr int SCR_FLOATS = SEG * NCB * CG * 4;
     static constexpr int SMEM_B = OFF_MISC + 128 + (SCR_FLOATS + 2 * MIDP) * 4 + 64;
     static_assert(NPX % 128 == 0, "band = whole M tiles");
     static_assert((W & (W - 1)) == 0, "W power of two");
@@ -85,8 +93,10 @@ struct B3 {
     static_assert(SMEM_B <= 232448, "shared memory");
     static_assert(MIDP % 16 == 0 && COUT % 16 == 0 && CIN % 16 == 0 && MID % 4 == 0, "MMA shapes");
     static_assert(H % R == 0 && H / R == NB, "bands");
-    static_assert(MID <= MIDP && COUT == 4 * MID, "OSBlock channel plan");
-    static_assert(SEG * CG * XP <= K3_THREADS, "depthwise tasks fit the CTA");
+    static_assert(MID <= MIDP && COUT == 4 * MID && MIDP <= 32 && COUT * (MIDP / 8) <= K3_THREADS, "OSBlock channel plan");
+    static_assert(CG % 2 == 0 && (CG / 2) % CPW == 0 && W % XL == 0, "depthwise warp tasks");
+    static_assert(SEG * TPS <= K3_THREADS / 32, "depthwise tasks fit the CTA");
+    static_assert((NT * CG) % K3_GROUPS == 0, "pointwise drain units divide the groups");
     static_assert(16 * 32 * 36 * 4 <= OFF_C3, "final-epilogue staging fits in the dead maps/weights");
     // global blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
     static constexpr int G_PAR = rup128(WALL_B);
@@ -122,10 +132,19 @@ __device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, uint32_t *r) {
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void fma4(float4 &o, const float4 &w, const float4 &v) {
-    o.x = fmaf(w.x, v.x, o.x); o.y = fmaf(w.y, v.y, o.y);
-    o.z = fmaf(w.z, v.z, o.z); o.w = fmaf(w.w, v.w, o.w);
+// four fp32 channels as two packed pairs: Blackwell's FFMA2 (fma.rn.f32x2) does two IEEE fp32
+// FMAs per issue slot -- the depthwise pass is issue-bound, not FMA-pipe-bound
+struct P4 { unsigned long long a, b; };          // channels (0,1), (2,3)
+__device__ __forceinline__ P4 ldp4(const float4 *p) {
+    const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
+    return P4{v.x, v.y};
 }
+__device__ __forceinline__ void fma4(P4 &o, const P4 &w, const P4 &v) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o.a) : "l"(w.a), "l"(v.a));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o.b) : "l"(w.b), "l"(v.b));
+}
+__device__ __forceinline__ float plo(unsigned long long v) { return __uint_as_float((uint32_t)v); }
+__device__ __forceinline__ float phi(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
 template <class C>
 __global__ void __launch_bounds__(K3_THREADS, 1)
@@ -150,8 +169,6 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     uint64_t *bar_c3 = bar_w + 11;                     // conv3 accumulation of the current stream
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_w + 12);
     float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 128);   // [SEG][CG][4] partial sums
-    float *s_mean = s_scr + C::SCR_FLOATS;                                // [MIDP]
-    float *s_gate = s_mean + C::MIDP;                                     // [MIDP]
 
     if (warp == 0) tc::tmem_alloc(s_tmem, 512);
     if (tid == 0) {
@@ -315,9 +332,18 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             tc::mma_commit(bar_tile + t);
         }
     };
-    const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);      // [MIDP][COUT]
-    // depthwise task of this thread: column pair xp, channel group cgi, row segment seg
-    const int dw_xp = tid % C::XP, dw_cg = (tid / C::XP) % C::CG, dw_seg = tid / (C::XP * C::CG);
+    float w3r[8];                             // conv3 weights of this thread's operand row (kc, co)
+    {
+        const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);  // [MIDP][COUT]
+        const int kc = tid / C::COUT, co = tid - kc * C::COUT;
+#pragma unroll
+        for (int j = 0; j < 8; j++) w3r[j] = tid < C::COUT * C::MCH ? w3[(kc * 8 + j) * C::COUT + co] : 0.f;
+    }
+    // depthwise task of this thread (see B3::XL): column, channel group (parity = lane bit XL), row segment
+    const int dw_par = (lane / C::XL) & 1;
+    const int dw_seg = warp / C::TPS, dw_cb = (warp % C::TPS) % C::NCB;
+    const int dw_cg = (((warp % C::TPS) / C::NCB) * C::CPW + lane / (2 * C::XL)) * 2 + dw_par;
+    const int dw_col = dw_cb * C::XL + lane % C::XL;
     int lc = 0;
     uint32_t tile_par = 0, c3_par = 0;
     bool c3_pending = false;
@@ -326,21 +352,34 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         for (int k = 0; k <= s; k++, lc++) {
             const int rem = s - k;                                // LightConvs after this one in the stream
             const bool last = (k == s);
-            // ---- pointwise result: TMEM -> fp32 T (zero ring untouched), units (tile, channel group)
-            for (int u = grp; u < C::NT * C::CG; u += K3_GROUPS) {
-                const int t = u / C::CG, cgi = u - t * C::CG;
-                if (!tc::mbar_wait(bar_tile + t, tile_par)) ok = false;
-                tc::fence_after_sync();
-                const int p = t * 128 + quad * 32 + lane;
-                const int lr = p / C::W, col = p % C::W;
-                uint32_t a[4], b[4];
-                const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + cgi * 4;
-                tmem_ld4_nw(ta, a);
-                tmem_ld4_nw(ta + C::MIDP, b);
+            // ---- pointwise result: TMEM -> fp32 T (zero ring untouched), units (tile, channel group);
+            //      all TMEM loads of the thread are in flight before the single wait
+            {
+                constexpr int UPT = (C::NT * C::CG) / K3_GROUPS;
+                uint32_t ra_[UPT][4], rb_[UPT][4];
+#pragma unroll
+                for (int i = 0; i < UPT; i++) {
+                    const int u = grp + i * K3_GROUPS;
+                    const int t = u / C::CG, cgi = u - t * C::CG;
+                    if (!tc::mbar_wait(bar_tile + t, tile_par)) ok = false;
+                    tc::fence_after_sync();
+                    const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + cgi * 4;
+                    tmem_ld4_nw(ta, ra_[i]);
+                    tmem_ld4_nw(ta + C::MIDP, rb_[i]);
+                }
                 tmem_wait_ld();
-                sT[cgi * C::TPX + (lr + 1) * C::TW + col + 1] =
-                    make_float4(__uint_as_float(a[0]) + __uint_as_float(b[0]), __uint_as_float(a[1]) + __uint_as_float(b[1]),
-                                __uint_as_float(a[2]) + __uint_as_float(b[2]), __uint_as_float(a[3]) + __uint_as_float(b[3]));
+#pragma unroll
+                for (int i = 0; i < UPT; i++) {
+                    const int u = grp + i * K3_GROUPS;
+                    const int t = u / C::CG, cgi = u - t * C::CG;
+                    const int p = t * 128 + quad * 32 + lane;
+                    const int lr = p / C::W, col = p % C::W;
+                    sT[cgi * C::TPX + (lr + 1) * C::TW + col + 1] =
+                        make_float4(__uint_as_float(ra_[i][0]) + __uint_as_float(rb_[i][0]),
+                                    __uint_as_float(ra_[i][1]) + __uint_as_float(rb_[i][1]),
+                                    __uint_as_float(ra_[i][2]) + __uint_as_float(rb_[i][2]),
+                                    __uint_as_float(ra_[i][3]) + __uint_as_float(rb_[i][3]));
+                }
             }
             tile_par ^= 1;
             tc::fence_before_sync();
@@ -366,66 +405,73 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
                 const int per = (rb - ra + C::SEG - 1) / C::SEG;
                 const int r0 = ra + dw_seg * per;
                 int r1 = r0 + per < rb ? r0 + per : rb;
-                if (dw_seg >= C::SEG) r1 = r0;
+                if (dw_seg >= C::SEG) r1 = r0;                       // warp-uniform
                 if (r0 < r1) {
-                    const float4 *Tp = sT + dw_cg * C::TPX + 2 * dw_xp;
+                    const float4 *Tp = sT + dw_cg * C::TPX + dw_col;     // window columns col-1 .. col+1 (ring offset 1)
                     const float *wl = sPar + C::P_LC + lc * (10 * C::MIDP) + dw_cg * 4;
-                    float4 wd[9];
+                    P4 wd[9];
 #pragma unroll
-                    for (int tap = 0; tap < 9; tap++) wd[tap] = *reinterpret_cast<const float4 *>(wl + tap * C::MIDP);
-                    const float4 bs = *reinterpret_cast<const float4 *>(wl + 9 * C::MIDP);
-                    float4 w0[4], w1[4], w2[4];
+                    for (int tap = 0; tap < 9; tap++) wd[tap] = ldp4(reinterpret_cast<const float4 *>(wl + tap * C::MIDP));
+                    const P4 bs = ldp4(reinterpret_cast<const float4 *>(wl + 9 * C::MIDP));
+                    // the even channel group of a K chunk writes the 16-byte hi operand, the odd one the lo
+                    unsigned char *dbase = sP + (dw_cg >> 1) * C::PLANE_B + dw_col * 16 + (dw_par ? C::MAP_HALF_B : 0);
+                    auto ldrow = [&](P4 *w, int trow) {
 #pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        w0[j] = Tp[r0 * C::TW + j];
-                        w1[j] = Tp[(r0 + 1) * C::TW + j];
-                    }
-                    unsigned char *dbase = sP + (dw_cg >> 1) * C::PLANE_B + (dw_cg & 1) * 8;
-                    for (int lr = r0; lr < r1; lr++) {
-#pragma unroll
-                        for (int j = 0; j < 4; j++) w2[j] = Tp[(lr + 2) * C::TW + j];
-                        float4 o0 = bs, o1 = bs;
+                        for (int j = 0; j < 3; j++) w[j] = ldp4(Tp + trow * C::TW + j);
+                    };
+                    auto dwrow = [&](int lr, const P4 *wa, const P4 *wb, const P4 *wc) {
+                        P4 o = bs;
 #pragma unroll
                         for (int dx = 0; dx < 3; dx++) {
-                            fma4(o0, wd[dx], w0[dx]);     fma4(o1, wd[dx], w0[dx + 1]);
-                            fma4(o0, wd[3 + dx], w1[dx]); fma4(o1, wd[3 + dx], w1[dx + 1]);
-                            fma4(o0, wd[6 + dx], w2[dx]); fma4(o1, wd[6 + dx], w2[dx + 1]);
+                            fma4(o, wd[dx], wa[dx]);
+                            fma4(o, wd[3 + dx], wb[dx]);
+                            fma4(o, wd[6 + dx], wc[dx]);
                         }
+                        float ox = fmaxf(plo(o.a), 0.f), oy = fmaxf(phi(o.a), 0.f);
+                        float oz = fmaxf(plo(o.b), 0.f), ow = fmaxf(phi(o.b), 0.f);
                         const int gr = row0 + lr;
-                        const bool in_img = gr >= 0 && gr < C::H;
-                        o0.x = in_img ? fmaxf(o0.x, 0.f) : 0.f; o0.y = in_img ? fmaxf(o0.y, 0.f) : 0.f;
-                        o0.z = in_img ? fmaxf(o0.z, 0.f) : 0.f; o0.w = in_img ? fmaxf(o0.w, 0.f) : 0.f;
-                        o1.x = in_img ? fmaxf(o1.x, 0.f) : 0.f; o1.y = in_img ? fmaxf(o1.y, 0.f) : 0.f;
-                        o1.z = in_img ? fmaxf(o1.z, 0.f) : 0.f; o1.w = in_img ? fmaxf(o1.w, 0.f) : 0.f;
+                        if (gr < 0 || gr >= C::H) { ox = 0.f; oy = 0.f; oz = 0.f; ow = 0.f; }     // warp-uniform
                         if (last) {            // rows [ra, rb) == the band's own rows when rem == 0
-                            gacc.x += o0.x + o1.x; gacc.y += o0.y + o1.y;
-                            gacc.z += o0.z + o1.z; gacc.w += o0.w + o1.w;
+                            gacc.x += ox; gacc.y += oy; gacc.z += oz; gacc.w += ow;
                         }
-                        __align__(8) __half2 h[2], l[2];
-                        unsigned char *d = dbase + (lr * C::W + 2 * dw_xp) * 16;
-                        split2(o0.x, o0.y, h[0], l[0]);
-                        split2(o0.z, o0.w, h[1], l[1]);
-                        *reinterpret_cast<uint2 *>(d) = *reinterpret_cast<uint2 *>(h);
-                        *reinterpret_cast<uint2 *>(d + C::MAP_HALF_B) = *reinterpret_cast<uint2 *>(l);
-                        split2(o1.x, o1.y, h[0], l[0]);
-                        split2(o1.z, o1.w, h[1], l[1]);
-                        *reinterpret_cast<uint2 *>(d + 16) = *reinterpret_cast<uint2 *>(h);
-                        *reinterpret_cast<uint2 *>(d + 16 + C::MAP_HALF_B) = *reinterpret_cast<uint2 *>(l);
-#pragma unroll
-                        for (int j = 0; j < 4; j++) { w0[j] = w1[j]; w1[j] = w2[j]; }
+                        __half2 h[2], l[2];
+                        split2(ox, oy, h[0], l[0]);
+                        split2(oz, ow, h[1], l[1]);
+                        // partner lane (same pixel, other half of the K chunk): even sends lo, odd sends hi
+                        const uint32_t h0 = *reinterpret_cast<uint32_t *>(&h[0]), h1 = *reinterpret_cast<uint32_t *>(&h[1]);
+                        const uint32_t l0 = *reinterpret_cast<uint32_t *>(&l[0]), l1 = *reinterpret_cast<uint32_t *>(&l[1]);
+                        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, dw_par ? h0 : l0, C::XL);
+                        const uint32_t g1 = __shfl_xor_sync(0xffffffffu, dw_par ? h1 : l1, C::XL);
+                        *reinterpret_cast<uint4 *>(dbase + lr * (C::W * 16)) =
+                            dw_par ? make_uint4(g0, g1, l0, l1) : make_uint4(h0, h1, g0, g1);
+                    };
+                    P4 w0[3], w1[3], w2[3];                        // rotating 3-row window (no register moves)
+                    ldrow(w0, r0);
+                    ldrow(w1, r0 + 1);
+                    for (int lr = r0; lr < r1; lr += 3) {
+                        ldrow(w2, lr + 2);
+                        dwrow(lr, w0, w1, w2);
+                        if (lr + 1 < r1) {
+                            ldrow(w0, lr + 3);
+                            dwrow(lr + 1, w1, w2, w0);
+                        }
+                        if (lr + 2 < r1) {
+                            ldrow(w1, lr + 4);
+                            dwrow(lr + 2, w2, w0, w1);
+                        }
                     }
                 }
             }
-            if (last) {                        // column-pair lanes of a (segment, channel group) are adjacent
+            if (last) {                        // the column lanes of a (segment, column block, channel group) are adjacent
 #pragma unroll
-                for (int off = C::XP / 2; off >= 1; off >>= 1) {
+                for (int off = C::XL / 2; off >= 1; off >>= 1) {
                     gacc.x += __shfl_xor_sync(0xffffffffu, gacc.x, off);
                     gacc.y += __shfl_xor_sync(0xffffffffu, gacc.y, off);
                     gacc.z += __shfl_xor_sync(0xffffffffu, gacc.z, off);
                     gacc.w += __shfl_xor_sync(0xffffffffu, gacc.w, off);
                 }
-                if (dw_seg < C::SEG && dw_xp == 0)
-                    *reinterpret_cast<float4 *>(s_scr + (dw_seg * C::CG + dw_cg) * 4) = gacc;
+                if (dw_seg < C::SEG && (lane % C::XL) == 0)
+                    *reinterpret_cast<float4 *>(s_scr + ((dw_seg * C::NCB + dw_cb) * C::CG + dw_cg) * 4) = gacc;
             }
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -436,50 +482,53 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
                 if (tid == 0) issue_pw(sP, lc + 1);
                 continue;
             }
-            // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid
-            if (tid < C::MIDP) {
+            // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid -> scaled conv3 weights
+            if (warp == 0) {
                 float tot = 0.f;
-                if (tid < C::MID)
-                    for (int g = 0; g < C::SEG; g++) tot += s_scr[(g * C::CG + (tid >> 2)) * 4 + (tid & 3)];
-                sGap[s * C::MIDP + tid] = tot;
+                if (lane < C::MID)
+                    for (int g = 0; g < C::SEG * C::NCB; g++) tot += s_scr[(g * C::CG + (lane >> 2)) * 4 + (lane & 3)];
+                if (lane < C::MIDP) sGap[s * C::MIDP + lane] = tot;
             }
             if (C::NB > 1) cluster.sync(); else __syncthreads();
-            if (tid < C::MIDP) {          // fixed band order: every CTA of the crop gets the same bits
-                float tot = 0.f;
-                for (int b = 0; b < C::NB; b++) {
-                    const float *rg = (C::NB > 1) ? cluster.map_shared_rank(sGap, b) : sGap;
-                    tot += rg[s * C::MIDP + tid];
+            if (warp * 32 < C::COUT * C::MCH) {      // warps that own conv3 weight rows; lane c = channel c
+                float tot = 0.f;                   // fixed band order: every CTA of the crop gets the same bits
+                if (lane < C::MIDP)
+                    for (int b = 0; b < C::NB; b++) {
+                        const float *rg = (C::NB > 1) ? cluster.map_shared_rank(sGap, b) : sGap;
+                        tot += rg[s * C::MIDP + lane];
+                    }
+                const float m = tot / (float)(C::H * C::W);
+                float h0 = lane < C::MIDP ? m * sPar[C::P_GW1 + lane * 2 + 0] : 0.f;
+                float h1 = lane < C::MIDP ? m * sPar[C::P_GW1 + lane * 2 + 1] : 0.f;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) {
+                    h0 += __shfl_xor_sync(0xffffffffu, h0, off);
+                    h1 += __shfl_xor_sync(0xffffffffu, h1, off);
                 }
-                s_mean[tid] = tot / (float)(C::H * C::W);
-            }
-            __syncthreads();
-            if (tid < C::MIDP) {
-                float h0 = sPar[C::P_GB1 + 0], h1 = sPar[C::P_GB1 + 1];
-                for (int q = 0; q < C::MIDP; q++) {
-                    const float m = s_mean[q];
-                    h0 = fmaf(m, sPar[C::P_GW1 + q * 2 + 0], h0);
-                    h1 = fmaf(m, sPar[C::P_GW1 + q * 2 + 1], h1);
+                h0 = fmaxf(h0 + sPar[C::P_GB1 + 0], 0.f);
+                h1 = fmaxf(h1 + sPar[C::P_GB1 + 1], 0.f);
+                float gate = 0.f;
+                if (lane < C::MIDP) {
+                    float g = sPar[C::P_GB2 + lane];
+                    g = fmaf(h0, sPar[C::P_GW2 + lane], g);
+                    g = fmaf(h1, sPar[C::P_GW2 + C::MIDP + lane], g);
+                    gate = 1.f / (1.f + expf(-g));
                 }
-                h0 = fmaxf(h0, 0.f);
-                h1 = fmaxf(h1, 0.f);
-                float g = sPar[C::P_GB2 + tid];
-                g = fmaf(h0, sPar[C::P_GW2 + tid], g);
-                g = fmaf(h1, sPar[C::P_GW2 + C::MIDP + tid], g);
-                s_gate[tid] = 1.f / (1.f + expf(-g));
-            }
-            __syncthreads();
-            // ---- gate-scaled conv3 weights  B[kc][co][8] = W3[k][co] * g[k]  (hi / lo)
-            for (int u = tid; u < C::COUT * C::MCH; u += K3_THREADS) {
-                const int kc = u / C::COUT, co = u - kc * C::COUT;
+                // gate-scaled conv3 weights  B[kc][co][8] = W3[k][co] * g[k]  (hi / lo); the thread's
+                // 8 fp32 W3 values live in registers for the whole kernel
+                const int u = tid;
+                const int kc = u / C::COUT;
                 __align__(16) __half h[8];
                 __align__(16) __half l[8];
 #pragma unroll
                 for (int j = 0; j < 8; j++) {
-                    const int kk = kc * 8 + j;
-                    split1(w3[kk * C::COUT + co] * s_gate[kk], h[j], l[j]);
+                    const float gk = __shfl_sync(0xffffffffu, gate, (kc * 8 + j) & 31);
+                    split1(w3r[j] * gk, h[j], l[j]);
                 }
-                *reinterpret_cast<uint4 *>(sC3 + (size_t)u * 16) = *reinterpret_cast<uint4 *>(h);
-                *reinterpret_cast<uint4 *>(sC3 + C::C3W_HALF_B + (size_t)u * 16) = *reinterpret_cast<uint4 *>(l);
+                if (u < C::COUT * C::MCH) {
+                    *reinterpret_cast<uint4 *>(sC3 + (size_t)u * 16) = *reinterpret_cast<uint4 *>(h);
+                    *reinterpret_cast<uint4 *>(sC3 + C::C3W_HALF_B + (size_t)u * 16) = *reinterpret_cast<uint4 *>(l);
+                }
             }
             tc::fence_async_smem();
             tc::fence_before_sync();
@@ -575,8 +624,8 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
 // the six OSBlocks of osnet_x0_25 (stage 2: 64x32, stage 3: 32x16, stage 4: 16x8)
 // ---------------------------------------------------------------------------
 //            CIN MID MIDP COUT  H   W   R HALO NB DOWN NSTAGE SEG
-using K0 = B3<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2, 8>;
-using K1 = B3<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2, 8>;
+using K0 = B3<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2, 4>;
+using K1 = B3<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2, 4>;
 using K2 = B3<64, 24, 32, 96, 32, 16, 8, 4, 4, true, 2, 5>;
 using K3 = B3<96, 24, 32, 96, 32, 16, 8, 4, 4, false, 2, 5>;
 using K4 = B3<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1, 8>;

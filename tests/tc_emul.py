@@ -166,7 +166,7 @@ def osblock_emul(b, x, blob, offs):
 # csrc/reid_tc3.cu: pointwise on the tensor cores (hi/lo operands), depthwise in fp32
 # ---------------------------------------------------------------------------
 class Cfg3:
-    GEO = [(64, 32, 16, 4, 4, 8), (64, 32, 16, 4, 4, 8), (32, 16, 8, 4, 4, 5), (32, 16, 8, 4, 4, 5),
+    GEO = [(64, 32, 16, 4, 4, 4), (64, 32, 16, 4, 4, 4), (32, 16, 8, 4, 4, 5), (32, 16, 8, 4, 4, 5),
            (16, 8, 16, 0, 1, 8), (16, 8, 16, 0, 1, 8)]
 
     def __init__(self, b):
