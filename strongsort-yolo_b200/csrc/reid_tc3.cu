@@ -95,7 +95,7 @@ struct B3 {
     static_assert(H % R == 0 && H / R == NB, "bands");
     static_assert(MID <= MIDP && COUT == 4 * MID && MIDP <= 32 && COUT * (MIDP / 8) <= K3_THREADS, "OSBlock channel plan");
     static_assert(CG % 2 == 0 && (CG / 2) % CPW == 0 && W % XL == 0, "depthwise warp tasks");
-    static_assert(SEG * TPS <= K3_THREADS / 32, "depthwise tasks fit the CTA");
+    static_assert(SEG * TPS < K3_THREADS / 32, "depthwise warps + one MMA-issuing warp");
     static_assert((NT * CG) % K3_GROUPS == 0, "pointwise drain units divide the groups");
     static_assert(16 * 32 * 36 * 4 <= OFF_C3, "final-epilogue staging fits in the dead maps/weights");
     // global blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
@@ -155,6 +155,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, grp = warp >> 2;          // TMEM lane quadrant / work group
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);            // provably warp-uniform copy of warp
     const int crop = blockIdx.x / C::NB, band = blockIdx.x % C::NB;
     const int row0 = band * C::R - C::HALO;              // image row of band-local row 0
 
@@ -250,7 +251,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
-        if (tid == 0) {
+        if (warp_u == 0 && tc::elect_one()) {
             const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(stg), 2048, 128);
             const uint64_t al0 = dadv(ah0, C::STG_HALF_B / 16);
             const uint64_t bc0 = tc::make_smem_desc(tc::smem_u32(sW), 2 * C::MIDP * 16, 128);
@@ -316,20 +317,28 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     // phase 2: four streams of LightConvs (pointwise on tcgen05, depthwise on the CUDA cores)
     //          + gated conv3 accumulation
     // ------------------------------------------------------------------
-    auto issue_pw = [&](const unsigned char *src, int layer) {      // one thread
+    // MMAs are issued from warp-uniform code by an elected lane (~28 cycles per MMA + commit instead of
+    // ~90 from a divergent single-thread branch, measured) of a warp that has no depthwise rows
+    // (SEG * TPS < 16 warps), so nobody waits for the issue
+    const bool issuer = warp_u == C::SEG * C::TPS;
+    auto issue_pw = [&](const unsigned char *src, int layer, int t0, int t1) {      // issuer warp; tiles [t0, t1)
         const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(src), C::PLANE_B, 128);
         const uint64_t al0 = dadv(ah0, C::MAP_HALF_B / 16);
         const uint64_t b0 = tc::make_smem_desc(tc::smem_u32(sW) + C::C1W_B + C::DNW_B + layer * C::LCW_B,
                                                2 * C::MIDP * 16, 128);
 #pragma unroll
         for (int t = 0; t < C::NT; t++) {
+            if (t < t0 || t >= t1) continue;
             const uint32_t d = tmem + t * C::LCN;
+            if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < C::MIDP / 16; ks++) {
-                tc::mma_f16_ss(d, dadv(ah0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_CAT, ks > 0);
-                tc::mma_f16_ss(d, dadv(al0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_MID, 1);
+                for (int ks = 0; ks < C::MIDP / 16; ks++) {
+                    tc::mma_f16_ss(d, dadv(ah0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_CAT, ks > 0);
+                    tc::mma_f16_ss(d, dadv(al0, t * 128 + ks * 2 * C::NPX), dadv(b0, ks * 4 * C::MIDP), IDESC_MID, 1);
+                }
+                tc::mma_commit(bar_tile + t);
             }
-            tc::mma_commit(bar_tile + t);
+            __syncwarp();
         }
     };
     float w3r[8];                             // conv3 weights of this thread's operand row (kc, co)
@@ -340,18 +349,30 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         for (int j = 0; j < 8; j++) w3r[j] = tid < C::COUT * C::MCH ? w3[(kc * 8 + j) * C::COUT + co] : 0.f;
     }
     // depthwise task of this thread (see B3::XL): column, channel group (parity = lane bit XL), row segment
-    const int dw_par = (lane / C::XL) & 1;
+    // lane = 2 * column + parity (+ 2 * XL * chunk pair): the two lanes of a pixel are adjacent, so their
+    // 8-byte hi (and lo) halves of a 16-byte operand row are one contiguous, conflict-free store
+    const int dw_par = lane & 1;
     const int dw_seg = warp / C::TPS, dw_cb = (warp % C::TPS) % C::NCB;
     const int dw_cg = (((warp % C::TPS) / C::NCB) * C::CPW + lane / (2 * C::XL)) * 2 + dw_par;
-    const int dw_col = dw_cb * C::XL + lane % C::XL;
+    const int dw_col = dw_cb * C::XL + (lane >> 1) % C::XL;
+    long long acc_issue = 0, acc_dw = 0, acc_pub = 0;      // debug accumulators of thread 0 (dbg != nullptr)
     int lc = 0;
     uint32_t tile_par = 0, c3_par = 0;
     bool c3_pending = false;
-    if (tid == 0) issue_pw(sX1, 0);
+    if (issuer) issue_pw(sX1, 0, 0, C::NT);
     for (int s = 0; s < 4; s++) {
         for (int k = 0; k <= s; k++, lc++) {
             const int rem = s - k;                                // LightConvs after this one in the stream
             const bool last = (k == s);
+            // ---- this layer's depthwise taps into registers: shared-memory traffic that rides under
+            //      the wait for the pointwise MMAs instead of the LSU-bound depthwise pass
+            P4 wd[9], bs;
+            {
+                const float *wl = sPar + C::P_LC + lc * (10 * C::MIDP) + dw_cg * 4;
+#pragma unroll
+                for (int tap = 0; tap < 9; tap++) wd[tap] = ldp4(reinterpret_cast<const float4 *>(wl + tap * C::MIDP));
+                bs = ldp4(reinterpret_cast<const float4 *>(wl + 9 * C::MIDP));
+            }
             // ---- pointwise result: TMEM -> fp32 T (zero ring untouched), units (tile, channel group);
             //      all TMEM loads of the thread are in flight before the single wait
             {
@@ -387,7 +408,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             tc::fence_after_sync();
             stamp();                           // T ready
             // the next stream starts from X1: its pointwise conv runs under this depthwise pass
-            if (last && s < 3 && tid == 0) issue_pw(sX1, lc + 1);
+            if (last && s < 3 && issuer) issue_pw(sX1, lc + 1, 0, C::NT);
             // the previous stream's conv3 MMAs read P: done before this stream overwrites it
             if (k == 0 && c3_pending) {
                 if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
@@ -399,89 +420,106 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             //      MMAs that read P have completed); rows [ra, rb) are the "trapezoid" this
             //      layer has to get right for the rem layers after it
             float4 gacc = make_float4(0.f, 0.f, 0.f, 0.f);
-            {
-                const int ra = C::HALO - rem > 0 ? C::HALO - rem : 0;
-                const int rb = C::HALO + C::R + rem < C::RH ? C::HALO + C::R + rem : C::RH;
-                const int per = (rb - ra + C::SEG - 1) / C::SEG;
-                const int r0 = ra + dw_seg * per;
-                int r1 = r0 + per < rb ? r0 + per : rb;
-                if (dw_seg >= C::SEG) r1 = r0;                       // warp-uniform
-                if (r0 < r1) {
-                    const float4 *Tp = sT + dw_cg * C::TPX + dw_col;     // window columns col-1 .. col+1 (ring offset 1)
-                    const float *wl = sPar + C::P_LC + lc * (10 * C::MIDP) + dw_cg * 4;
-                    P4 wd[9];
+            auto dw_rows = [&](int ra, int rb) {
+                if (rb <= ra) return;
+                if (dw_seg >= C::SEG) return;                        // warp-uniform
+                const int r0 = ra + ((rb - ra) * dw_seg) / C::SEG, r1 = ra + ((rb - ra) * (dw_seg + 1)) / C::SEG;
+                if (r0 >= r1) return;
+                const float4 *Tp = sT + dw_cg * C::TPX + dw_col;         // window columns col-1 .. col+1 (ring offset 1)
+                unsigned char *dbase = sP + (dw_cg >> 1) * C::PLANE_B + dw_col * 16 + dw_par * 8;
+                auto ldrow = [&](P4 *w, int trow) {
 #pragma unroll
-                    for (int tap = 0; tap < 9; tap++) wd[tap] = ldp4(reinterpret_cast<const float4 *>(wl + tap * C::MIDP));
-                    const P4 bs = ldp4(reinterpret_cast<const float4 *>(wl + 9 * C::MIDP));
-                    // the even channel group of a K chunk writes the 16-byte hi operand, the odd one the lo
-                    unsigned char *dbase = sP + (dw_cg >> 1) * C::PLANE_B + dw_col * 16 + (dw_par ? C::MAP_HALF_B : 0);
-                    auto ldrow = [&](P4 *w, int trow) {
+                    for (int j = 0; j < 3; j++) w[j] = ldp4(Tp + trow * C::TW + j);
+                };
+                auto dwrow = [&](int lr, const P4 *wa, const P4 *wb, const P4 *wc) {
+                    P4 o = bs;
 #pragma unroll
-                        for (int j = 0; j < 3; j++) w[j] = ldp4(Tp + trow * C::TW + j);
-                    };
-                    auto dwrow = [&](int lr, const P4 *wa, const P4 *wb, const P4 *wc) {
-                        P4 o = bs;
-#pragma unroll
-                        for (int dx = 0; dx < 3; dx++) {
-                            fma4(o, wd[dx], wa[dx]);
-                            fma4(o, wd[3 + dx], wb[dx]);
-                            fma4(o, wd[6 + dx], wc[dx]);
-                        }
-                        float ox = fmaxf(plo(o.a), 0.f), oy = fmaxf(phi(o.a), 0.f);
-                        float oz = fmaxf(plo(o.b), 0.f), ow = fmaxf(phi(o.b), 0.f);
-                        const int gr = row0 + lr;
-                        if (gr < 0 || gr >= C::H) { ox = 0.f; oy = 0.f; oz = 0.f; ow = 0.f; }     // warp-uniform
-                        if (last) {            // rows [ra, rb) == the band's own rows when rem == 0
-                            gacc.x += ox; gacc.y += oy; gacc.z += oz; gacc.w += ow;
-                        }
-                        __half2 h[2], l[2];
-                        split2(ox, oy, h[0], l[0]);
-                        split2(oz, ow, h[1], l[1]);
-                        // partner lane (same pixel, other half of the K chunk): even sends lo, odd sends hi
-                        const uint32_t h0 = *reinterpret_cast<uint32_t *>(&h[0]), h1 = *reinterpret_cast<uint32_t *>(&h[1]);
-                        const uint32_t l0 = *reinterpret_cast<uint32_t *>(&l[0]), l1 = *reinterpret_cast<uint32_t *>(&l[1]);
-                        const uint32_t g0 = __shfl_xor_sync(0xffffffffu, dw_par ? h0 : l0, C::XL);
-                        const uint32_t g1 = __shfl_xor_sync(0xffffffffu, dw_par ? h1 : l1, C::XL);
-                        *reinterpret_cast<uint4 *>(dbase + lr * (C::W * 16)) =
-                            dw_par ? make_uint4(g0, g1, l0, l1) : make_uint4(h0, h1, g0, g1);
-                    };
-                    P4 w0[3], w1[3], w2[3];                        // rotating 3-row window (no register moves)
-                    ldrow(w0, r0);
-                    ldrow(w1, r0 + 1);
-                    for (int lr = r0; lr < r1; lr += 3) {
-                        ldrow(w2, lr + 2);
-                        dwrow(lr, w0, w1, w2);
-                        if (lr + 1 < r1) {
-                            ldrow(w0, lr + 3);
-                            dwrow(lr + 1, w1, w2, w0);
-                        }
-                        if (lr + 2 < r1) {
-                            ldrow(w1, lr + 4);
-                            dwrow(lr + 2, w2, w0, w1);
-                        }
+                    for (int dx = 0; dx < 3; dx++) {
+                        fma4(o, wd[dx], wa[dx]);
+                        fma4(o, wd[3 + dx], wb[dx]);
+                        fma4(o, wd[6 + dx], wc[dx]);
+                    }
+                    float ox = fmaxf(plo(o.a), 0.f), oy = fmaxf(phi(o.a), 0.f);
+                    float oz = fmaxf(plo(o.b), 0.f), ow = fmaxf(phi(o.b), 0.f);
+                    const int gr = row0 + lr;
+                    if (gr < 0 || gr >= C::H) { ox = 0.f; oy = 0.f; oz = 0.f; ow = 0.f; }     // warp-uniform
+                    if (last) {                // rows [ra, rb) == the band's own rows when rem == 0
+                        gacc.x += ox; gacc.y += oy; gacc.z += oz; gacc.w += ow;
+                    }
+                    __half2 h[2], l[2];
+                    split2(ox, oy, h[0], l[0]);
+                    split2(oz, ow, h[1], l[1]);
+                    unsigned char *d = dbase + lr * (C::W * 16);
+                    *reinterpret_cast<uint2 *>(d) = make_uint2(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]));
+                    *reinterpret_cast<uint2 *>(d + C::MAP_HALF_B) =
+                        make_uint2(*reinterpret_cast<uint32_t *>(&l[0]), *reinterpret_cast<uint32_t *>(&l[1]));
+                };
+                P4 w0[3], w1[3], w2[3];                            // rotating 3-row window (no register moves)
+                ldrow(w0, r0);
+                ldrow(w1, r0 + 1);
+                for (int lr = r0; lr < r1; lr += 3) {
+                    ldrow(w2, lr + 2);
+                    dwrow(lr, w0, w1, w2);
+                    if (lr + 1 < r1) {
+                        ldrow(w0, lr + 3);
+                        dwrow(lr + 1, w1, w2, w0);
+                    }
+                    if (lr + 2 < r1) {
+                        ldrow(w1, lr + 4);
+                        dwrow(lr + 2, w2, w0, w1);
                     }
                 }
+            };
+            auto publish = [&]() {             // operand map writes -> visible to the tensor core, CTA-wide
+                tc::fence_async_smem();
+                tc::fence_before_sync();
+                __syncthreads();
+                tc::fence_after_sync();
+            };
+            const int ra = C::HALO - rem > 0 ? C::HALO - rem : 0;
+            const int rb = C::HALO + C::R + rem < C::RH ? C::HALO + C::R + rem : C::RH;
+            if (!last) {
+                // the next LightConv's pointwise conv is per pixel: its MMAs on the upper half of the
+                // tiles are issued as soon as the upper rows are written and run under the lower
+                // half's depthwise pass; the lower half's MMAs run under the upper half's drain
+                if (C::NT >= 2) {
+                    constexpr int TH_ = C::NT / 2, HR = TH_ * 128 / C::W;
+                    long long c0 = clock64();
+                    dw_rows(ra, rb < HR ? rb : HR);
+                    long long c1 = clock64();
+                    publish();
+                    long long c2 = clock64();
+                    if (issuer) issue_pw(sP, lc + 1, 0, TH_);
+                    long long c3 = clock64();
+                    dw_rows(ra > HR ? ra : HR, rb);
+                    long long c4 = clock64();
+                    publish();
+                    long long c5 = clock64();
+                    if (issuer) issue_pw(sP, lc + 1, TH_, C::NT);
+                    long long c6 = clock64();
+                    acc_dw += (c1 - c0) + (c4 - c3); acc_pub += (c2 - c1) + (c5 - c4); acc_issue += (c3 - c2) + (c6 - c5);
+                } else {
+                    dw_rows(ra, rb);
+                    publish();
+                    if (issuer) issue_pw(sP, lc + 1, 0, C::NT);
+                }
+                stamp();                       // depthwise done, next pointwise issued
+                continue;
             }
-            if (last) {                        // the column lanes of a (segment, column block, channel group) are adjacent
+            dw_rows(ra, rb);
+            {                                  // the column lanes of a (segment, column block, channel group) are adjacent
 #pragma unroll
-                for (int off = C::XL / 2; off >= 1; off >>= 1) {
+                for (int off = C::XL; off >= 2; off >>= 1) {
                     gacc.x += __shfl_xor_sync(0xffffffffu, gacc.x, off);
                     gacc.y += __shfl_xor_sync(0xffffffffu, gacc.y, off);
                     gacc.z += __shfl_xor_sync(0xffffffffu, gacc.z, off);
                     gacc.w += __shfl_xor_sync(0xffffffffu, gacc.w, off);
                 }
-                if (dw_seg < C::SEG && (lane % C::XL) == 0)
+                if (dw_seg < C::SEG && ((lane >> 1) % C::XL) == 0)
                     *reinterpret_cast<float4 *>(s_scr + ((dw_seg * C::NCB + dw_cb) * C::CG + dw_cg) * 4) = gacc;
             }
-            tc::fence_async_smem();
-            tc::fence_before_sync();
-            __syncthreads();
-            tc::fence_after_sync();
+            publish();
             stamp();                           // depthwise done
-            if (!last) {
-                if (tid == 0) issue_pw(sP, lc + 1);
-                continue;
-            }
             // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid -> scaled conv3 weights
             if (warp == 0) {
                 float tot = 0.f;
@@ -534,23 +572,26 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             tc::fence_before_sync();
             __syncthreads();
             tc::fence_after_sync();
-            if (tid == 0) {
+            if (issuer) {
                 const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(sP), C::PLANE_B, 128);
                 const uint64_t al0 = dadv(ah0, C::MAP_HALF_B / 16);
                 const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sC3), C::COUT * 16, 128);
                 const uint64_t bl0 = dadv(bh0, C::C3W_HALF_B / 16);
                 const uint32_t acc0 = (C::DOWN || s > 0) ? 1u : 0u;
+                if (tc::elect_one()) {
 #pragma unroll
-                for (int i = 0; i < C::NIT; i++) {
-                    const uint32_t d = tmem + C::TM_C3 + i * C::COUT;
+                    for (int i = 0; i < C::NIT; i++) {
+                        const uint32_t d = tmem + C::TM_C3 + i * C::COUT;
 #pragma unroll
-                    for (int ks = 0; ks < C::MIDP / 16; ks++) {
-                        const int ka = (C::IT0 + i) * 128 + ks * 2 * C::NPX, kb = ks * 2 * C::COUT;
-                        mma3(d, dadv(ah0, ka), dadv(al0, ka), dadv(bh0, kb), dadv(bl0, kb), IDESC_OUT,
-                             ks > 0 ? 1u : acc0);
+                        for (int ks = 0; ks < C::MIDP / 16; ks++) {
+                            const int ka = (C::IT0 + i) * 128 + ks * 2 * C::NPX, kb = ks * 2 * C::COUT;
+                            mma3(d, dadv(ah0, ka), dadv(al0, ka), dadv(bh0, kb), dadv(bl0, kb), IDESC_OUT,
+                                 ks > 0 ? 1u : acc0);
+                        }
                     }
+                    tc::mma_commit(bar_c3);
                 }
-                tc::mma_commit(bar_c3);
+                __syncwarp();
             }
             c3_pending = true;
             stamp();                           // gate + conv3 issued
@@ -612,7 +653,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         __syncwarp();
     }
     stamp();                                   // final epilogue done
-    if (dbg && blockIdx.x == 0 && tid == 0) dbg[0] = dbg_n;
+    if (dbg && blockIdx.x == 0 && tid == 0) { dbg[0] = dbg_n; dbg[60] = acc_issue; dbg[61] = acc_dw; dbg[62] = acc_pub; }
     if (!ok) { if (tid == 0) atomicExch(status, 5); }
     tc::fence_before_sync();
     if (C::NB > 1) cluster.sync(); else __syncthreads();     // remote sGap reads are done
@@ -624,12 +665,12 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
 // the six OSBlocks of osnet_x0_25 (stage 2: 64x32, stage 3: 32x16, stage 4: 16x8)
 // ---------------------------------------------------------------------------
 //            CIN MID MIDP COUT  H   W   R HALO NB DOWN NSTAGE SEG
-using K0 = B3<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2, 4>;
-using K1 = B3<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2, 4>;
+using K0 = B3<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2, 3>;
+using K1 = B3<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2, 3>;
 using K2 = B3<64, 24, 32, 96, 32, 16, 8, 4, 4, true, 2, 5>;
 using K3 = B3<96, 24, 32, 96, 32, 16, 8, 4, 4, false, 2, 5>;
-using K4 = B3<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1, 8>;
-using K5 = B3<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1, 8>;
+using K4 = B3<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1, 7>;
+using K5 = B3<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1, 7>;
 
 template <class C>
 int launch3(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,

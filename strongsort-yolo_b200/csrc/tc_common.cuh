@@ -53,6 +53,16 @@ __device__ __forceinline__ void mma_f16_ss(uint32_t tmem_d, uint64_t a_desc, uin
         : "memory");
 }
 
+// One lane of a CONVERGED warp.  Issue tcgen05.mma / commit from warp-uniform code under this
+// predicate: measured on B200 (tools/probes/mma_issue_probe.cu) an MMA + commit costs the issuing
+// thread ~28 cycles this way and ~90 cycles from a divergent `if (tid == 0)` branch, where the
+// compiler wraps every UTCHMMA in an ELECT / BRA.U.ANY loop.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(pred));
+    return pred != 0;
+}
+
 // all previously issued MMAs of this thread arrive on the mbarrier when done
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(

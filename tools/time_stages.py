@@ -68,6 +68,8 @@ def main():
             d = dbg.cpu().numpy()
             k = int(d[0])
             out[f"osblock{b}{tag}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
+            if mode == 2:
+                out[f"osblock{b}_acc_issue_dw_publish"] = [int(d[60]), int(d[61]), int(d[62])]
     # stage-A-like clamped cost matrices from the live tracker
     a, b = trk.debug_costs()
     for name, m in (("lsap_stageA", a), ("lsap_stageB", b)):
