@@ -1,10 +1,9 @@
 """One ReID forward (all kernels of ssb_reid) on a C2 frame, for `ncu --set full`:
 
-  ncu --set full --clock-control none --import-source on \
-      -k regex:'osblock_tc|stem_tc|pw_tc|tail_tc' -s 22 -c 11 -o gpurun_out/prof_reid \
-      python tools/ncu_reid.py
+  ncu --set full --clock-control none --import-source on --profile-from-start off \
+      -o gpurun_out/prof_reid python tools/ncu_reid.py
 
-2 warm forwards (22 matching launches, skipped with -s) + 1 profiled forward.
+2 warm forwards, then one forward between cudaProfilerStart/Stop (the only one ncu captures).
 """
 import ctypes as C
 import os
@@ -31,10 +30,15 @@ def main():
     feats = torch.zeros((n, 512), dtype=torch.float32, device="cuda")
     sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.ssb_crop_boxes(P(dets), n, 1080, 1920, P(boxes), sp))
-    reps = int(sys.argv[1]) if len(sys.argv) > 1 else 3
-    for _ in range(reps):
+    backend = sys.argv[1] if len(sys.argv) > 1 else "tc"
+    trk.set_reid_backend(backend)
+    for r in range(3):
+        if r == 2:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.start()
         _lib.check(lib.ssb_reid(trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), sp))
     torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
     print("crops", n, "status", trk.reid_tc_status())
 
 
