@@ -709,6 +709,7 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int quad = warp & 3, grp = warp >> 2;
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
     unsigned char *sStg = smem + C::OFF_STG, *sW = smem + C::OFF_W;
     float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);     // [2] mma, [2]=weights
@@ -801,12 +802,12 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         tc::fence_before_sync();
         __syncthreads();
         tc::fence_after_sync();
-        if (tid == 0) {
+        if (warp_u == 0 && tc::elect_one()) {      // warp-uniform issue: ~3x cheaper than `if (tid == 0)` (tc_common.cuh)
             const uint32_t a_hi = tc::smem_u32(stg), a_lo = a_hi + C::STG_HALF_B;
             const uint32_t b_hi = tc::smem_u32(sW), b_lo = b_hi + C::W_HALF_B;
             constexpr uint32_t LBO_B = C::COUT * 16;
             const uint32_t d = tmem + buf * C::COUT;
-#pragma unroll 1
+#pragma unroll
             for (int ks = 0; ks < C::CIN / 16; ks++) {
                 const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
                 const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
@@ -886,12 +887,12 @@ tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    if (tid == 0) {
+    if (__shfl_sync(0xffffffffu, warp, 0) == 0 && tc::elect_one()) {
         constexpr uint32_t IDESC = tc::make_idesc_f16(128, C::COUT);
         const uint32_t a_hi = tc::smem_u32(stg), a_lo = a_hi + C::STG_HALF_B;
         const uint32_t b_hi = tc::smem_u32(sW), b_lo = b_hi + C::W_HALF_B;
         constexpr uint32_t LBO_B = C::COUT * 16;
-#pragma unroll 1
+#pragma unroll
         for (int ks = 0; ks < C::CIN / 16; ks++) {
             const uint64_t ah = tc::make_smem_desc(a_hi + ks * 2 * 2048, 2048, 128);
             const uint64_t al = tc::make_smem_desc(a_lo + ks * 2 * 2048, 2048, 128);
@@ -981,7 +982,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);     // [0] mma, [1] weights
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
-    if (warp == 0) tc::tmem_alloc(s_tmem, 256);
+    if (warp == 0) tc::tmem_alloc(s_tmem, 512);
     if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
     if (tid < 16) sBias[tid] = reinterpret_cast<const float *>(wblob + C::G_BIAS)[tid];
     // zero the operand map (padding rows/cols and the 4 pad channels stay zero)
@@ -1035,21 +1036,24 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
-    if (tid == 0) {
+    // warp-uniform issue by an elected lane (~3x cheaper per MMA than `if (tid == 0)`, tc_common.cuh);
+    // hi and lo weight rows concatenated along N: D[:, 0:16] += Ah*Bh + Al*Bh, D[:, 16:32] += Ah*Bl --
+    // two reads of the 4 KB A tile (what bounds an M=128, K=16 MMA) per product instead of three
+    if (__shfl_sync(0xffffffffu, warp, 0) == 0 && tc::elect_one()) {
         constexpr uint32_t IDESC = tc::make_idesc_f16(128, 16);
+        constexpr uint32_t IDESC_CAT = tc::make_idesc_f16(128, 32);
         const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(sMap), C::PLANE_B, 128);
         const uint64_t al0 = desc_adv(ah0, C::MAP_HALF_B / 16);
-        const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(sW), 16 * 16, 128);
-        const uint64_t bl0 = desc_adv(bh0, C::W_HALF_B / 16);
+        const uint64_t bc0 = tc::make_smem_desc(tc::smem_u32(sW), 32 * 16, 128);      // [tap][kc][hi 16 | lo 16][8]
 #pragma unroll 1
         for (int t = 0; t < C::NT; t++) {
-            const uint32_t d = tmem + t * 16;
+            const uint32_t d = tmem + t * 32;
             const uint64_t aht = desc_adv(ah0, t * 128), alt = desc_adv(al0, t * 128);
 #pragma unroll
             for (int tap = 0; tap < 16; tap++) {
                 const int po = (tap >> 2) * C::WPS + (tap & 3);
-                mma3(d, desc_adv(aht, po), desc_adv(alt, po), desc_adv(bh0, tap * 32), desc_adv(bl0, tap * 32),
-                     IDESC, tap != 0);
+                tc::mma_f16_ss(d, desc_adv(aht, po), desc_adv(bc0, tap * 64), IDESC_CAT, tap != 0);
+                tc::mma_f16_ss(d, desc_adv(alt, po), desc_adv(bc0, tap * 64), IDESC, 1);
             }
         }
         tc::mma_commit(bar);
@@ -1059,8 +1063,11 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     // ---- epilogue: bias + ReLU -> sConv[lcy][cx][16]; rows outside the conv map = -inf
     for (int t = grp; t < C::NT; t += OSB_GROUPS) {
         const int p = t * 128 + quad * 32 + lane;
-        float v[16];
-        tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * 16, v);
+        float v[16], w[16];
+        tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * 32, v);
+        tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * 32 + 16, w);
+#pragma unroll
+        for (int j = 0; j < 16; j++) v[j] += w[j];
         const int lcy = p / C::WPS, cx = p - lcy * C::WPS;
         if (lcy < C::CROWS && cx < 64) {
             const int gcy = cy0 + lcy;
@@ -1099,7 +1106,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     if (!ok && tid == 0) atomicExch(status, 4);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 256);
+    if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
 using PwT1 = PwCfg<64, 64, 64, 32, true>;     // after conv2: 64x32x64 -> 32x16x64

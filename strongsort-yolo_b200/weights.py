@@ -259,7 +259,8 @@ def pack_tc(tensors):
                         wt[a * 4 + b, e:e + 3, :] = sw[2 * a + dy, 2 * b + dx]
     hi, lo = _hi_lo(np.ascontiguousarray(wt.reshape(16, 2, 8, 16).transpose(0, 1, 3, 2)))   # [tap][kc][n][8]
     offs.append(len(blob))
-    blob += _pad128(hi.tobytes() + lo.tobytes() + _pad128(T["stem.b"].astype(np.float32).tobytes()))
+    cat = np.concatenate([hi, lo], axis=2)                    # [tap][kc][hi 16 rows | lo 16 rows][8]
+    blob += _pad128(cat.tobytes() + _pad128(T["stem.b"].astype(np.float32).tobytes()))
     for bi in range(6):
         offs.append(len(blob))
         blob += _pad128(_pack_tc3_block(T, bi))

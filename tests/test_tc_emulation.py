@@ -59,9 +59,8 @@ def test_stem_space_to_depth_packing(state_dict):
     T = dict(tensors)
     sec = bytes(blob[int(offs[9]):])
     half = 16 * 16 * 16 * 2
-    hi = np.frombuffer(sec[:half], dtype=np.float16).astype(np.float64)
-    lo = np.frombuffer(sec[half:2 * half], dtype=np.float16).astype(np.float64)
-    wt = (hi + lo).reshape(16, 2, 16, 8).transpose(0, 1, 3, 2).reshape(16, 16, 16)     # [tap][k][co]
+    cat = np.frombuffer(sec[:2 * half], dtype=np.float16).astype(np.float64).reshape(16, 2, 32, 8)
+    wt = (cat[:, :, :16] + cat[:, :, 16:]).transpose(0, 1, 3, 2).reshape(16, 16, 16)   # [tap][k][co], hi | lo rows
     bias = np.frombuffer(sec[2 * half:2 * half + 64], dtype=np.float32)
     np.testing.assert_array_equal(bias, T["stem.b"])
     rng = np.random.default_rng(0)
