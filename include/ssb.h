@@ -165,6 +165,20 @@ int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_
                  float *out_dev, int32_t *count_dev, void *scratch_dev,
                  ssb_stream_t stream);
 
+/* YOLOv8 detect / pose head decode: raw float32 [4*16 + nc + 3*kpts, A] (DFL bins,
+ * class logits, keypoint x,y,vis) for a network input of in_h x in_w (multiples of 32; A =
+ * ssb_yolo_num_anchors, stride-8/16/32 levels concatenated) -> pred float32 [4 + nc + 3*kpts, A],
+ * the layout ssb_yolo_nms consumes (extra channels = 3*kpts).                                    */
+int ssb_yolo_num_anchors(int in_h, int in_w);
+int ssb_yolo_decode_v8(const float *raw_dev, int num_classes, int num_kpts, int in_h, int in_w,
+                       float *pred_out_dev, ssb_stream_t stream);
+
+/* camera-motion compensation, tracker side (upstream Track.camera_update after its ECC call,
+ * SURVEY.md A.9): warp2x3_host = row-major 2x3 matrix (host doubles, e.g. cv2.findTransformECC's
+ * result with the translation scaled back to full resolution), applied to the tl/br corners of
+ * every live track; rewrites mean[:4].  Called between frames, outside ssb_update.             */
+int ssb_camera_update(ssb_tracker *t, const double *warp2x3_host, ssb_stream_t stream);
+
 /* ---- introspection for tests: copy the live track table (list order) ----- */
 /* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];
  * mean float64 [T,8]; cov [T,8,8]; feat float32 [T,dim]                     */

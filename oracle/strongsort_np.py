@@ -161,6 +161,21 @@ class Track:
         self.age += 1
         self.time_since_update += 1
 
+    def camera_update(self, warp_matrix):
+        """Upstream Track.camera_update after its ECC call: warp the tl / br corners
+        with the 2x3 matrix (homogeneous row appended) and rewrite mean[:4].  float64."""
+        m = np.vstack([np.asarray(warp_matrix, dtype=np.float64).reshape(2, 3), [0.0, 0.0, 1.0]])
+        tlbr = self.to_tlwh()
+        tlbr[2:] = tlbr[:2] + tlbr[2:]
+        x1, y1, x2, y2 = tlbr
+        x1_ = m[0, 0] * x1 + m[0, 1] * y1 + m[0, 2]
+        y1_ = m[1, 0] * x1 + m[1, 1] * y1 + m[1, 2]
+        x2_ = m[0, 0] * x2 + m[0, 1] * y2 + m[0, 2]
+        y2_ = m[1, 0] * x2 + m[1, 1] * y2 + m[1, 2]
+        w, h = x2_ - x1_, y2_ - y1_
+        cx, cy = x1_ + w / 2, y1_ + h / 2
+        self.mean[:4] = [cx, cy, w / h, h]
+
     def update(self, detection, class_id, conf):
         self.conf = conf
         self.class_id = int(class_id)
@@ -339,6 +354,12 @@ class Tracker:
     def predict(self):
         for track in self.tracks:
             track.predict()
+
+    def camera_update(self, warp_matrix):
+        """One warp per frame applied to every track (upstream estimates the same ECC warp once
+        per track)."""
+        for track in self.tracks:
+            track.camera_update(warp_matrix)
 
     def update(self, detections, classes, confidences):
         matches, unmatched_tracks, unmatched_detections = self._match(detections)

@@ -17,6 +17,7 @@ SYMBOLS = [
     "ssb_crop_boxes", "ssb_kf_predict", "ssb_kf_update", "ssb_kf_gating",
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
+    "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_camera_update",
 ]
 
 SSB_CNT_N = 8
@@ -83,12 +84,16 @@ def load():
     lib.ssb_nms_scratch_bytes.argtypes = [i32]
     lib.ssb_nms_scratch_bytes.restype = i64
     lib.ssb_yolo_nms.argtypes = [vp, i32, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp]
+    lib.ssb_yolo_num_anchors.argtypes = [i32, i32]
+    lib.ssb_yolo_num_anchors.restype = i32
+    lib.ssb_yolo_decode_v8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.ssb_camera_update.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.ssb_export_tracks.argtypes = [vp] * 11
     lib.ssb_tc_probe.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.ssb_debug_cost_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     for name in SYMBOLS:
         fn = getattr(lib, name)
-        if fn.restype is C.c_int and name not in ("ssb_version", "ssb_reid_num_tensors"):
+        if fn.restype is C.c_int and name not in ("ssb_version", "ssb_reid_num_tensors", "ssb_yolo_num_anchors"):
             fn.restype = i32
     _lib = lib
     return lib

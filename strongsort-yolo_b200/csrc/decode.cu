@@ -1,0 +1,73 @@
+// YOLOv8 detection / pose head decode on the GPU: the raw head tensor
+//   raw [4*16 + nc + 3*K][A]   (DFL box bins, class logits, K keypoints x (x, y, vis)), A = anchors of
+//   the stride-8/16/32 levels of an (in_h x in_w) network input, level after level, row-major
+// becomes the decoded tensor ssb_yolo_nms() consumes
+//   pred [4 + nc + 3*K][A]     (cx, cy, w, h in input pixels, class probabilities, keypoints).
+// Arithmetic follows ultralytics' Detect/Pose inference path (third-party, not vendored): softmax over
+// the 16 DFL bins -> expectation -> dist2bbox(xywh) around the anchor centre (+0.5) -> x stride;
+// sigmoid class scores; keypoints (v*2 + anchor - 0.5) * stride, visibility sigmoid.  float32.
+//
+// One thread per anchor; every channel row is read/written coalesced over anchors.  HBM-bound:
+// (64 + nc + 3K + 4 + nc + 3K) * A * 4 bytes = 1.9 MB for nc = 80, A = 8400 -- a few microseconds.
+#include "ssb_common.cuh"
+
+namespace {
+
+__global__ void yolo_decode_v8_kernel(const float *__restrict__ raw, int nc, int nk, int in_h, int in_w,
+                                      int A, float *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    // level / grid position of anchor a
+    int rem = a, stride = 8, gw = in_w / 8, gh = in_h / 8;
+    for (int l = 0; l < 3; l++) {
+        if (rem < gw * gh) break;
+        rem -= gw * gh;
+        stride *= 2; gw = in_w / stride; gh = in_h / stride;
+    }
+    const float ax = (float)(rem % gw) + 0.5f, ay = (float)(rem / gw) + 0.5f, fs = (float)stride;
+    float d[4];
+#pragma unroll
+    for (int s = 0; s < 4; s++) {
+        float v[16], m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; j++) { v[j] = raw[(size_t)(s * 16 + j) * A + a]; m = fmaxf(m, v[j]); }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) { v[j] = expf(v[j] - m); sum += v[j]; }
+        float e = 0.f;
+#pragma unroll
+        for (int j = 0; j < 16; j++) e += (v[j] / sum) * (float)j;
+        d[s] = e;
+    }
+    const float x1 = ax - d[0], y1 = ay - d[1], x2 = ax + d[2], y2 = ay + d[3];
+    out[(size_t)0 * A + a] = ((x1 + x2) / 2.f) * fs;
+    out[(size_t)1 * A + a] = ((y1 + y2) / 2.f) * fs;
+    out[(size_t)2 * A + a] = (x2 - x1) * fs;
+    out[(size_t)3 * A + a] = (y2 - y1) * fs;
+    for (int c = 0; c < nc; c++)
+        out[(size_t)(4 + c) * A + a] = 1.f / (1.f + expf(-raw[(size_t)(64 + c) * A + a]));
+    for (int k = 0; k < nk; k++) {
+        const size_t ri = (size_t)(64 + nc + 3 * k) * A + a, oi = (size_t)(4 + nc + 3 * k) * A + a;
+        out[oi] = (raw[ri] * 2.f + (ax - 0.5f)) * fs;
+        out[oi + A] = (raw[ri + A] * 2.f + (ay - 0.5f)) * fs;
+        out[oi + 2 * (size_t)A] = 1.f / (1.f + expf(-raw[ri + 2 * (size_t)A]));
+    }
+}
+
+}  // namespace
+
+extern "C" int ssb_yolo_num_anchors(int in_h, int in_w) {
+    if (in_h <= 0 || in_w <= 0 || in_h % 32 || in_w % 32) return -1;
+    return (in_h / 8) * (in_w / 8) + (in_h / 16) * (in_w / 16) + (in_h / 32) * (in_w / 32);
+}
+
+extern "C" int ssb_yolo_decode_v8(const float *raw_dev, int num_classes, int num_kpts, int in_h, int in_w,
+                                  float *pred_out_dev, ssb_stream_t stream) {
+    if (!raw_dev || !pred_out_dev) { ssb_set_error("null argument"); return -1; }
+    const int A = ssb_yolo_num_anchors(in_h, in_w);
+    if (A <= 0 || num_classes < 1 || num_kpts < 0) { ssb_set_error("bad head geometry %dx%d nc=%d kpts=%d", in_h, in_w, num_classes, num_kpts); return -1; }
+    yolo_decode_v8_kernel<<<(A + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw_dev, num_classes, num_kpts, in_h, in_w, A,
+                                                                             pred_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}

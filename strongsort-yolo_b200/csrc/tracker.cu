@@ -1183,6 +1183,33 @@ extern "C" int ssb_crop_boxes(const float *dets_dev, int n, int h, int w, int32_
     return 0;
 }
 
+// Track.camera_update for every live track: warp the tl / br corners with
+// the 2x3 matrix and rewrite mean[:4].  Same float64 expression order as oracle Track.camera_update.
+struct Warp6 { double a, b, tx, c, d, ty; };
+__global__ void camera_update_kernel(TrackTable tt, Warp6 m) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= tt.scalars[SC_N_TRACKS]) return;
+    double *mean = tt.mean + (size_t)tt.order[i] * 8;
+    const double h0 = mean[3], w0 = mean[2] * h0;
+    const double x1 = mean[0] - w0 / 2, y1 = mean[1] - h0 / 2;
+    const double x2 = x1 + w0, y2 = y1 + h0;
+    const double x1_ = m.a * x1 + m.b * y1 + m.tx, y1_ = m.c * x1 + m.d * y1 + m.ty;
+    const double x2_ = m.a * x2 + m.b * y2 + m.tx, y2_ = m.c * x2 + m.d * y2 + m.ty;
+    const double w = x2_ - x1_, h = y2_ - y1_;
+    mean[0] = x1_ + w / 2;
+    mean[1] = y1_ + h / 2;
+    mean[2] = w / h;
+    mean[3] = h;
+}
+
+extern "C" int ssb_camera_update(ssb_tracker *t, const double *warp2x3_host, ssb_stream_t stream) {
+    if (!t || !warp2x3_host) { ssb_set_error("null argument"); return -1; }
+    Warp6 m = {warp2x3_host[0], warp2x3_host[1], warp2x3_host[2], warp2x3_host[3], warp2x3_host[4], warp2x3_host[5]};
+    camera_update_kernel<<<(t->dims.S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->tt, m);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
 extern "C" int ssb_kf_predict(double *mean_dev, double *cov_dev, int n, ssb_stream_t stream) {
     if (n <= 0) return 0;
     kf_predict_arrays_kernel<<<(n * 32 + 127) / 128, 128, 0, (cudaStream_t)stream>>>(mean_dev, cov_dev, n);

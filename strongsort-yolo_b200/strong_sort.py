@@ -209,6 +209,24 @@ class StrongSORT:
         return rows[:, :7]
 
     # ------------------------------------------------------------------
+    def camera_update(self, previous_img, current_img, warp_matrix=None):
+        """Upstream ``tracker.camera_update(prev, curr)``, called by the stream loop
+        between frames when ECC is on.  Upstream runs cv2.findTransformECC once PER TRACK on the
+        same image pair; here the 2x3 warp is estimated once per frame (``ecc.ecc_warp``: same
+        0.1x grayscale, MOTION_EUCLIDEAN, eps 1e-5, 100 iterations) -- or passed in as
+        ``warp_matrix`` -- and applied to every live track by one kernel."""
+        if warp_matrix is None:
+            from . import ecc
+            warp_matrix = ecc.ecc_warp(previous_img, current_img)
+            if warp_matrix is None:
+                return None
+        w = np.ascontiguousarray(np.asarray(warp_matrix, dtype=np.float64).reshape(2, 3))
+        arr = (C.c_double * 6)(*w.reshape(-1).tolist())
+        _lib.check(self._lib.ssb_camera_update(self._h, arr, C.c_void_p(self.stream.cuda_stream)),
+                   "ssb_camera_update")
+        return w
+
+    # ------------------------------------------------------------------
     def extract_features(self, ori_img, boxes_xyxy_int):
         """OSNet embeddings of integer crop boxes (parity tests / ssb_reid)."""
         torch = self._torch

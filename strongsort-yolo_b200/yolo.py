@@ -56,6 +56,79 @@ class YoloNMS:
         return out[:m].cpu().numpy()
 
 
+class YoloV8Decode:
+    """Raw YOLOv8 detect / pose head [4*16 + nc + 3*kpts, A] -> decoded [4 + nc + 3*kpts, A]
+    (csrc/decode.cu), the tensor ``YoloNMS`` consumes."""
+
+    def __init__(self, num_classes=80, num_kpts=0, in_h=640, in_w=640, device="cuda:0"):
+        torch = _lib.require_cuda()
+        self._torch, self._lib = torch, _lib.load()
+        self.device = torch.device(device)
+        self.nc, self.nk, self.in_h, self.in_w = int(num_classes), int(num_kpts), int(in_h), int(in_w)
+        self.A = int(self._lib.ssb_yolo_num_anchors(self.in_h, self.in_w))
+        if self.A <= 0:
+            raise ValueError("network input size must be a positive multiple of 32")
+        self._out = torch.empty((4 + self.nc + 3 * self.nk, self.A), dtype=torch.float32, device=self.device)
+
+    def __call__(self, raw, stream=None):
+        torch = self._torch
+        if raw.dim() == 3:
+            raw = raw[0]
+        if tuple(raw.shape) != (64 + self.nc + 3 * self.nk, self.A):
+            raise ValueError(f"raw head shape {tuple(raw.shape)} != {(64 + self.nc + 3 * self.nk, self.A)}")
+        raw = raw.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.ssb_yolo_decode_v8(_lib.ptr(raw), self.nc, self.nk, self.in_h, self.in_w,
+                                                _lib.ptr(self._out), C.c_void_p(st.cuda_stream)),
+                   "ssb_yolo_decode_v8")
+        return self._out
+
+
+def synth_raw_head_v8(dets, num_classes, in_h, in_w, rng=None, kpts=None):
+    """Synthetic RAW v8 head [64 + nc (+3*K), A] whose decode + NMS gives (close to) ``dets`` [N,6]
+    (boxes in network-input pixels): each detection is written into the anchor of the finest level
+    whose cell contains its centre and whose ltrb distances fit the 0..15 DFL range, as one-hot-ish
+    DFL logits interpolating the fractional distance; all other anchors get background logits."""
+    from math import floor, log
+    rng = rng or np.random.default_rng(0)
+    dets = np.asarray(dets, dtype=np.float32).reshape(-1, 6)
+    nk = 0 if kpts is None else int(np.asarray(kpts).shape[1])
+    levels, base = [], 0
+    for s in (8, 16, 32):
+        levels.append((s, in_h // s, in_w // s, base))
+        base += (in_h // s) * (in_w // s)
+    A = base
+    raw = np.zeros((64 + num_classes + 3 * nk, A), dtype=np.float32)
+    raw[:64] = rng.normal(0, 0.1, (64, A))
+    raw[64:64 + num_classes] = rng.uniform(-6.0, -3.5, (num_classes, A))       # sigmoid < 0.03
+    for i, (x1, y1, x2, y2, conf, cls) in enumerate(dets):
+        cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+        for s, gh, gw, b0 in levels:
+            gx, gy = int(floor(cx / s)), int(floor(cy / s))
+            if not (0 <= gx < gw and 0 <= gy < gh):
+                continue
+            ax, ay = (gx + 0.5) * s, (gy + 0.5) * s
+            d = np.array([ax - x1, ay - y1, x2 - ax, y2 - ay], dtype=np.float64) / s
+            if d.min() < 0 or d.max() > 14.5:
+                continue
+            a = b0 + gy * gw + gx
+            for side in range(4):
+                j, f = int(floor(d[side])), d[side] - floor(d[side])
+                logit = np.full(16, -12.0)
+                f = min(max(f, 1e-4), 1 - 1e-4)
+                logit[j], logit[j + 1] = log(1 - f), log(f)              # softmax -> (1-f, f)
+                raw[side * 16:(side + 1) * 16, a] = logit
+            p = min(max(float(conf), 1e-4), 1 - 1e-4)
+            raw[64 + int(cls), a] = log(p / (1 - p))
+            if nk:
+                kp = np.asarray(kpts)[i]
+                raw[64 + num_classes + 0:64 + num_classes + 3 * nk:3, a] = (kp[:, 0] / s - (gx + 0.5 - 0.5)) / 2
+                raw[64 + num_classes + 1:64 + num_classes + 3 * nk:3, a] = (kp[:, 1] / s - (gy + 0.5 - 0.5)) / 2
+                raw[64 + num_classes + 2:64 + num_classes + 3 * nk:3, a] = 4.0
+            break
+    return raw
+
+
 def synth_head(dets, num_classes=80, num_anchors=8400, rng=None, extra=None, jitter=3):
     """Synthetic decoded head tensor [4+nc(+extra), A] float32 whose NMS output
     is (close to) ``dets`` [N,6]: every detection spawns ``jitter`` overlapping

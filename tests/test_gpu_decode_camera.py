@@ -1,0 +1,66 @@
+"""GPU: YOLOv8 head decode (csrc/decode.cu) and the batched camera-motion update against the
+CPU restatements, through the C-ABI."""
+import numpy as np
+import pytest
+
+from helpers import FeatureBank, assert_rows_equal, assert_tables_equal
+from oracle import nms_np, strongsort_np as ss, yolo_decode_np
+from strongsort_yolo_b200 import synth, yolo
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("in_h,in_w,nc,nk", [(640, 640, 80, 0), (384, 640, 80, 0), (640, 640, 1, 17)])
+def test_decode_v8_matches_restatement(in_h, in_w, nc, nk):
+    import torch
+    rng = np.random.default_rng(in_h + nk)
+    dec = yolo.YoloV8Decode(nc, nk, in_h, in_w)
+    raw = rng.normal(0, 2.0, (64 + nc + 3 * nk, dec.A)).astype(np.float32)
+    got = dec(torch.as_tensor(raw).cuda()).cpu().numpy()
+    want = yolo_decode_np.decode_v8(raw, nc, nk, in_h, in_w)
+    # float32 expf / division differ by a few ulp between libm and CUDA: 1e-5 relative on boxes
+    # (pixels up to ~1e3), 1e-6 absolute on probabilities
+    np.testing.assert_allclose(got[:4], want[:4], rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(got[4:4 + nc], want[4:4 + nc], rtol=1e-5, atol=1e-6)
+    if nk:
+        k_got, k_want = got[4 + nc:].reshape(nk, 3, -1), want[4 + nc:].reshape(nk, 3, -1)
+        np.testing.assert_allclose(k_got[:, :2], k_want[:, :2], rtol=1e-5, atol=1e-3)
+        np.testing.assert_allclose(k_got[:, 2], k_want[:, 2], rtol=1e-5, atol=1e-6)
+
+
+def test_decode_then_nms_recovers_detections():
+    import torch
+    rng = np.random.default_rng(11)
+    in_h, in_w, nc = 384, 640, 80
+    st = synth.make_stream("C1", render=False)
+    d = st.next_frame().dets.copy()
+    d[:, [0, 2]] *= in_w / 640.0; d[:, [1, 3]] *= in_h / 640.0          # into the network-input frame
+    raw = yolo.synth_raw_head_v8(d, nc, in_h, in_w, rng=rng)
+    dec = yolo.YoloV8Decode(nc, 0, in_h, in_w)
+    nms = yolo.YoloNMS(num_classes=nc, max_anchors=dec.A)
+    rows = nms.detect(dec(torch.as_tensor(raw).cuda()))
+    want = nms_np.yolo_nms(yolo_decode_np.decode_v8(raw, nc, 0, in_h, in_w), nc, 0, 0.3, 0.4, 1000, False)
+    assert rows.shape == want.shape
+    np.testing.assert_allclose(rows[:, :4], want[:, :4], rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(rows[:, 4], want[:, 4], atol=1e-6)
+    np.testing.assert_array_equal(rows[:, 5], want[:, 5])
+
+
+def test_camera_update_matches_oracle_and_tracking_continues():
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1", render=False)
+    bank = FeatureBank(seed=2)
+    ora = ss.StrongSORTOracle(None)
+    gpu = StrongSORT(max_tracks=128, max_dets=64)
+    img = np.zeros((st.H, st.W, 3), dtype=np.uint8)
+    th = np.deg2rad(0.4)
+    warp = np.array([[np.cos(th), -np.sin(th), 3.25], [np.sin(th), np.cos(th), -1.5]])
+    for f in range(12):
+        fr = st.next_frame()
+        feats = bank(fr.gt_ids)
+        if f in (4, 5, 9):                 # the caller warps the tracks between frames (ECC on)
+            ora.tracker.camera_update(warp)
+            gpu.camera_update(None, None, warp_matrix=warp)
+            assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-12)
+        assert_rows_equal(gpu.update(fr.dets, img, features=feats), ora.update(fr.dets, img, features=feats))
+    assert_tables_equal(gpu.export_tracks(), ora.track_table())
