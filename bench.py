@@ -46,6 +46,14 @@ METRIC = "tracked frames/sec at 1080p, 100 dets/frame"
 UNIT = "frames/s"
 REID_MACS_PER_CROP = 82314880          # oracle/osnet_torch.count_macs()
 WORKLOAD = "C2: 1 stream/GPU, 1080p synthetic, 100 dets/frame, OSNet-x0.25 ReID + StrongSORT"
+# --workload C4 (not the default bench line): BASELINE.json configs[3]
+WORKLOADS = {
+    "C2": (METRIC, WORKLOAD),
+    "C4": ("tracked frames/sec at 4K, 500 dets/frame, 256 live tracks",
+           "C4: 1 stream/GPU, 4K synthetic crowded scene, 500 dets/frame, 256 persistent tracks, "
+           "OSNet-x0.25 ReID + StrongSORT"),
+}
+CFG = "C2"
 
 
 def load_peaks():
@@ -61,7 +69,7 @@ def gen_frames(stream_id, count, pin):
     tensors when `pin`)."""
     import torch
     from strongsort_yolo_b200 import synth
-    st = synth.make_stream("C2", stream_id=stream_id)
+    st = synth.make_stream(CFG, stream_id=stream_id)
     imgs, dets = [], []
     for _ in range(count):
         fr = st.next_frame()
@@ -173,7 +181,7 @@ def impl_reference(args, rank):
     cores = os.cpu_count() or 1
     steps, warm = min(args.steps, 60), min(args.warmup, 5)
     from strongsort_yolo_b200 import synth
-    st = synth.make_stream("C2", stream_id=0)
+    st = synth.make_stream(CFG, stream_id=0)
     imgs, dets = [], []
     for _ in range(warm + steps):
         fr = st.next_frame()
@@ -203,12 +211,20 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-frames", type=int, default=20)
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
+                    help="C2 (default, the BASELINE.json metric) or C4 (4K, 500 dets/frame)")
+    ap.add_argument("--shared-gallery", action="store_true",
+                    help="config C5's optional exchange: all-gather every stream's confirmed-track features over "
+                         "NCCL after each frame and match across streams (read-only), inside the timed region")
     ap.add_argument("--only-device", action="store_true",
                     help="profiling aid: run only the device-resident timed loop (for ncu launch lists)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
+    global CFG, METRIC, WORKLOAD
+    CFG = args.workload
+    METRIC, WORKLOAD = WORKLOADS[CFG]
     if args.impl == "reference":
         impl_reference(args, rank)
         return
@@ -249,7 +265,8 @@ def main():
         return ssb_dist.max_over_ranks(x, device)
 
     # ---------------- value: device-resident inputs, per-step events ----------
-    trk = StrongSORT(device=str(device))
+    trk_kw = dict(max_tracks=2048, max_dets=640) if CFG == "C4" else {}
+    trk = StrongSORT(device=str(device), **trk_kw)
     st = trk.stream
     imgs_dev = [im.to(device) for im in imgs]
     dets_dev = [torch.from_numpy(d).to(device) for d in dets]
@@ -290,11 +307,14 @@ def main():
     # (b) value: the two-stage pipeline (embedding of frame k on one stream overlaps the
     # association of frame k-1 on another), device-resident inputs, K frames timed as a whole.
     # Inputs rotate through W+K distinct frames (>= 5x the 126 MB L2), no flush needed.
-    trk = StrongSORT(device=str(device))
+    trk = StrongSORT(device=str(device), **trk_kw)
     st = trk.stream
     sptr = C.c_void_p(st.cuda_stream)
+    gal = ssb_dist.SharedGallery(trk) if args.shared_gallery else None
     for i in range(W):
         trk.update_pipelined(dets_dev[i], imgs_dev[i])
+        if gal is not None:
+            gal.step()
     trk.flush_pipelined()
     barrier()
     clocks = ClockSampler(local_rank)
@@ -304,6 +324,8 @@ def main():
     e0.record(st)
     for k in range(K):
         trk.update_pipelined(dets_dev[W + k], imgs_dev[W + k])
+        if gal is not None:
+            gal.step()                     # export + NCCL all-gather + cross-stream match, on the tracker's stream
     trk.flush_pipelined()
     e1.record(st)
     barrier()
@@ -352,7 +374,8 @@ def main():
             traffic = None
 
     # ---------------- e2e: host buffers through StrongSORT.update -------------
-    trk2 = StrongSORT(device=str(device))
+    n_cross = len(gal.report()) if gal is not None else None
+    trk2 = StrongSORT(device=str(device), **trk_kw)
     for i in range(W):
         trk2.update(dets[i], imgs[i])
     barrier()
@@ -397,7 +420,10 @@ def main():
                                    "(ssb_embed / ssb_associate); results identical to the serial path",
                        "serial_flushed_ms_per_step": serial_ms,
                        "weights": "seeded random OSNet-x0.25, BN calibrated on synthetic crops",
-                       "e2e_ids_equal_device_run": bool(same_ids)},
+                       "e2e_ids_equal_device_run": bool(same_ids),
+                       **({"shared_gallery": "per frame: export + all-gather (NCCL) of [256,512] f32 + ids per rank + "
+                                             "cross-stream cosine match, read-only; inside the timed region",
+                           "cross_stream_matches_last_frame_rank0": n_cross} if gal is not None else {})},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,
             "clocks": clk,

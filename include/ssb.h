@@ -179,6 +179,21 @@ int ssb_yolo_decode_v8(const float *raw_dev, int num_classes, int num_kpts, int 
  * every live track; rewrites mean[:4].  Called between frames, outside ssb_update.             */
 int ssb_camera_update(ssb_tracker *t, const double *warp2x3_host, ssb_stream_t stream);
 
+/* ---- optional cross-stream ReID gallery (config C5; read-only, see csrc/gallery.cu) ----------
+ * export: the confirmed tracks of this stream in list order -> feat float32 [t_max, feat_dim] (unit
+ * EMA vectors, zero rows past the count), ids int32 [2 * t_max] (first t_max: track ids, -1 past the
+ * count; second half: scratch), count int32 [1].  The host all-gathers feat / ids over NCCL.
+ * cross_match: local [t_max, dim] against the gathered [n_ranks, t_max, dim]: per local track the
+ * nearest track of another rank in cosine distance -> rank / id (-1 when farther than max_dist
+ * or no foreign track) and the distance.                                                        */
+int ssb_gallery_export(ssb_tracker *t, int t_max, float *feat_out_dev, int32_t *ids_out_dev,
+                       int32_t *count_out_dev, ssb_stream_t stream);
+int ssb_gallery_cross_match(const float *local_feat_dev, const int32_t *local_ids_dev,
+                            const float *all_feat_dev, const int32_t *all_ids_dev, int n_ranks,
+                            int self_rank, int t_max, int dim, float max_dist,
+                            int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
+                            float *match_dist_out_dev, ssb_stream_t stream);
+
 /* ---- introspection for tests: copy the live track table (list order) ----- */
 /* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];
  * mean float64 [T,8]; cov [T,8,8]; feat float32 [T,dim]                     */

@@ -1,7 +1,8 @@
 """Multi-GPU plumbing: the path shards by independent video stream (the reference's one
 worker per --source, /root/reference/yolo_multi_model.py:351-354), one process per GPU,
 NO data-path collective.  torch.distributed is used only for the barrier and for the
-max-over-ranks of timed regions (NCCL on GPUs, gloo in the CPU tests)."""
+max-over-ranks of timed regions (NCCL on GPUs, gloo in the CPU tests) -- and for the one
+optional exchange the north star names: the cross-stream ReID gallery (SharedGallery)."""
 from __future__ import annotations
 
 import os
@@ -41,3 +42,69 @@ def max_over_ranks(x, device="cpu"):
 def aggregate_fps(frames_per_rank, seconds_max, world):
     """whole-job throughput: all ranks' frames over the slowest rank's time."""
     return world * frames_per_rank / seconds_max
+
+
+def gather_tracks(local_feat, local_ids):
+    """all-gather every rank's exported tracks: [t_max, D] -> [G, t_max, D], [t_max] -> [G, t_max]
+    (rank-major).  NCCL over NVLink / NVSwitch on GPUs (<= 513 KiB per rank at t_max 256), gloo on CPU."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local_feat.unsqueeze(0), local_ids.unsqueeze(0)
+    world = dist.get_world_size()
+    all_feat = torch.empty((world,) + tuple(local_feat.shape), dtype=local_feat.dtype, device=local_feat.device)
+    all_ids = torch.empty((world,) + tuple(local_ids.shape), dtype=local_ids.dtype, device=local_ids.device)
+    # per-rank views of the stacked outputs: one ncclAllGather each on NCCL, and gloo accepts it too
+    dist.all_gather(list(all_feat.unbind(0)), local_feat.contiguous())
+    dist.all_gather(list(all_ids.unbind(0)), local_ids.contiguous())
+    return all_feat, all_ids
+
+
+class SharedGallery:
+    """Read-only cross-stream ReID gallery (BASELINE.json config C5): after a frame, ``step()`` exports
+    this stream's confirmed tracks (csrc/gallery.cu), all-gathers every stream's export and matches
+    each local track to the nearest track of another stream.  Nothing is written back into the
+    tracker, so per-stream ids and the parity with the oracle are unaffected."""
+
+    def __init__(self, tracker, t_max=256, max_dist=0.2):
+        import ctypes as C
+        import torch
+        from . import _lib
+        self._C, self._torch, self._lib_mod = C, torch, _lib
+        self.trk, self.t_max, self.max_dist = tracker, int(t_max), float(max_dist)
+        dev, D = tracker.device, tracker.cfg.feat_dim
+        self.feat = torch.zeros((self.t_max, D), dtype=torch.float32, device=dev)
+        self._ids2 = torch.full((2 * self.t_max,), -1, dtype=torch.int32, device=dev)
+        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.m_rank = torch.full((self.t_max,), -1, dtype=torch.int32, device=dev)
+        self.m_id = torch.full((self.t_max,), -1, dtype=torch.int32, device=dev)
+        self.m_dist = torch.zeros(self.t_max, dtype=torch.float32, device=dev)
+        self.rank = env_rank_world()[0]
+
+    @property
+    def ids(self):
+        return self._ids2[:self.t_max]
+
+    def step(self):
+        """export -> all-gather -> match; results stay on the device (``report()`` reads them)."""
+        C, torch, _lib = self._C, self._torch, self._lib_mod
+        lib, trk = _lib.load(), self.trk
+        with torch.cuda.device(trk.device), torch.cuda.stream(trk.stream):
+            sp = C.c_void_p(trk.stream.cuda_stream)
+            _lib.check(lib.ssb_gallery_export(trk._h, self.t_max, _lib.ptr(self.feat), _lib.ptr(self._ids2),
+                                              _lib.ptr(self.count), sp), "ssb_gallery_export")
+            all_feat, all_ids = gather_tracks(self.feat, self.ids)
+            _lib.check(lib.ssb_gallery_cross_match(
+                _lib.ptr(self.feat), _lib.ptr(self.ids), _lib.ptr(all_feat), _lib.ptr(all_ids),
+                int(all_feat.shape[0]), self.rank if all_feat.shape[0] > 1 else 0, self.t_max,
+                int(self.feat.shape[1]), self.max_dist, _lib.ptr(self.m_rank), _lib.ptr(self.m_id),
+                _lib.ptr(self.m_dist), sp), "ssb_gallery_cross_match")
+            self._all = (all_feat, all_ids)
+        return self.m_rank, self.m_id, self.m_dist
+
+    def report(self):
+        """[(local track id, remote rank, remote track id, cosine distance)] of the last step()."""
+        self.trk.stream.synchronize()
+        n = int(self.count.item())
+        ids, r, i, d = (x[:n].cpu().numpy() for x in (self.ids, self.m_rank, self.m_id, self.m_dist))
+        return [(int(ids[k]), int(r[k]), int(i[k]), float(d[k])) for k in range(n) if r[k] >= 0]
