@@ -477,9 +477,20 @@ __device__ __forceinline__ unsigned long long f64_order_key(double x) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-template <int CPL>
+// SPARSE: the matrix is `bg` everywhere except the entries listed per working row in shared memory
+// (rowptr / rowlen / ecol / eval) -- the clamped cost matrices of min_cost_matching are >99 % one value
+// (max_d + 1e-5), so a search step needs no global loads at all; cij is the same double either way,
+// hence bit-identical results.
+struct LsapSparse {
+    double bg;
+    const int *rowptr, *rowlen, *ecol;
+    const double *eval;
+};
+
+template <int CPL, bool SPARSE>
 __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr, int nc0, int nr,
-                              int nc, double *u, int *col4row, int *row4col_out, int lane) {
+                              int nc, double *u, int *col4row, int *row4col_out, int lane,
+                              LsapSparse sp = LsapSparse()) {
     double v[CPL], spc[CPL];
     int pos[CPL], r4c[CPL], path[CPL];
     unsigned sc = 0;
@@ -500,12 +511,26 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
             double bv = INFINITY;
             unsigned bkey = 0;
             int bk = -1;
+            double cs[SPARSE ? CPL : 1];
+            if (SPARSE) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++) cs[k] = sp.bg;
+                const int e0 = sp.rowptr[i], e1 = e0 + sp.rowlen[i];
+                for (int e = e0; e < e1; e++) {                  // warp-uniform trip count
+                    const int cj = sp.ecol[e];
+                    const double cv = sp.eval[e];
+#pragma unroll
+                    for (int k = 0; k < CPL; k++)
+                        if (k == (cj >> 5) && lane == (cj & 31)) cs[k] = cv;
+                }
+            }
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 const int j = lane + 32 * k;
                 if (j < nc && !((sc >> k) & 1u)) {
-                    const double cij = staged ? C[(size_t)i * nc + j]
-                                              : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]);
+                    const double cij = SPARSE ? cs[SPARSE ? k : 0]
+                                              : (staged ? C[(size_t)i * nc + j]
+                                                        : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]));
                     const double r = minVal + cij - ui - v[k];
                     if (r < spc[k]) { path[k] = i; spc[k] = r; }
                     const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k])
@@ -611,12 +636,75 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     for (int j = tid; j < nc; j += blockDim.x) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
     __syncthreads();
 
+    // Too big for shared memory (C4: 344 x 498): every search step would wait for an L2 round trip.
+    // The clamped matrices are one background value (their maximum) plus a few real entries per row,
+    // so keep only those in shared memory (the register solver's SPARSE mode).  m.remaining / m.path
+    // (unused by the register path) hold the per-row offsets / lengths; falls back to the dense
+    // global-memory path when the real entries do not fit.
+    LsapSparse sp;
+    bool sparse = false;
+    if (!staged && nc <= 512) {
+        __shared__ double s_bg[8];
+        __shared__ int s_cnt[8], s_total;
+        const int wid = tid >> 5, nwarp = blockDim.x >> 5;
+        double mx = -INFINITY;
+        for (int e = tid; e < nr0 * nc0; e += blockDim.x) { const double c = C[e]; if (c > mx) mx = c; }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
+        if (lane == 0) s_bg[wid] = mx;
+        __syncthreads();
+        mx = s_bg[0];
+        for (int w = 1; w < nwarp; w++) if (s_bg[w] > mx) mx = s_bg[w];
+        const size_t cap = cost_smem_bytes / 12;
+        double *evals = m.cost;
+        int *ecols = (int *)(m.cost + cap);
+        int *rowptr = m.remaining, *rowlen = m.path;
+        // pass 1: entries != bg per working row (warp per row)
+        for (int i = wid; i < nr; i += nwarp) {
+            int cnt = 0;
+            for (int j0 = 0; j0 < nc; j0 += 32) {
+                const int j = j0 + lane;
+                const bool nz = j < nc && !((tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]) == mx);
+                cnt += __popc(__ballot_sync(0xffffffffu, nz));
+            }
+            if (lane == 0) rowlen[i] = cnt;
+        }
+        __syncthreads();
+        if (tid == 0) {                                    // serial exclusive scan (nr <= 512)
+            int acc = 0;
+            for (int i = 0; i < nr; i++) { rowptr[i] = acc; acc += rowlen[i]; }
+            s_total = acc;
+        }
+        __syncthreads();
+        (void)s_cnt;
+        if ((size_t)s_total <= cap) {
+            for (int i = wid; i < nr; i += nwarp) {        // pass 2: fill, column order
+                int off = rowptr[i];
+                for (int j0 = 0; j0 < nc; j0 += 32) {
+                    const int j = j0 + lane;
+                    const double c = j < nc ? (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]) : mx;
+                    const bool nz = j < nc && !(c == mx);
+                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                    if (nz) { const int q = off + __popc(bal & ((1u << lane) - 1)); evals[q] = c; ecols[q] = j; }
+                    off += __popc(bal);
+                }
+            }
+            sparse = true;
+            sp.bg = mx; sp.rowptr = rowptr; sp.rowlen = rowlen; sp.ecol = ecols; sp.eval = evals;
+        }
+        __syncthreads();
+    }
+
     if (tid < 32 && nc <= 512) {
         const double *Cw = staged ? m.cost : C;
         bool okr;
-        if (nc <= 128) okr = lsap_warp_reg<4>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else if (nc <= 256) okr = lsap_warp_reg<8>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else okr = lsap_warp_reg<16>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        if (sparse) {
+            if (nc <= 128) okr = lsap_warp_reg<4, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+            else if (nc <= 256) okr = lsap_warp_reg<8, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+            else okr = lsap_warp_reg<16, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+        } else if (nc <= 128) okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else if (nc <= 256) okr = lsap_warp_reg<8, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else okr = lsap_warp_reg<16, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         if (!okr) {
             for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
             for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;

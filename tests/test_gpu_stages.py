@@ -127,9 +127,9 @@ def test_appearance_cost(lib, T, B, N):
 def _lsap_cases():
     rng = np.random.default_rng(8)
     shapes = [(1, 1), (1, 9), (9, 1), (10, 10), (33, 64), (64, 33), (100, 100), (115, 100),
-              (100, 130), (256, 500), (300, 170), (40, 40)]
+              (100, 130), (256, 500), (300, 170), (40, 40), (344, 498), (498, 491), (500, 300)]
     for (nr, nc) in shapes:
-        for kind in range(5):
+        for kind in range(6):
             if kind == 0:
                 c = rng.random((nr, nc))
             elif kind == 1:
@@ -138,10 +138,16 @@ def _lsap_cases():
                 c = np.full((nr, nc), 0.2 + 1e-5)
             elif kind == 3:
                 c = rng.random((nr, nc)) * 0.3; c[c > 0.2] = 0.2 + 1e-5
-            else:
+            elif kind == 4:
                 c = np.full((nr, nc), 0.7 + 1e-5)
                 for i in range(min(nr, nc)):
                     c[i, (i * 7) % nc] = rng.random() * 0.7
+            else:       # clamped background + a few real entries per row drawn from 8 values (exact ties):
+                c = np.full((nr, nc), 0.2 + 1e-5)       # the sparse-background mode of the big matrices
+                vals = rng.random(8) * 0.2
+                for i in range(nr):
+                    for j in rng.integers(0, nc, 3):
+                        c[i, j] = vals[rng.integers(0, 8)]
             yield c
 
 
