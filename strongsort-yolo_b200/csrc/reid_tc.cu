@@ -970,7 +970,8 @@ struct StemCfg {
 
 __global__ void __launch_bounds__(OSB_THREADS, 1)
 stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const int *__restrict__ boxes,
-               const unsigned char *__restrict__ wblob, float *__restrict__ out, int *__restrict__ status) {
+               const unsigned char *__restrict__ wblob, float *__restrict__ out, int *__restrict__ status,
+               long long *__restrict__ dbg) {
     using C = StemCfg;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -985,9 +986,12 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     if (warp == 0) tc::tmem_alloc(s_tmem, 512);
     if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
     if (tid < 16) sBias[tid] = reinterpret_cast<const float *>(wblob + C::G_BIAS)[tid];
-    // zero the operand map (padding rows/cols and the 4 pad channels stay zero)
-    for (int i = tid; i < C::MAP_B / 16; i += OSB_THREADS)
-        reinterpret_cast<uint4 *>(sMap)[i] = make_uint4(0u, 0u, 0u, 0u);
+    // the operand map is written in full below (every S pixel, all 16 channels); only the guard
+    // pixels past the band's S rows (read by the shifted taps of the last tile) are zeroed here
+    for (int i = tid; i < (C::MAP_PX - C::SROWS * C::WPS) * 4; i += OSB_THREADS) {
+        const int px = C::SROWS * C::WPS + i / 4, pl = i & 3;       // 4 planes: hi c0, hi c1, lo c0, lo c1
+        *reinterpret_cast<uint4 *>(sMap + (pl >> 1) * C::MAP_HALF_B + (pl & 1) * C::PLANE_B + px * 16) = make_uint4(0u, 0u, 0u, 0u);
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -1000,42 +1004,90 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     const int bx1 = boxes[crop * 4 + 0], by1 = boxes[crop * 4 + 1];
     const int cw = boxes[crop * 4 + 2] - bx1, ch = boxes[crop * 4 + 3] - by1;
     const float sc_y = (float)ch / 256.f, sc_x = (float)cw / 128.f;
-    const float mean[3] = {0.485f, 0.456f, 0.406f};
-    const float stdv[3] = {0.229f, 0.224f, 0.225f};
     const int gy0 = 2 * cy0 - 3;                               // resized row of S row 0, dy = 0
-    for (int i = tid; i < 2 * C::SROWS * 134; i += OSB_THREADS) {
-        const int ry = i / 134, rx = i - ry * 134;            // local resized row / Rpad column
-        const int gy = gy0 + ry, gx = rx - 3;
-        if (gy < 0 || gy >= 256 || gx < 0 || gx >= 128 || cw <= 0 || ch <= 0) continue;
-        float sy = sc_y * ((float)gy + 0.5f) - 0.5f, sx = sc_x * ((float)gx + 0.5f) - 0.5f;
-        if (sy < 0.f) sy = 0.f;
-        if (sx < 0.f) sx = 0.f;
-        const int y0 = (int)sy, x0 = (int)sx;
-        const int y1 = y0 + (y0 < ch - 1 ? 1 : 0), x1 = x0 + (x0 < cw - 1 ? 1 : 0);
-        const float ly = sy - (float)y0, lx = sx - (float)x0, hy = 1.f - ly, hx = 1.f - lx;
-        const uint8_t *r0 = img + (size_t)(by1 + y0) * pitch + (size_t)bx1 * 3;
-        const uint8_t *r1 = img + (size_t)(by1 + y1) * pitch + (size_t)bx1 * 3;
-        const int Y = ry >> 1, dy = ry & 1, X = rx >> 1, dx = rx & 1;
-        const int q = Y * C::WPS + X;
+    int dbg_n = 0;
+    auto stamp = [&]() { if (dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 15) dbg[41 + dbg_n++] = clock64(); };   // slots 40..: stem
+    stamp();
+    // One thread per S pixel q = (Y, X): its 2x2 resized pixels x 3 channels = the 12 real channels of the
+    // pixel's two 16-byte operand rows (hi and lo), written with four conflict-free 16-byte stores.
+    // All 48 byte loads are unconditional (coordinates clamped into the crop, out-of-range samples zeroed
+    // afterwards) so they are in flight together; u8 -> f32 is the 2^23 magic-number trick (LOP3 + FADD,
+    // full rate; I2F runs at a quarter of it); (v/255 - mean)/std is one FMA.
+    const bool crop_ok = cw > 0 && ch > 0;
+    const int cwm = crop_ok ? cw - 1 : 0, chm = crop_ok ? ch - 1 : 0;
+    const uint8_t *cbase = img + (size_t)(crop_ok ? by1 : 0) * pitch + (size_t)(crop_ok ? bx1 : 0) * 3;
+    const float nsc[3] = {1.0f / (255.0f * 0.229f), 1.0f / (255.0f * 0.224f), 1.0f / (255.0f * 0.225f)};
+    const float nof[3] = {-0.485f / 0.229f, -0.456f / 0.224f, -0.406f / 0.225f};
+    auto u8f = [](uint8_t b) { return __uint_as_float(0x4B000000u | (unsigned)b) - 8388608.0f; };
+    for (int q = tid; q < C::SROWS * C::WPS; q += OSB_THREADS) {
+        const int Y = q / C::WPS, X = q - Y * C::WPS;
+        int xo0[2], xo1[2];
+        float lxv[2];
+        bool xin[2];
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const float p00 = r0[x0 * 3 + c], p01 = r0[x1 * 3 + c];
-            const float p10 = r1[x0 * 3 + c], p11 = r1[x1 * 3 + c];
-            const float val = hy * (hx * p00 + lx * p01) + ly * (hx * p10 + lx * p11);
-            const float v = (val / 255.0f - mean[c]) / stdv[c];
-            __half h, l;
-            split_hl(v, h, l);
-            const int e = (dy * 2 + dx) * 3 + c;
-            const int off = (e >> 3) * C::PLANE_B + q * 16 + (e & 7) * 2;
-            *reinterpret_cast<__half *>(sMap + off) = h;
-            *reinterpret_cast<__half *>(sMap + C::MAP_HALF_B + off) = l;
+        for (int dx = 0; dx < 2; dx++) {
+            const int gx = 2 * X + dx - 3;
+            float sx = sc_x * ((float)gx + 0.5f) - 0.5f;
+            if (sx < 0.f) sx = 0.f;
+            int x0 = (int)sx;
+            lxv[dx] = sx - (float)x0;
+            x0 = x0 < cwm ? x0 : cwm;
+            xo0[dx] = x0 * 3;
+            xo1[dx] = (x0 + (x0 < cwm ? 1 : 0)) * 3;
+            xin[dx] = gx >= 0 && gx < 128;
         }
+        uint8_t pa[2][2][2][3], pb[2][2][2][3];       // [dy][source row 0/1][dx][c] at x0 (pa) and x1 (pb)
+        float lyv[2];
+        bool yin[2];
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++) {
+            const int gy = gy0 + 2 * Y + dy;
+            float sy = sc_y * ((float)gy + 0.5f) - 0.5f;
+            if (sy < 0.f) sy = 0.f;
+            int y0 = (int)sy;
+            lyv[dy] = sy - (float)y0;
+            y0 = y0 < chm ? y0 : chm;
+            const int y1 = y0 + (y0 < chm ? 1 : 0);
+            yin[dy] = crop_ok && gy >= 0 && gy < 256;
+            const uint8_t *r0 = cbase + (size_t)y0 * pitch, *r1 = cbase + (size_t)y1 * pitch;
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++)
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    pa[dy][0][dx][c] = r0[xo0[dx] + c];  pb[dy][0][dx][c] = r0[xo1[dx] + c];
+                    pa[dy][1][dx][c] = r1[xo0[dx] + c];  pb[dy][1][dx][c] = r1[xo1[dx] + c];
+                }
+        }
+        __align__(16) __half hv[16];
+        __align__(16) __half lv[16];
+#pragma unroll
+        for (int e = 12; e < 16; e++) { hv[e] = __float2half_rn(0.f); lv[e] = __float2half_rn(0.f); }
+#pragma unroll
+        for (int dy = 0; dy < 2; dy++)
+#pragma unroll
+            for (int dx = 0; dx < 2; dx++) {
+                const float ly = lyv[dy], hy = 1.f - ly, lx = lxv[dx], hx = 1.f - lx;
+                const bool in = yin[dy] && xin[dx];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const float val = hy * (hx * u8f(pa[dy][0][dx][c]) + lx * u8f(pb[dy][0][dx][c])) +
+                                      ly * (hx * u8f(pa[dy][1][dx][c]) + lx * u8f(pb[dy][1][dx][c]));
+                    const float v = in ? fmaf(val, nsc[c], nof[c]) : 0.f;
+                    split_hl(v, hv[(dy * 2 + dx) * 3 + c], lv[(dy * 2 + dx) * 3 + c]);
+                }
+            }
+        unsigned char *d = sMap + q * 16;
+        *reinterpret_cast<uint4 *>(d) = *reinterpret_cast<uint4 *>(&hv[0]);
+        *reinterpret_cast<uint4 *>(d + C::PLANE_B) = *reinterpret_cast<uint4 *>(&hv[8]);
+        *reinterpret_cast<uint4 *>(d + C::MAP_HALF_B) = *reinterpret_cast<uint4 *>(&lv[0]);
+        *reinterpret_cast<uint4 *>(d + C::MAP_HALF_B + C::PLANE_B) = *reinterpret_cast<uint4 *>(&lv[8]);
     }
     tc::fence_async_smem();
     bool ok = tc::mbar_wait(bar + 1, 0);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    stamp();                                   // S built
     // warp-uniform issue by an elected lane (~3x cheaper per MMA than `if (tid == 0)`, tc_common.cuh);
     // hi and lo weight rows concatenated along N: D[:, 0:16] += Ah*Bh + Al*Bh, D[:, 16:32] += Ah*Bl --
     // two reads of the 4 KB A tile (what bounds an M=128, K=16 MMA) per product instead of three
@@ -1060,6 +1112,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     }
     if (!tc::mbar_wait(bar, 0)) ok = false;
     tc::fence_after_sync();
+    stamp();                                   // MMAs done
     // ---- epilogue: bias + ReLU -> sConv[lcy][cx][16]; rows outside the conv map = -inf
     for (int t = grp; t < C::NT; t += OSB_GROUPS) {
         const int p = t * 128 + quad * 32 + lane;
@@ -1086,6 +1139,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     }
     tc::fence_before_sync();
     __syncthreads();
+    stamp();                                   // conv drained
     // ---- maxpool 3x3 s2 p1 -> out[crop][py][px][16]
     for (int o = tid; o < C::PR * 32 * 4; o += OSB_THREADS) {
         const int c4 = o & 3, px = (o >> 2) & 31, pr = o >> 7;
@@ -1103,6 +1157,8 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
         }
         *reinterpret_cast<float4 *>(out + (((size_t)crop * 64 + py0 + pr) * 32 + px) * 16 + c4 * 4) = m;
     }
+    stamp();                                   // pooled + stored
+    if (dbg && blockIdx.x == 0 && tid == 0) dbg[40] = dbg_n;
     if (!ok && tid == 0) atomicExch(status, 4);
     tc::fence_before_sync();
     __syncthreads();
@@ -1189,7 +1245,7 @@ int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *box
         SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
         attr = true;
     }
-    stem_tc_kernel<<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status);
+    stem_tc_kernel<<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
     SSB_CHECK_LAUNCH();
     return 0;
 }

@@ -70,6 +70,13 @@ def main():
             out[f"osblock{b}{tag}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
             if mode == 2:
                 out[f"osblock{b}_acc_issue_dw_publish"] = [int(d[60]), int(d[61]), int(d[62])]
+    # stem phases (CTA 0): S built, MMAs done, conv drained, pooled
+    lib.ssb_reid_tc_debug(P(dbg))
+    _lib.check(lib.ssb_reid(trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST()))
+    torch.cuda.synchronize()
+    lib.ssb_reid_tc_debug(None)
+    d = dbg.cpu().numpy()
+    out["stem_phase_cycles"] = [int(v - d[41]) for v in d[42:41 + int(d[40])]]
     # stage-A-like clamped cost matrices from the live tracker
     a, b = trk.debug_costs()
     for name, m in (("lsap_stageA", a), ("lsap_stageB", b)):
