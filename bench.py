@@ -327,6 +327,8 @@ def main():
         if gal is not None:
             gal.step()                     # export + NCCL all-gather + cross-stream match, on the tracker's stream
     trk.flush_pipelined()
+    if gal is not None:
+        st.wait_stream(gal.stream)         # the exchange of the last frame ends inside the timed region
     e1.record(st)
     barrier()
     launches = int(lib.ssb_launch_count() - l0)
@@ -422,7 +424,7 @@ def main():
                        "weights": "seeded random OSNet-x0.25, BN calibrated on synthetic crops",
                        "e2e_ids_equal_device_run": bool(same_ids),
                        **({"shared_gallery": "per frame: export + all-gather (NCCL) of [256,512] f32 + ids per rank + "
-                                             "cross-stream cosine match, read-only; inside the timed region",
+                                             "cross-stream cosine match, read-only, on a side stream; inside the timed region",
                            "cross_stream_matches_last_frame_rank0": n_cross} if gal is not None else {})},
             "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches,

@@ -82,10 +82,10 @@ struct B3 {
     static constexpr int OFF_W = OFF_A + A_B;
     static constexpr int OFF_C3 = OFF_W + rup128(WALL_B);
     static constexpr int OFF_PAR = OFF_C3 + C3W_B;
-    static constexpr int OFF_GAP = OFF_PAR + rup128(NPAR * 4);       // [4][MIDP] floats
-    static constexpr int OFF_MISC = OFF_GAP + 4 * MIDP * 4;
+    static constexpr int OFF_GAP = OFF_PAR + rup128(NPAR * 4);       // [4 streams][NB bands][MIDP] floats
+    static constexpr int OFF_MISC = OFF_GAP + 4 * NB * MIDP * 4;
     static constexpr int SCR_FLOATS = SEG * NCB * CG * 4;
-    static constexpr int SMEM_B = OFF_MISC + 128 + (SCR_FLOATS + 2 * MIDP) * 4 + 64;
+    static constexpr int SMEM_B = OFF_MISC + 192 + (SCR_FLOATS + 2 * MIDP) * 4 + 64;
     static_assert(NPX % 128 == 0, "band = whole M tiles");
     static_assert((W & (W - 1)) == 0, "W power of two");
     static_assert(NT <= 8, "per-tile barriers");
@@ -129,6 +129,12 @@ __device__ __forceinline__ void tmem_ld4_nw(uint32_t taddr, uint32_t *r) {
                  : "r"(taddr)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t *r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -163,13 +169,13 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     float4 *sT = reinterpret_cast<float4 *>(sP + C::MAP_B);
     unsigned char *sW = smem + C::OFF_W, *sC3 = smem + C::OFF_C3;
     float *sPar = reinterpret_cast<float *>(smem + C::OFF_PAR);
-    float *sGap = reinterpret_cast<float *>(smem + C::OFF_GAP);      // [4][MIDP] band-partial sums
+    float *sGap = reinterpret_cast<float *>(smem + C::OFF_GAP);      // [4][NB][MIDP] band-partial sums of every band
     uint64_t *bar_w = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);
     uint64_t *bar_stg = bar_w + 1;                     // [2] one per x-staging buffer
     uint64_t *bar_tile = bar_w + 3;                    // [8] per M tile of the current pointwise conv
     uint64_t *bar_c3 = bar_w + 11;                     // conv3 accumulation of the current stream
-    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_w + 12);
-    float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 128);   // [SEG][CG][4] partial sums
+    uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar_w + 16);
+    float *s_scr = reinterpret_cast<float *>(smem + C::OFF_MISC + 192);   // [SEG][CG][4] partial sums
 
     if (warp == 0) tc::tmem_alloc(s_tmem, 512);
     if (tid == 0) {
@@ -212,20 +218,23 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     constexpr int F4 = C::CIN / 4;
     constexpr int PER = (128 * F4) / K3_THREADS;             // float4 items per thread per tile
     static_assert((128 * F4) % K3_THREADS == 0, "tile items divide the CTA");
-    float4 xr[PER];
-    auto load_tile = [&](int t) {
+    // two tiles of x are in flight while a third is staged (the phase is bound by L2 latency x bytes in flight)
+    float4 xr[2][PER];
+    auto load_tile = [&](int t, float4 *dst) {
 #pragma unroll
         for (int q = 0; q < PER; q++) {
             const int idx = tid + q * K3_THREADS;
             const int px = idx / F4, f4 = idx - px * F4;
             const int p = t * 128 + px;
             const int gr = row0 + p / C::W, gc = p % C::W;
-            xr[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+            dst[q] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gr >= 0 && gr < C::H)
-                xr[q] = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
+                dst[q] = *reinterpret_cast<const float4 *>(xin + ((size_t)gr * C::W + gc) * C::CIN + f4 * 4);
         }
     };
-    load_tile(0);
+    load_tile(0, xr[0]);
+    if (C::NT > 1) load_tile(1, xr[1]);
+#pragma unroll
     for (int t = 0; t < C::NT; t++) {
         const int sb = t % C::NSTAGE;
         unsigned char *stg = sP + sb * C::STG_B;
@@ -237,7 +246,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         for (int q = 0; q < PER; q++) {                      // stage tile t of x: [CIN/8][128][8] hi, then lo
             const int idx = tid + q * K3_THREADS;
             const int px = idx / F4, f4 = idx - px * F4;
-            const float4 v = xr[q];
+            const float4 v = xr[t & 1][q];
             __align__(8) __half2 h[2], l[2];
             split2(v.x, v.y, h[0], l[0]);
             split2(v.z, v.w, h[1], l[1]);
@@ -245,7 +254,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             *reinterpret_cast<uint2 *>(stg + off) = *reinterpret_cast<uint2 *>(h);
             *reinterpret_cast<uint2 *>(stg + C::STG_HALF_B + off) = *reinterpret_cast<uint2 *>(l);
         }
-        if (t + 1 < C::NT) load_tile(t + 1);
+        if (t + 2 < C::NT) load_tile(t + 2, xr[t & 1]);
         tc::fence_async_smem();
         if (t == 0) { if (!tc::mbar_wait(bar_w, 0)) ok = false; }
         tc::fence_before_sync();
@@ -283,28 +292,43 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     // the staging area becomes the P map (its pad-channel planes must read as zero) and T (zero ring)
     for (int i = tid; i < (C::MAP_B + C::T_B) / 16; i += K3_THREADS)
         reinterpret_cast<uint4 *>(sP)[i] = make_uint4(0u, 0u, 0u, 0u);
-    // X1 epilogue: TMEM tile -> (+bias, relu, out-of-image mask) -> hi/lo operand map
-    for (int t = grp; t < C::NT; t += K3_GROUPS) {
-        const int p = t * 128 + quad * 32 + lane;
-        const int gr = row0 + p / C::W;
-        const bool valid = gr >= 0 && gr < C::H;
-        unsigned char *d_hi = sX1 + p * 16, *d_lo = d_hi + C::MAP_HALF_B;
-        float v[C::MIDP], w[C::MIDP];
-        tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN, v);
-        tc::tmem_ldN<C::MIDP>(tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + C::MIDP, w);
-        const float *bias = sPar + C::P_B1;
+    // X1 epilogue: TMEM tile -> (+bias, relu, out-of-image mask) -> hi/lo operand map; units (tile, 8-channel
+    // K chunk) spread evenly over the 4 warp groups, all TMEM loads of a thread in flight before one wait
+    {
+        constexpr int NU1 = C::NT * C::MCH, UPT1 = (NU1 + K3_GROUPS - 1) / K3_GROUPS;
+        uint32_t va[UPT1][8], vb[UPT1][8];
 #pragma unroll
-        for (int c0 = 0; c0 < C::MIDP; c0 += 8) {
-            __align__(16) __half2 h[4];
-            __align__(16) __half2 l[4];
-#pragma unroll
-            for (int j = 0; j < 8; j += 2) {
-                const float f0 = valid ? fmaxf(v[c0 + j] + w[c0 + j] + bias[c0 + j], 0.f) : 0.f;
-                const float f1 = valid ? fmaxf(v[c0 + j + 1] + w[c0 + j + 1] + bias[c0 + j + 1], 0.f) : 0.f;
-                split2(f0, f1, h[j >> 1], l[j >> 1]);
+        for (int e = 0; e < UPT1; e++) {
+            const int u = grp + e * K3_GROUPS;
+            if (u < NU1) {
+                const int t = u / C::MCH, kc = u - t * C::MCH;
+                const uint32_t ta = tmem + ((uint32_t)(quad * 32) << 16) + t * C::LCN + kc * 8;
+                tmem_ld8_nw(ta, va[e]);
+                tmem_ld8_nw(ta + C::MIDP, vb[e]);
             }
-            *reinterpret_cast<uint4 *>(d_hi + (c0 >> 3) * C::PLANE_B) = *reinterpret_cast<uint4 *>(h);
-            *reinterpret_cast<uint4 *>(d_lo + (c0 >> 3) * C::PLANE_B) = *reinterpret_cast<uint4 *>(l);
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int e = 0; e < UPT1; e++) {
+            const int u = grp + e * K3_GROUPS;
+            if (u < NU1) {
+                const int t = u / C::MCH, kc = u - t * C::MCH;
+                const int p = t * 128 + quad * 32 + lane;
+                const int gr = row0 + p / C::W;
+                const bool valid = gr >= 0 && gr < C::H;
+                const float *bias = sPar + C::P_B1 + kc * 8;
+                __align__(16) __half2 h[4];
+                __align__(16) __half2 l[4];
+#pragma unroll
+                for (int j = 0; j < 8; j += 2) {
+                    const float f0 = valid ? fmaxf(__uint_as_float(va[e][j]) + __uint_as_float(vb[e][j]) + bias[j], 0.f) : 0.f;
+                    const float f1 = valid ? fmaxf(__uint_as_float(va[e][j + 1]) + __uint_as_float(vb[e][j + 1]) + bias[j + 1], 0.f) : 0.f;
+                    split2(f0, f1, h[j >> 1], l[j >> 1]);
+                }
+                unsigned char *d_hi = sX1 + kc * C::PLANE_B + p * 16;
+                *reinterpret_cast<uint4 *>(d_hi) = *reinterpret_cast<uint4 *>(h);
+                *reinterpret_cast<uint4 *>(d_hi + C::MAP_HALF_B) = *reinterpret_cast<uint4 *>(l);
+            }
         }
     }
     tc::fence_async_smem();
@@ -521,20 +545,27 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             publish();
             stamp();                           // depthwise done
             // ---- ChannelGate: band-partial sums -> cluster -> mean -> MLP -> sigmoid -> scaled conv3 weights
-            if (warp == 0) {
+            // every band PUSHES its partial sums into all bands' shared memory (st.shared::cluster); the
+            // cluster barrier (release / acquire) then makes them visible, and the sums are read locally --
+            // no remote loads after the barrier.  (Per-lane remote mbarrier arrives instead of the hardware
+            // cluster barrier were measured slower: 2.65 K vs 2.2 K cycles per gate.)
+            if (warp == 0 && lane < C::MIDP) {
                 float tot = 0.f;
                 if (lane < C::MID)
                     for (int g = 0; g < C::SEG * C::NCB; g++) tot += s_scr[(g * C::CG + (lane >> 2)) * 4 + (lane & 3)];
-                if (lane < C::MIDP) sGap[s * C::MIDP + lane] = tot;
+                float *slot = sGap + (s * C::NB + band) * C::MIDP + lane;
+                if (C::NB > 1) {
+#pragma unroll
+                    for (int b = 0; b < C::NB; b++) tc::st_cluster_f32(tc::mapa_u32(slot, b), tot);
+                } else {
+                    *slot = tot;
+                }
             }
             if (C::NB > 1) cluster.sync(); else __syncthreads();
             if (warp * 32 < C::COUT * C::MCH) {      // warps that own conv3 weight rows; lane c = channel c
                 float tot = 0.f;                   // fixed band order: every CTA of the crop gets the same bits
                 if (lane < C::MIDP)
-                    for (int b = 0; b < C::NB; b++) {
-                        const float *rg = (C::NB > 1) ? cluster.map_shared_rank(sGap, b) : sGap;
-                        tot += rg[s * C::MIDP + lane];
-                    }
+                    for (int b = 0; b < C::NB; b++) tot += sGap[(s * C::NB + b) * C::MIDP + lane];
                 const float m = tot / (float)(C::H * C::W);
                 float h0 = lane < C::MIDP ? m * sPar[C::P_GW1 + lane * 2 + 0] : 0.f;
                 float h1 = lane < C::MIDP ? m * sPar[C::P_GW1 + lane * 2 + 1] : 0.f;
@@ -597,6 +628,33 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
             stamp();                           // gate + conv3 issued
         }
     }
+    // identity blocks: the residual x rows of this warp's (tile, 32-column) units are fetched (coalesced:
+    // 8 lanes per 128-byte pixel row) before the wait for the last conv3 MMAs, so their latency is hidden
+    float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
+    constexpr int CCH = C::COUT / 32;                         // 32-column chunks per tile
+    constexpr int NUE = C::NIT * CCH, UE = (NUE + K3_GROUPS - 1) / K3_GROUPS;
+    float4 xres[C::DOWN ? 1 : UE][8];
+    int rowoffs[UE];
+#pragma unroll
+    for (int e = 0; e < UE; e++) {
+        const int u = grp + e * K3_GROUPS;
+        rowoffs[e] = -1;
+        if (u < NUE) {                                        // warp-uniform
+            const int i = u / CCH, c0 = (u - i * CCH) * 32;
+            const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
+            const bool own = p >= C::OWN_P0 && p < C::OWN_P1;
+            rowoffs[e] = own ? band * C::R * C::W + (p - C::OWN_P0) : -1;     // pixel index inside the crop
+            if (!C::DOWN) {
+#pragma unroll
+                for (int it = 0; it < 8; it++) {
+                    const int ro = __shfl_sync(0xffffffffu, rowoffs[e], it * 4 + (lane >> 3));
+                    xres[C::DOWN ? 0 : e][it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (ro >= 0)
+                        xres[C::DOWN ? 0 : e][it] = *reinterpret_cast<const float4 *>(xin + (size_t)ro * C::CIN + c0 + (lane & 7) * 4);
+                }
+            }
+        }
+    }
     if (c3_pending) {                 // the last stream's conv3 MMAs
         if (!tc::mbar_wait(bar_c3, c3_par)) ok = false;
         c3_par ^= 1;
@@ -608,23 +666,17 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     // final epilogue: y = relu(conv3 + bias (+ downsample already in TMEM) (+ x)), rows transposed
     // through a warp-private staging tile so that 8 lanes cover one 128-byte pixel row
     // ------------------------------------------------------------------
-    float *yout = y + (size_t)crop * C::H * C::W * C::COUT;
-    constexpr int CCH = C::COUT / 32;                         // 32-column chunks per tile
     float *stage = reinterpret_cast<float *>(smem) + warp * (32 * 36);
-    for (int u = grp; u < C::NIT * CCH; u += K3_GROUPS) {     // (tile, chunk) units over the 4 groups
-        const int i = u / CCH, c0 = (u - i * CCH) * 32;
-        const int p = (C::IT0 + i) * 128 + quad * 32 + lane;
-        const bool own = p >= C::OWN_P0 && p < C::OWN_P1;
-        const int rowoff = own ? band * C::R * C::W + (p - C::OWN_P0) : -1;   // pixel index inside the crop
-        if (!C::DOWN) {                                       // identity residual, coalesced
 #pragma unroll
-            for (int it = 0; it < 8; it++) {
-                const int row = it * 4 + (lane >> 3);
-                const int ro = __shfl_sync(0xffffffffu, rowoff, row);
-                float4 x4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ro >= 0) x4 = *reinterpret_cast<const float4 *>(xin + (size_t)ro * C::CIN + c0 + (lane & 7) * 4);
-                *reinterpret_cast<float4 *>(stage + row * 36 + (lane & 7) * 4) = x4;
-            }
+    for (int e = 0; e < UE; e++) {
+        const int u = grp + e * K3_GROUPS;
+        if (u >= NUE) continue;                               // warp-uniform
+        const int i = u / CCH, c0 = (u - i * CCH) * 32;
+        const int rowoff = rowoffs[e];
+        if (!C::DOWN) {
+#pragma unroll
+            for (int it = 0; it < 8; it++)
+                *reinterpret_cast<float4 *>(stage + (it * 4 + (lane >> 3)) * 36 + (lane & 7) * 4) = xres[C::DOWN ? 0 : e][it];
         }
         float v[32];
         tc::tmem_ld32(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + i * C::COUT + c0, v);
@@ -656,7 +708,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     if (dbg && blockIdx.x == 0 && tid == 0) { dbg[0] = dbg_n; dbg[60] = acc_issue; dbg[61] = acc_dw; dbg[62] = acc_pub; }
     if (!ok) { if (tid == 0) atomicExch(status, 5); }
     tc::fence_before_sync();
-    if (C::NB > 1) cluster.sync(); else __syncthreads();     // remote sGap reads are done
+    if (C::NB > 1) cluster.sync(); else __syncthreads();     // no band exits while its peers may still push into it
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
     (void)n_crops;
 }

@@ -181,6 +181,40 @@ __device__ __forceinline__ bool mbar_wait(uint64_t *bar, uint32_t parity) {
     }
 }
 
+// ---- distributed shared memory (thread-block cluster): push + remote mbarrier arrive ----------
+// address of `local_smem_ptr`'s counterpart in CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(const void *local_smem_ptr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(local_smem_ptr)), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f32(uint32_t cluster_addr, float v) {
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(cluster_addr), "f"(v) : "memory");
+}
+// arrive (release at cluster scope: this thread's earlier remote stores are visible to the waiter)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+}
+// bounded wait with acquire at cluster scope (pairs with mbar_arrive_cluster from peer CTAs)
+__device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    long long t0 = 0;
+    for (uint32_t it = 0;; it++) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}\n"
+            : "=r"(ok)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (ok) return true;
+        __nanosleep(it < 8 ? 32 : 128);
+        if (it == 64) t0 = clock64();
+        if (it > 64 && clock64() - t0 > 500000000LL) return false;
+    }
+}
+
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map needed),
 // completion counted in bytes on an mbarrier.  size % 16 == 0, 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,

@@ -64,7 +64,11 @@ class SharedGallery:
     """Read-only cross-stream ReID gallery (BASELINE.json config C5): after a frame, ``step()`` exports
     this stream's confirmed tracks (csrc/gallery.cu), all-gathers every stream's export and matches
     each local track to the nearest track of another stream.  Nothing is written back into the
-    tracker, so per-stream ids and the parity with the oracle are unaffected."""
+    tracker, so per-stream ids and the parity with the oracle are unaffected.
+
+    Only the export (two tiny kernels reading the track table) runs on the tracker's stream; the
+    all-gather and the match run on a side stream with double-buffered exports, so the lock-step the
+    collective imposes on the ranks never stalls the per-stream association."""
 
     def __init__(self, tracker, t_max=256, max_dist=0.2):
         import ctypes as C
@@ -73,38 +77,57 @@ class SharedGallery:
         self._C, self._torch, self._lib_mod = C, torch, _lib
         self.trk, self.t_max, self.max_dist = tracker, int(t_max), float(max_dist)
         dev, D = tracker.device, tracker.cfg.feat_dim
-        self.feat = torch.zeros((self.t_max, D), dtype=torch.float32, device=dev)
-        self._ids2 = torch.full((2 * self.t_max,), -1, dtype=torch.int32, device=dev)
-        self.count = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.m_rank = torch.full((self.t_max,), -1, dtype=torch.int32, device=dev)
-        self.m_id = torch.full((self.t_max,), -1, dtype=torch.int32, device=dev)
-        self.m_dist = torch.zeros(self.t_max, dtype=torch.float32, device=dev)
+        z = lambda *shape, dt=torch.float32, fill=0: torch.full(shape, fill, dtype=dt, device=dev)
+        self._feat = [z(self.t_max, D) for _ in range(2)]
+        self._ids2 = [z(2 * self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
+        self._count = [z(1, dt=torch.int32) for _ in range(2)]
+        self._m_rank = [z(self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
+        self._m_id = [z(self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
+        self._m_dist = [z(self.t_max) for _ in range(2)]
+        with torch.cuda.device(dev):
+            self.stream = torch.cuda.Stream(device=dev)
+            self._done = [torch.cuda.Event() for _ in range(2)]
+        self._k = 0
+        self._last = 0
         self.rank = env_rank_world()[0]
 
-    @property
-    def ids(self):
-        return self._ids2[:self.t_max]
+    # views of the most recent step
+    feat = property(lambda self: self._feat[self._last])
+    ids = property(lambda self: self._ids2[self._last][:self.t_max])
+    count = property(lambda self: self._count[self._last])
+    m_rank = property(lambda self: self._m_rank[self._last])
+    m_id = property(lambda self: self._m_id[self._last])
+    m_dist = property(lambda self: self._m_dist[self._last])
 
     def step(self):
-        """export -> all-gather -> match; results stay on the device (``report()`` reads them)."""
+        """export (tracker stream) -> all-gather -> match (side stream); results stay on the device
+        (``report()`` waits for and reads them)."""
         C, torch, _lib = self._C, self._torch, self._lib_mod
-        lib, trk = _lib.load(), self.trk
-        with torch.cuda.device(trk.device), torch.cuda.stream(trk.stream):
-            sp = C.c_void_p(trk.stream.cuda_stream)
-            _lib.check(lib.ssb_gallery_export(trk._h, self.t_max, _lib.ptr(self.feat), _lib.ptr(self._ids2),
-                                              _lib.ptr(self.count), sp), "ssb_gallery_export")
-            all_feat, all_ids = gather_tracks(self.feat, self.ids)
-            _lib.check(lib.ssb_gallery_cross_match(
-                _lib.ptr(self.feat), _lib.ptr(self.ids), _lib.ptr(all_feat), _lib.ptr(all_ids),
-                int(all_feat.shape[0]), self.rank if all_feat.shape[0] > 1 else 0, self.t_max,
-                int(self.feat.shape[1]), self.max_dist, _lib.ptr(self.m_rank), _lib.ptr(self.m_id),
-                _lib.ptr(self.m_dist), sp), "ssb_gallery_cross_match")
-            self._all = (all_feat, all_ids)
-        return self.m_rank, self.m_id, self.m_dist
+        lib, trk, b = _lib.load(), self.trk, self._k & 1
+        feat, ids2, ids = self._feat[b], self._ids2[b], self._ids2[b][:self.t_max]
+        with torch.cuda.device(trk.device):
+            with torch.cuda.stream(trk.stream):
+                trk.stream.wait_event(self._done[b])          # the side stream is done with this buffer
+                _lib.check(lib.ssb_gallery_export(trk._h, self.t_max, _lib.ptr(feat), _lib.ptr(ids2),
+                                                  _lib.ptr(self._count[b]), C.c_void_p(trk.stream.cuda_stream)),
+                           "ssb_gallery_export")
+            self.stream.wait_stream(trk.stream)
+            with torch.cuda.stream(self.stream):
+                all_feat, all_ids = gather_tracks(feat, ids)
+                _lib.check(lib.ssb_gallery_cross_match(
+                    _lib.ptr(feat), _lib.ptr(ids), _lib.ptr(all_feat), _lib.ptr(all_ids),
+                    int(all_feat.shape[0]), self.rank if all_feat.shape[0] > 1 else 0, self.t_max,
+                    int(feat.shape[1]), self.max_dist, _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]),
+                    _lib.ptr(self._m_dist[b]), C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_cross_match")
+                self._all = (all_feat, all_ids)
+                self._done[b].record(self.stream)
+        self._last = b
+        self._k += 1
+        return self._m_rank[b], self._m_id[b], self._m_dist[b]
 
     def report(self):
         """[(local track id, remote rank, remote track id, cosine distance)] of the last step()."""
-        self.trk.stream.synchronize()
+        self.stream.synchronize()
         n = int(self.count.item())
         ids, r, i, d = (x[:n].cpu().numpy() for x in (self.ids, self.m_rank, self.m_id, self.m_dist))
         return [(int(ids[k]), int(r[k]), int(i[k]), float(d[k])) for k in range(n) if r[k] >= 0]

@@ -64,3 +64,55 @@ def test_camera_update_matches_oracle_and_tracking_continues():
             assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-12)
         assert_rows_equal(gpu.update(fr.dets, img, features=feats), ora.update(fr.dets, img, features=feats))
     assert_tables_equal(gpu.export_tracks(), ora.track_table())
+
+
+def test_c5_pose_pipeline_keypoints_follow_their_tracks():
+    """Config C5's per-stream path: raw YOLOv8-pose head -> decode -> NMS (51 keypoint channels ride
+    along) -> StrongSORT.update -> Results whose keypoints are re-indexed by the tracker's source
+    detection index, consumed the way the reference's process() does (:45-62)."""
+    import torch
+    from strongsort_yolo_b200.results import results_from_tracks
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    in_h = in_w = 640
+    st = synth.make_stream("C1", render=False)
+    bank = FeatureBank(seed=6)
+    dec = yolo.YoloV8Decode(1, 17, in_h, in_w)
+    nms = yolo.YoloNMS(num_classes=1, num_extra=51, max_anchors=dec.A)
+    trk = StrongSORT(max_tracks=128, max_dets=64)
+    ora = ss.StrongSORTOracle(None)
+    img = np.zeros((in_h, in_w, 3), dtype=np.uint8)
+    rng = np.random.default_rng(3)
+    seen_ids = 0
+    for f in range(6):
+        fr = st.next_frame()
+        d = fr.dets.copy(); d[:, 5] = 0
+        # keypoints = 17 points inside each box, derived from the box so they can be checked afterwards
+        t = np.linspace(0.1, 0.9, 17)
+        kp = np.stack([d[:, 0:1] + t * (d[:, 2:3] - d[:, 0:1]), d[:, 1:2] + t * (d[:, 3:4] - d[:, 1:2]),
+                       np.ones((len(d), 17))], 2)
+        raw = yolo.synth_raw_head_v8(d, 1, in_h, in_w, rng=rng, kpts=kp)
+        rows = nms.detect(dec(torch.as_tensor(raw).cuda()))          # [M, 6 + 51]
+        want = nms_np.yolo_nms(yolo_decode_np.decode_v8(raw, 1, 17, in_h, in_w), 1, 51, 0.3, 0.4, 1000, False)
+        assert rows.shape == want.shape and len(rows) > 0
+        # the detections feed tracker and oracle alike (embeddings from the bank, matched by position)
+        order = np.argsort(-d[:, 4], kind="stable")
+        feats = bank(fr.gt_ids[order][:len(rows)])
+        out = trk.update(rows[:, :6], img, features=feats)
+        ref = ora.update(rows[:, :6], img, features=feats)        # same detections for both trackers
+        assert_rows_equal(out, ref)
+        res = results_from_tracks(out, trk.last_det_index, keypoints=rows[:, 6:].reshape(-1, 17, 3))
+        if res.boxes.id is None or len(res.boxes) == 0:
+            continue
+        ids = [int(b.id) for b in res.boxes]                          # the reference's :46
+        assert len(set(ids)) == len(ids)
+        seen_ids += len(ids)
+        for k, (b, kpts) in enumerate(zip(res.boxes, res.keypoints)):  # the reference's :58-62
+            di = int(trk.last_det_index[k])
+            if di < 0:
+                continue
+            xy = np.asarray(kpts.xy.tolist())[0]
+            np.testing.assert_allclose(xy, rows[di, 6:].reshape(17, 3)[:, :2], atol=1e-4)
+            x1, y1, x2, y2 = rows[di, :4]
+            assert (xy[:, 0] >= x1 - 1).all() and (xy[:, 0] <= x2 + 1).all()
+            assert (xy[:, 1] >= y1 - 1).all() and (xy[:, 1] <= y2 + 1).all()
+    assert seen_ids > 0

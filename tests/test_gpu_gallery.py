@@ -26,7 +26,7 @@ def test_export_matches_oracle_table_and_world1_step():
         gpu.update(fr.dets, img, features=f)
     gal = dist.SharedGallery(gpu, t_max=32)
     gal.step()
-    gpu.stream.synchronize()
+    gal.stream.synchronize()
     want_f, want_i = gallery_np.export(ora.track_table())
     n = int(gal.count.item())
     assert n == len(want_i) > 0
