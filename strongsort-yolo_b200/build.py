@@ -15,6 +15,8 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]
 # per-file extra flags: the float64 tracker math keeps NumPy's expression order
 EXTRA = {"tracker.cu": ["-fmad=false"]}
+if os.environ.get("SSB_DW_FFMA2") in ("0", "1"):      # A/B switch of the depthwise FMA form (reid_tc3.cu)
+    EXTRA["reid_tc3.cu"] = ["-DSSB_DW_FFMA2=" + os.environ["SSB_DW_FFMA2"]]
 
 
 def sources():

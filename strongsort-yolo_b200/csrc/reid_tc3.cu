@@ -138,8 +138,12 @@ __device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t *r) {
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-// four fp32 channels as two packed pairs: Blackwell's FFMA2 (fma.rn.f32x2) does two IEEE fp32
-// FMAs per issue slot -- the depthwise pass is issue-bound, not FMA-pipe-bound
+// four fp32 channels of the depthwise pass.  SSB_DW_FFMA2 = 1: two packed pairs and Blackwell's FFMA2
+// (fma.rn.f32x2, two IEEE fp32 FMAs per instruction); 0: four scalar FFMAs.  Same results either way.
+#ifndef SSB_DW_FFMA2
+#define SSB_DW_FFMA2 1
+#endif
+#if SSB_DW_FFMA2
 struct P4 { unsigned long long a, b; };          // channels (0,1), (2,3)
 __device__ __forceinline__ P4 ldp4(const float4 *p) {
     const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(p);
@@ -149,6 +153,22 @@ __device__ __forceinline__ void fma4(P4 &o, const P4 &w, const P4 &v) {
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o.a) : "l"(w.a), "l"(v.a));
     asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(o.b) : "l"(w.b), "l"(v.b));
 }
+__device__ __forceinline__ float p4x(const P4 &v) { return __uint_as_float((uint32_t)v.a); }
+__device__ __forceinline__ float p4y(const P4 &v) { return __uint_as_float((uint32_t)(v.a >> 32)); }
+__device__ __forceinline__ float p4z(const P4 &v) { return __uint_as_float((uint32_t)v.b); }
+__device__ __forceinline__ float p4w(const P4 &v) { return __uint_as_float((uint32_t)(v.b >> 32)); }
+#else
+typedef float4 P4;
+__device__ __forceinline__ P4 ldp4(const float4 *p) { return *p; }
+__device__ __forceinline__ void fma4(P4 &o, const P4 &w, const P4 &v) {
+    o.x = fmaf(w.x, v.x, o.x); o.y = fmaf(w.y, v.y, o.y);
+    o.z = fmaf(w.z, v.z, o.z); o.w = fmaf(w.w, v.w, o.w);
+}
+__device__ __forceinline__ float p4x(const P4 &v) { return v.x; }
+__device__ __forceinline__ float p4y(const P4 &v) { return v.y; }
+__device__ __forceinline__ float p4z(const P4 &v) { return v.z; }
+__device__ __forceinline__ float p4w(const P4 &v) { return v.w; }
+#endif
 __device__ __forceinline__ float plo(unsigned long long v) { return __uint_as_float((uint32_t)v); }
 __device__ __forceinline__ float phi(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
@@ -463,8 +483,8 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
                         fma4(o, wd[3 + dx], wb[dx]);
                         fma4(o, wd[6 + dx], wc[dx]);
                     }
-                    float ox = fmaxf(plo(o.a), 0.f), oy = fmaxf(phi(o.a), 0.f);
-                    float oz = fmaxf(plo(o.b), 0.f), ow = fmaxf(phi(o.b), 0.f);
+                    float ox = fmaxf(p4x(o), 0.f), oy = fmaxf(p4y(o), 0.f);
+                    float oz = fmaxf(p4z(o), 0.f), ow = fmaxf(p4w(o), 0.f);
                     const int gr = row0 + lr;
                     if (gr < 0 || gr >= C::H) { ox = 0.f; oy = 0.f; oz = 0.f; ow = 0.f; }     // warp-uniform
                     if (last) {                // rows [ra, rb) == the band's own rows when rem == 0
