@@ -14,7 +14,10 @@
  *     never allocates device memory: ssb_create() carves the caller-provided
  *     workspace of ssb_workspace_bytes() bytes.
  *   - all work is enqueued on the caller's stream (cudaStream_t passed as
- *     void*); no entry point synchronises; graph-capturable.
+ *     void*); no entry point synchronises; graph-capturable.  (ssb_update and ssb_reid fork
+ *     half of a frame's embedding onto an internal non-blocking stream and joins
+ *     it back with events before the association -- ordering on the caller's
+ *     stream is unchanged.)
  *   - return 0 on success, negative on error; ssb_last_error() returns a
  *     thread-local message.  No exceptions cross the ABI.
  *   - one handle per video stream; a handle is not thread-safe, distinct

@@ -100,6 +100,10 @@ struct ssb_tracker {
                               // 2: tcgen05 pointwise + fp32 CUDA-core depthwise (reid_tc3.cu)
     int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
     DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
+    // ssb_update embeds the two halves of a frame's crops on two streams (fork / join by events):
+    // the partial last waves of one half's kernels are filled by the other half's
+    cudaStream_t side_stream;
+    cudaEvent_t ev_fork, ev_join;
 };
 
 void ssb_set_error(const char *fmt, ...);
