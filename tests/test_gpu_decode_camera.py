@@ -116,3 +116,32 @@ def test_c5_pose_pipeline_keypoints_follow_their_tracks():
             assert (xy[:, 0] >= x1 - 1).all() and (xy[:, 0] <= x2 + 1).all()
             assert (xy[:, 1] >= y1 - 1).all() and (xy[:, 1] <= y2 + 1).all()
     assert seen_ids > 0
+
+
+def test_decode_and_camera_against_committed_golden(golden_dir):
+    """The committed fixtures (tools/make_golden.py): decode of raw detect / pose heads, camera warp."""
+    import os
+    import torch
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    g = np.load(os.path.join(golden_dir, "decode_kat.npz"))
+    in_h, in_w = [int(v) for v in g["in_hw"]]
+    for raw, out, nc, nk in ((g["raw_det"], g["out_det"], 5, 0), (g["raw_pose"], g["out_pose"], 1, 17)):
+        got = yolo.YoloV8Decode(nc, nk, in_h, in_w)(torch.as_tensor(raw).cuda()).cpu().numpy()
+        np.testing.assert_allclose(got[:4], out[:4], rtol=2e-5, atol=2e-3)
+        np.testing.assert_allclose(got[4:4 + nc], out[4:4 + nc], rtol=1e-5, atol=1e-6)
+        if nk:
+            kg, ko = got[4 + nc:].reshape(nk, 3, -1), out[4 + nc:].reshape(nk, 3, -1)
+            np.testing.assert_allclose(kg[:, :2], ko[:, :2], rtol=1e-5, atol=1e-3)
+            np.testing.assert_allclose(kg[:, 2], ko[:, 2], rtol=1e-5, atol=1e-6)
+    c = np.load(os.path.join(golden_dir, "camera_kat.npz"))
+    # same stream / bank as tools/make_golden.py: camera_kat -> the table before the warp is the golden one
+    st = synth.make_stream("C1", render=False)
+    bank = FeatureBank(seed=11)
+    gpu = StrongSORT(max_tracks=128, max_dets=64)
+    img = np.zeros((640, 640, 3), dtype=np.uint8)
+    for _ in range(5):
+        fr = st.next_frame()
+        gpu.update(fr.dets, img, features=bank(fr.gt_ids))
+    np.testing.assert_allclose(gpu.export_tracks()["mean"], c["mean_before"], rtol=1e-9, atol=1e-9)
+    gpu.camera_update(None, None, warp_matrix=c["warp"])
+    np.testing.assert_allclose(gpu.export_tracks()["mean"], c["mean_after"], rtol=1e-9, atol=1e-9)

@@ -69,3 +69,24 @@ def test_cross_match_matches_restatement(self_rank):
     live = all_ids[self_rank] >= 0
     np.testing.assert_allclose(m_dist.cpu().numpy()[live], w_dist[live], atol=2e-6)
     assert (w_rank[live] >= 0).sum() > 5            # the scenario does produce cross-stream matches
+
+
+def test_cross_match_against_committed_golden(golden_dir):
+    import os
+    import torch
+    from strongsort_yolo_b200 import _lib
+    lib = _lib.load()
+    g = np.load(os.path.join(golden_dir, "gallery_kat.npz"))
+    G, T, D = g["feat"].shape
+    P = lambda t: C.c_void_p(t.data_ptr())
+    af, ai = torch.as_tensor(g["feat"]).cuda(), torch.as_tensor(g["ids"]).cuda()
+    for r in range(G):
+        m_rank = torch.zeros(T, dtype=torch.int32, device="cuda")
+        m_id = torch.zeros(T, dtype=torch.int32, device="cuda")
+        m_dist = torch.zeros(T, dtype=torch.float32, device="cuda")
+        _lib.check(lib.ssb_gallery_cross_match(P(af[r].contiguous()), P(ai[r].contiguous()), P(af), P(ai), G, r, T, D,
+                                               0.2, P(m_rank), P(m_id), P(m_dist),
+                                               C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(m_rank.cpu().numpy(), g["m_rank"][r])
+        np.testing.assert_array_equal(m_id.cpu().numpy(), g["m_id"][r])

@@ -92,3 +92,30 @@ def test_empty_and_ragged_frames():
         k = [5, 0, 3, 5, 1, 5][f]
         out = trk.update(fr.dets[:k], img, features=bank(fr.gt_ids[:k]))
     assert out.shape[1] == 7
+
+
+def test_decode_golden(golden_dir):
+    from oracle import yolo_decode_np
+    g = np.load(os.path.join(golden_dir, "decode_kat.npz"))
+    in_h, in_w = [int(v) for v in g["in_hw"]]
+    np.testing.assert_allclose(yolo_decode_np.decode_v8(g["raw_det"], 5, 0, in_h, in_w), g["out_det"], rtol=1e-6, atol=1e-5)
+    np.testing.assert_allclose(yolo_decode_np.decode_v8(g["raw_pose"], 1, 17, in_h, in_w), g["out_pose"], rtol=1e-6, atol=1e-5)
+
+
+def test_camera_update_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "camera_kat.npz"))
+    for before, after in zip(g["mean_before"], g["mean_after"]):
+        t = ss.Track(before.copy(), np.eye(8), 1, 0, 0.5, 3, 30, 0.9, None)
+        t.camera_update(g["warp"])
+        np.testing.assert_allclose(t.mean, after, rtol=1e-13, atol=0)
+
+
+def test_gallery_cross_match_golden(golden_dir):
+    from oracle import gallery_np
+    g = np.load(os.path.join(golden_dir, "gallery_kat.npz"))
+    for r in range(g["feat"].shape[0]):
+        m_rank, m_id, m_dist = gallery_np.cross_match(g["feat"][r], g["ids"][r], g["feat"], g["ids"], r, 0.2)
+        np.testing.assert_array_equal(m_rank, g["m_rank"][r])
+        np.testing.assert_array_equal(m_id, g["m_id"][r])
+        live = g["ids"][r] >= 0
+        np.testing.assert_allclose(m_dist[live], g["m_dist"][r][live], atol=1e-6)

@@ -7,6 +7,9 @@ oracle (self-pinned: the reference ships no fixtures).
                   FeatureBank embeddings: outputs per frame + decision margins
   reid_kat.npz    one 320x320 frame, 6 crop boxes, oracle embeddings
   nms_kat.npz     a decoded YOLOv8 head [84,1200] and torchvision's NMS result
+  decode_kat.npz  raw YOLOv8 detect and pose heads (96x160 input, A = 315) and their decode
+  camera_kat.npz  a tracker state before / after Tracker.camera_update with a Euclidean warp
+  gallery_kat.npz 3 streams' exported tracks and the cross-stream match of every stream
 
 Run from the repo root:  python tools/make_golden.py
 """
@@ -19,7 +22,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-from oracle import nms_np, osnet_torch, strongsort_np as ss  # noqa: E402
+from oracle import gallery_np, nms_np, osnet_torch, strongsort_np as ss, yolo_decode_np  # noqa: E402
 from strongsort_yolo_b200 import synth, weights, yolo  # noqa: E402
 from helpers import FeatureBank  # noqa: E402
 
@@ -107,8 +110,59 @@ def nms_kat():
     print("nms_kat: kept", len(out))
 
 
+def decode_kat():
+    rng = np.random.default_rng(314)
+    in_h, in_w = 96, 160                                   # A = 12*20 + 6*10 + 3*5 = 315
+    raw_det = rng.normal(0, 2.0, (64 + 5, 315)).astype(np.float32)
+    raw_pose = rng.normal(0, 2.0, (64 + 1 + 3 * 17, 315)).astype(np.float32)
+    np.savez_compressed(os.path.join(OUT, "decode_kat.npz"), in_hw=np.asarray([in_h, in_w]),
+                        raw_det=raw_det, out_det=yolo_decode_np.decode_v8(raw_det, 5, 0, in_h, in_w),
+                        raw_pose=raw_pose, out_pose=yolo_decode_np.decode_v8(raw_pose, 1, 17, in_h, in_w))
+    print("decode_kat: 315 anchors, det + pose heads")
+
+
+def camera_kat():
+    st = synth.make_stream("C1", render=False)
+    bank = FeatureBank(seed=11)
+    trk = ss.StrongSORTOracle(None)
+    img = np.zeros((640, 640, 3), dtype=np.uint8)
+    frames = []
+    for _ in range(5):
+        fr = st.next_frame()
+        frames.append(fr)
+        trk.update(fr.dets, img, features=bank(fr.gt_ids))
+    th = np.deg2rad(0.7)
+    warp = np.array([[np.cos(th), -np.sin(th), 4.5], [np.sin(th), np.cos(th), -2.25]])
+    before = np.stack([t.mean.copy() for t in trk.tracker.tracks])
+    trk.tracker.camera_update(warp)
+    after = np.stack([t.mean.copy() for t in trk.tracker.tracks])
+    np.savez_compressed(os.path.join(OUT, "camera_kat.npz"), warp=warp, mean_before=before, mean_after=after)
+    print("camera_kat:", len(before), "tracks")
+
+
+def gallery_kat():
+    rng = np.random.default_rng(2718)
+    G, T, D = 3, 16, 512
+    base = np.maximum(rng.normal(0, 1, (14, D)), 0)
+    feat = np.zeros((G, T, D), dtype=np.float32)
+    ids = np.full((G, T), -1, dtype=np.int32)
+    for g in range(G):
+        n = 8 + 2 * g
+        who = rng.permutation(14)[:n]
+        f = base[who] + rng.normal(0, 0.04, (n, D))
+        feat[g, :n] = (f / np.linalg.norm(f, axis=1, keepdims=True)).astype(np.float32)
+        ids[g, :n] = 1 + np.arange(n) + 50 * g
+    res = [gallery_np.cross_match(feat[g], ids[g], feat, ids, g, 0.2) for g in range(G)]
+    np.savez_compressed(os.path.join(OUT, "gallery_kat.npz"), feat=feat, ids=ids,
+                        m_rank=np.stack([r[0] for r in res]), m_id=np.stack([r[1] for r in res]),
+                        m_dist=np.stack([r[2] for r in res]))
+    print("gallery_kat: matches per stream", [(r[0] >= 0).sum() for r in res])
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    c1_e2e(); c2_tracker(); reid_kat(); nms_kat()
+    if "--new-only" not in sys.argv:
+        c1_e2e(); c2_tracker(); reid_kat(); nms_kat()
+    decode_kat(); camera_kat(); gallery_kat()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
