@@ -80,37 +80,106 @@ def gen_frames(stream_id, count, pin):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (every 5 ms,
+    in-process, so even a 150 ms region gets tens of samples); falls back to `nvidia-smi -lms` if NVML
+    cannot be loaded.  CUDA_VISIBLE_DEVICES is honoured through the device's UUID / PCI bus id."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
         self.idx = gpu_index
-        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
-        self.p = None
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = False
+        self._thr = None
+        self._smi = None
+        self._nv = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            props = torch.cuda.get_device_properties(gpu_index)
+            h = None
+            try:                                   # the CUDA device's UUID survives CUDA_VISIBLE_DEVICES remapping
+                u = str(props.uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID((u if u.startswith("GPU-") else "GPU-" + u).encode())
+            except Exception:
+                h = None
+            if h is None:
+                try:
+                    h = pynvml.nvmlDeviceGetHandleByPciBusId(
+                        ("%08x:%02x:%02x.0" % (props.pci_domain_id, props.pci_bus_id, props.pci_device_id)).encode())
+                except Exception:
+                    vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+                    ids = [int(v) for v in vis.split(",") if v.strip().isdigit()]
+                    h = pynvml.nvmlDeviceGetHandleByIndex(ids[gpu_index] if gpu_index < len(ids) else gpu_index)
+            self._h = h
+            self._nv = pynvml
+        except Exception:
+            self._nv = None
+
+    def _poll(self):
+        nv = self._nv
+        bits = ((nv.nvmlClocksEventReasonHwSlowdown, "hw_slowdown"),
+                (nv.nvmlClocksEventReasonHwThermalSlowdown, "hw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwThermalSlowdown, "sw_thermal_slowdown"),
+                (nv.nvmlClocksEventReasonSwPowerCap, "sw_power_cap"))
+        while not self._stop:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM)))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                for bit, name in bits:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        if self._nv is not None:
+            import threading
+            try:
+                self.max_mhz = float(self._nv.nvmlDeviceGetMaxClockInfo(self._h, self._nv.NVML_CLOCK_SM))
+            except Exception:
+                self.max_mhz = None
+            self._thr = threading.Thread(target=self._poll, daemon=True)
+            self._thr.start()
+            return
         try:
-            self.p = subprocess.Popen(
+            self._f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+            self._smi = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
-                stdout=self.f, stderr=subprocess.DEVNULL)
+                 "--format=csv,noheader,nounits", "-lms", "20"],
+                stdout=self._f, stderr=subprocess.DEVNULL)
         except Exception:
-            self.p = None
+            self._smi = None
 
     def stop(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
-        if self.p is None:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": None}
+        if self._thr is not None:
+            self._stop = True
+            self._thr.join(timeout=2)
+            src = "nvml"
+            if not self.samples:                   # the poller never ran inside the region: one reading right after it
+                try:
+                    self.samples.append(float(self._nv.nvmlDeviceGetClockInfo(self._h, self._nv.NVML_CLOCK_SM)))
+                    src = "nvml (single reading right after the timed region)"
+                except Exception:
+                    pass
+            if self.samples:
+                out.update(sm_mhz=float(np.median(self.samples)), sm_max_mhz=self.max_mhz,
+                           reasons=sorted(self.reasons), samples=len(self.samples), source=src)
             return out
-        self.p.terminate()
+        if self._smi is None:
+            return out
+        self._smi.terminate()
         try:
-            self.p.wait(timeout=5)
+            self._smi.wait(timeout=5)
         except Exception:
-            self.p.kill()
-        self.f.flush()
-        rows = [r.strip().split(",") for r in open(self.f.name).read().strip().splitlines() if r.strip()]
-        os.unlink(self.f.name)
+            self._smi.kill()
+        self._f.flush()
+        rows = [r.strip().split(",") for r in open(self._f.name).read().strip().splitlines() if r.strip()]
+        os.unlink(self._f.name)
         sm, reasons = [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -125,6 +194,7 @@ class ClockSampler:
             out["sm_mhz"] = float(np.median(sm))
         out["reasons"] = sorted(reasons)
         out["samples"] = len(sm)
+        out["source"] = "nvidia-smi"
         return out
 
 
