@@ -80,8 +80,8 @@ def gen_frames(stream_id, count, pin):
 
 
 class ClockSampler:
-    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (every 5 ms,
-    in-process, so even a 150 ms region gets tens of samples); falls back to `nvidia-smi -lms` if NVML
+    """SM clock / throttle reasons sampled DURING the timed region: an NVML polling thread (every 20 ms,
+    in-process, so even a 150 ms region gets several samples); falls back to `nvidia-smi -lms` if NVML
     cannot be loaded.  CUDA_VISIBLE_DEVICES is honoured through the device's UUID / PCI bus id."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -133,7 +133,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.005)
+            time.sleep(0.02)
 
     def start(self):
         if self._nv is not None:
