@@ -175,6 +175,12 @@ int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_
 int ssb_yolo_num_anchors(int in_h, int in_w);
 int ssb_yolo_decode_v8(const float *raw_dev, int num_classes, int num_kpts, int in_h, int in_w,
                        float *pred_out_dev, ssb_stream_t stream);
+/* YOLOv5 / v7 head (BASELINE config C1, the detectors upstream StrongSORT-YOLO pairs with the tracker):
+ * raw float32 [3 * ssb_yolo_num_anchors(in_h, in_w), 5 + nc] logits (level by level, [na][gy][gx] inside a
+ * level), anchors_px_dev float32 [3 levels][3][w, h] in pixels -> pred [4 + nc, A] with score = obj * cls,
+ * zero where obj <= conf_thres (yolov5 non_max_suppression's candidate rule), ready for ssb_yolo_nms.   */
+int ssb_yolo_decode_v5(const float *raw_dev, int num_classes, int in_h, int in_w, float conf_thres,
+                       const float *anchors_px_dev, float *pred_out_dev, ssb_stream_t stream);
 
 /* camera-motion compensation, tracker side (upstream Track.camera_update after its ECC call,
  * SURVEY.md A.9): warp2x3_host = row-major 2x3 matrix (host doubles, e.g. cv2.findTransformECC's

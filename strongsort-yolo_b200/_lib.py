@@ -17,7 +17,7 @@ SYMBOLS = [
     "ssb_crop_boxes", "ssb_kf_predict", "ssb_kf_update", "ssb_kf_gating",
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
-    "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_camera_update",
+    "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
     "ssb_gallery_export", "ssb_gallery_cross_match",
 ]
 
@@ -88,6 +88,7 @@ def load():
     lib.ssb_yolo_num_anchors.argtypes = [i32, i32]
     lib.ssb_yolo_num_anchors.restype = i32
     lib.ssb_yolo_decode_v8.argtypes = [vp, i32, i32, i32, i32, vp, vp]
+    lib.ssb_yolo_decode_v5.argtypes = [vp, i32, i32, i32, C.c_float, vp, vp, vp]
     lib.ssb_camera_update.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.ssb_gallery_export.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ssb_gallery_cross_match.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp]

@@ -54,7 +54,48 @@ __global__ void yolo_decode_v8_kernel(const float *__restrict__ raw, int nc, int
     }
 }
 
+// YOLOv5 / v7 head (the detectors upstream StrongSORT-YOLO wires to the tracker): raw [A][5 + nc] logits,
+// A = 3 anchors x the stride-8/16/32 grids, level by level, anchor-major inside a level ([na][gy][gx]).
+//   xy = (2 s(x) - 0.5 + grid) * stride ; wh = (2 s(w))^2 * anchor ; obj, cls = sigmoid
+// and non_max_suppression's scoring folded in: score_c = obj * cls_c, zeroed when obj <= conf_thres
+// (yolov5 utils/general.py: `xc = prediction[..., 4] > conf_thres`, `x[:, 5:] *= x[:, 4:5]`), so the result
+// is the channel-major [4 + nc][A] tensor ssb_yolo_nms consumes.  anchors_px: 3 levels x 3 anchors x (w, h).
+__global__ void yolo_decode_v5_kernel(const float *__restrict__ raw, int nc, int in_h, int in_w, int A,
+                                      float conf_thres, const float *__restrict__ anchors_px,
+                                      float *__restrict__ out) {
+    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= A) return;
+    int rem = a, stride = 8, gw = in_w / 8, gh = in_h / 8, lvl = 0;
+    for (; lvl < 2; lvl++) {
+        if (rem < 3 * gw * gh) break;
+        rem -= 3 * gw * gh;
+        stride *= 2; gw = in_w / stride; gh = in_h / stride;
+    }
+    const int ia = rem / (gw * gh), cell = rem - ia * gw * gh;
+    const float gx = (float)(cell % gw), gy = (float)(cell / gw), fs = (float)stride;
+    const float *p = raw + (size_t)a * (5 + nc);
+    auto sg = [](float v) { return 1.f / (1.f + expf(-v)); };
+    const float sx = sg(p[0]), sy = sg(p[1]), sw = sg(p[2]), sh = sg(p[3]), obj = sg(p[4]);
+    out[(size_t)0 * A + a] = (sx * 2.f - 0.5f + gx) * fs;
+    out[(size_t)1 * A + a] = (sy * 2.f - 0.5f + gy) * fs;
+    out[(size_t)2 * A + a] = (sw * 2.f) * (sw * 2.f) * anchors_px[(lvl * 3 + ia) * 2 + 0];
+    out[(size_t)3 * A + a] = (sh * 2.f) * (sh * 2.f) * anchors_px[(lvl * 3 + ia) * 2 + 1];
+    const bool cand = obj > conf_thres;
+    for (int c = 0; c < nc; c++) out[(size_t)(4 + c) * A + a] = cand ? sg(p[5 + c]) * obj : 0.f;
+}
+
 }  // namespace
+
+extern "C" int ssb_yolo_decode_v5(const float *raw_dev, int num_classes, int in_h, int in_w, float conf_thres,
+                                  const float *anchors_px_dev, float *pred_out_dev, ssb_stream_t stream) {
+    if (!raw_dev || !pred_out_dev || !anchors_px_dev) { ssb_set_error("null argument"); return -1; }
+    if (in_h <= 0 || in_w <= 0 || in_h % 32 || in_w % 32 || num_classes < 1) { ssb_set_error("bad head geometry"); return -1; }
+    const int A = 3 * ((in_h / 8) * (in_w / 8) + (in_h / 16) * (in_w / 16) + (in_h / 32) * (in_w / 32));
+    yolo_decode_v5_kernel<<<(A + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw_dev, num_classes, in_h, in_w, A, conf_thres,
+                                                                             anchors_px_dev, pred_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int ssb_yolo_num_anchors(int in_h, int in_w) {
     if (in_h <= 0 || in_w <= 0 || in_h % 32 || in_w % 32) return -1;

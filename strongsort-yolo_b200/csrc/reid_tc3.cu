@@ -399,7 +399,6 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
     const int dw_seg = warp / C::TPS, dw_cb = (warp % C::TPS) % C::NCB;
     const int dw_cg = (((warp % C::TPS) / C::NCB) * C::CPW + lane / (2 * C::XL)) * 2 + dw_par;
     const int dw_col = dw_cb * C::XL + (lane >> 1) % C::XL;
-    long long acc_issue = 0, acc_dw = 0, acc_pub = 0;      // debug accumulators of thread 0 (dbg != nullptr)
     int lc = 0;
     uint32_t tile_par = 0, c3_par = 0;
     bool c3_pending = false;
@@ -528,20 +527,12 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
                 // half's depthwise pass; the lower half's MMAs run under the upper half's drain
                 if (C::NT >= 2) {
                     constexpr int TH_ = C::NT / 2, HR = TH_ * 128 / C::W;
-                    long long c0 = clock64();
                     dw_rows(ra, rb < HR ? rb : HR);
-                    long long c1 = clock64();
                     publish();
-                    long long c2 = clock64();
                     if (issuer) issue_pw(sP, lc + 1, 0, TH_);
-                    long long c3 = clock64();
                     dw_rows(ra > HR ? ra : HR, rb);
-                    long long c4 = clock64();
                     publish();
-                    long long c5 = clock64();
                     if (issuer) issue_pw(sP, lc + 1, TH_, C::NT);
-                    long long c6 = clock64();
-                    acc_dw += (c1 - c0) + (c4 - c3); acc_pub += (c2 - c1) + (c5 - c4); acc_issue += (c3 - c2) + (c6 - c5);
                 } else {
                     dw_rows(ra, rb);
                     publish();
@@ -725,7 +716,7 @@ osblock3_kernel(const float *__restrict__ x, float *__restrict__ y,
         __syncwarp();
     }
     stamp();                                   // final epilogue done
-    if (dbg && blockIdx.x == 0 && tid == 0) { dbg[0] = dbg_n; dbg[60] = acc_issue; dbg[61] = acc_dw; dbg[62] = acc_pub; }
+    if (dbg && blockIdx.x == 0 && tid == 0) dbg[0] = dbg_n;
     if (!ok) { if (tid == 0) atomicExch(status, 5); }
     tc::fence_before_sync();
     if (C::NB > 1) cluster.sync(); else __syncthreads();     // no band exits while its peers may still push into it

@@ -84,6 +84,42 @@ class YoloV8Decode:
         return self._out
 
 
+# yolov5n/s/m/l/x anchors (models/yolov5*.yaml), pixels, P3/8, P4/16, P5/32
+V5_ANCHORS = np.asarray([[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
+                        dtype=np.float32).reshape(3, 3, 2)
+
+
+class YoloV5Decode:
+    """Raw YOLOv5 / v7 head [A, 5 + nc] (A = 3 anchors x 3 levels, 25200 at 640x640) -> [4 + nc, A] with
+    score = obj * cls (csrc/decode.cu), the tensor ``YoloNMS`` consumes."""
+
+    def __init__(self, num_classes=80, in_h=640, in_w=640, conf=DEFAULT_CONF, anchors=None, device="cuda:0"):
+        torch = _lib.require_cuda()
+        self._torch, self._lib = torch, _lib.load()
+        self.device = torch.device(device)
+        self.nc, self.in_h, self.in_w, self.conf = int(num_classes), int(in_h), int(in_w), float(conf)
+        n = int(self._lib.ssb_yolo_num_anchors(self.in_h, self.in_w))
+        if n <= 0:
+            raise ValueError("network input size must be a positive multiple of 32")
+        self.A = 3 * n
+        a = V5_ANCHORS if anchors is None else np.asarray(anchors, dtype=np.float32).reshape(3, 3, 2)
+        self._anchors = torch.as_tensor(np.ascontiguousarray(a)).to(self.device)
+        self._out = torch.empty((4 + self.nc, self.A), dtype=torch.float32, device=self.device)
+
+    def __call__(self, raw, stream=None):
+        torch = self._torch
+        if raw.dim() == 3:
+            raw = raw[0]
+        if tuple(raw.shape) != (self.A, 5 + self.nc):
+            raise ValueError(f"raw head shape {tuple(raw.shape)} != {(self.A, 5 + self.nc)}")
+        raw = raw.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.ssb_yolo_decode_v5(_lib.ptr(raw), self.nc, self.in_h, self.in_w, self.conf,
+                                                _lib.ptr(self._anchors), _lib.ptr(self._out),
+                                                C.c_void_p(st.cuda_stream)), "ssb_yolo_decode_v5")
+        return self._out
+
+
 def synth_raw_head_v8(dets, num_classes, in_h, in_w, rng=None, kpts=None):
     """Synthetic RAW v8 head [64 + nc (+3*K), A] whose decode + NMS gives (close to) ``dets`` [N,6]
     (boxes in network-input pixels): each detection is written into the anchor of the finest level

@@ -145,3 +145,26 @@ def test_decode_and_camera_against_committed_golden(golden_dir):
     np.testing.assert_allclose(gpu.export_tracks()["mean"], c["mean_before"], rtol=1e-9, atol=1e-9)
     gpu.camera_update(None, None, warp_matrix=c["warp"])
     np.testing.assert_allclose(gpu.export_tracks()["mean"], c["mean_after"], rtol=1e-9, atol=1e-9)
+
+
+def test_decode_v5_matches_restatement_and_feeds_nms():
+    """BASELINE config C1's detector head format (YOLOv5n: [1, 25200, 85] at 640x640)."""
+    import torch
+    rng = np.random.default_rng(21)
+    nc = 80
+    dec = yolo.YoloV5Decode(nc, 640, 640, conf=0.3)
+    assert dec.A == 25200
+    raw = rng.normal(-1.0, 2.0, (dec.A, 5 + nc)).astype(np.float32)
+    got = dec(torch.as_tensor(raw).cuda()).cpu().numpy()
+    want = yolo_decode_np.decode_v5(raw, nc, 640, 640, 0.3)
+    np.testing.assert_allclose(got[:4], want[:4], rtol=2e-5, atol=2e-3)
+    np.testing.assert_allclose(got[4:], want[4:], rtol=1e-5, atol=1e-6)
+    assert ((got[4:] == 0) == (want[4:] == 0)).all()
+    raw[:, 4] -= 6.0                                   # few candidates, like a real frame: run the NMS on them
+    nms = yolo.YoloNMS(num_classes=nc, max_anchors=dec.A, conf=0.05)
+    dec2 = yolo.YoloV5Decode(nc, 640, 640, conf=0.05)
+    rows = nms.detect(dec2(torch.as_tensor(raw).cuda()))
+    ref = nms_np.yolo_nms(yolo_decode_np.decode_v5(raw, nc, 640, 640, 0.05), nc, 0, 0.05, 0.4, 1000, False)
+    assert rows.shape == ref.shape and len(rows) > 0
+    np.testing.assert_allclose(rows[:, :5], ref[:, :5], rtol=2e-5, atol=2e-3)
+    np.testing.assert_array_equal(rows[:, 5], ref[:, 5])

@@ -78,3 +78,17 @@ def test_ecc_warp_estimates_translation():
     assert w is not None and w.shape == (2, 3)
     assert abs(abs(w[0, 2]) - 20) < 3 and abs(abs(w[1, 2]) - 10) < 3
     assert abs(w[0, 0] - 1) < 0.02 and abs(w[0, 1]) < 0.02
+
+
+def test_decode_v5_restatement_shapes_and_rule():
+    rng = np.random.default_rng(12)
+    in_h = in_w = 64                                   # A = 3 * (64 + 16 + 4) = 252
+    raw = rng.normal(0, 2.0, (252, 5 + 4)).astype(np.float32)
+    out = yolo_decode_np.decode_v5(raw, 4, in_h, in_w, 0.3)
+    assert out.shape == (8, 252)
+    obj = 1 / (1 + np.exp(-raw[:, 4]))
+    assert (out[4:, obj <= 0.3] == 0).all() and (out[4:, obj > 0.3] > 0).all()
+    # first anchor of the first level, cell (0, 0): xy = (2 s - 0.5) * 8, wh = (2 s)^2 * (10, 13)
+    s = 1 / (1 + np.exp(-raw[0, :4].astype(np.float64)))
+    np.testing.assert_allclose(out[:4, 0], [(2 * s[0] - 0.5) * 8, (2 * s[1] - 0.5) * 8, (2 * s[2]) ** 2 * 10,
+                                            (2 * s[3]) ** 2 * 13], rtol=1e-5)

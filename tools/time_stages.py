@@ -68,8 +68,6 @@ def main():
             d = dbg.cpu().numpy()
             k = int(d[0])
             out[f"osblock{b}{tag}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
-            if mode == 2:
-                out[f"osblock{b}_acc_issue_dw_publish"] = [int(d[60]), int(d[61]), int(d[62])]
     # stem phases (CTA 0): S built, MMAs done, conv drained, pooled
     lib.ssb_reid_tc_debug(P(dbg))
     _lib.check(lib.ssb_reid(trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST()))
