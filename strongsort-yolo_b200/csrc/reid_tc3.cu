@@ -169,8 +169,6 @@ __device__ __forceinline__ float p4y(const P4 &v) { return v.y; }
 __device__ __forceinline__ float p4z(const P4 &v) { return v.z; }
 __device__ __forceinline__ float p4w(const P4 &v) { return v.w; }
 #endif
-__device__ __forceinline__ float plo(unsigned long long v) { return __uint_as_float((uint32_t)v); }
-__device__ __forceinline__ float phi(unsigned long long v) { return __uint_as_float((uint32_t)(v >> 32)); }
 
 template <class C>
 __global__ void __launch_bounds__(K3_THREADS, 1)

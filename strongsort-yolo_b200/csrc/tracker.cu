@@ -645,7 +645,7 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     bool sparse = false;
     if (!staged && nc <= 512) {
         __shared__ double s_bg[8];
-        __shared__ int s_cnt[8], s_total;
+        __shared__ int s_total;
         const int wid = tid >> 5, nwarp = blockDim.x >> 5;
         double mx = -INFINITY;
         for (int e = tid; e < nr0 * nc0; e += blockDim.x) { const double c = C[e]; if (c > mx) mx = c; }
@@ -676,7 +676,6 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
             s_total = acc;
         }
         __syncthreads();
-        (void)s_cnt;
         if ((size_t)s_total <= cap) {
             for (int i = wid; i < nr; i += nwarp) {        // pass 2: fill, column order
                 int off = rowptr[i];
