@@ -11,19 +11,26 @@ every detection crop + Kalman predict + gated appearance cost + IoU cost + two
 linear assignments + track-table update.  Seeded random-weight OSNet (no
 pretrained file exists offline) and synthetic frames -- "data": "synthetic".
 
-  value  : frames/s with frames and detections already resident in HBM,
-           timed per step with CUDA events on the tracker's stream, L2 flushed
-           between steps (a 256 MiB write outside the timed pair)
-  e2e    : frames/s through the public ``StrongSORT.update`` with HOST inputs
+  value  : frames/s with frames and detections already resident in HBM, through the
+           two-stage pipeline (``update_pipelined``: the OSNet of frame k on one stream
+           overlaps the association of frame k-1 on another; identical results), K frames
+           timed as a whole with CUDA events; inputs rotate through W+K distinct frames
+           (>= 5x the L2), ``config.serial_flushed_ms_per_step`` is the one-frame-at-a-
+           time figure with a 256 MiB L2 flush between steps
+  e2e    : frames/s through the public synchronous ``StrongSORT.update`` with HOST inputs
            (pinned frame + dets), H2D and the D2H of the result rows inside
            the timed region, one synchronisation per frame
-  roofline     : ReID forward (the dominant kernels) timed alone with CUDA
+  roofline     : ReID forward (``ssb_reid``, the dominant kernels) timed alone with CUDA
                  events; algorithmic flops 2*82.3e6*N per frame vs the measured
-                 bf16 peak in MEASURED_PEAKS.json
+                 bf16 peak in MEASURED_PEAKS.json; traffic = DRAM bytes of the same
+                 forward from the committed ncu --set full capture
   cpu_baseline : the CPU oracle (oracle/: NumPy/SciPy tracker + fp32 torch
                  OSNet; the reference's own StrongSORT code is absent) on the
                  host cores over a bounded sample of the same stream
+  clocks       : SM clock / throttle reasons polled through NVML during the timed region
 
+``--workload C4`` runs BASELINE.json's configs[3]; ``--shared-gallery`` adds config C5's
+per-frame cross-stream exchange (NCCL all-gather) to the timed region.
 ``--impl reference`` times that CPU oracle alone and prints the same line.
 """
 from __future__ import annotations
