@@ -58,7 +58,9 @@ enum {
     SSB_CNT_MATCHES_A = 4,  /* matches of the appearance stage          */
     SSB_CNT_MATCHES_B = 5,  /* matches of the IoU stage                 */
     SSB_CNT_NEW = 6,        /* tracks initiated this frame              */
-    SSB_CNT_ERROR = 7,      /* !=0: table overflow (tracks/dets dropped)*/
+    SSB_CNT_ERROR = 7,      /* bit 0: table overflow (tracks/dets dropped);
+                               bit 1: a tensor-core barrier wait of the ReID
+                               kernels timed out (embeddings invalid)   */
     SSB_CNT_N = 8
 };
 #define SSB_OUT_COLS 8 /* x1,y1,x2,y2,track_id,cls,conf,det_index(-1 if none) */
@@ -76,6 +78,11 @@ int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t workspace_byt
 int ssb_destroy(ssb_tracker *t);
 /* forget all tracks, ids restart at 1 */
 int ssb_reset(ssb_tracker *t, ssb_stream_t stream);
+
+/* StrongSORT.increment_ages() of upstream (SURVEY.md A.2 caller side: its stream loop calls it on
+ * frames WITHOUT detections instead of update()): every track  age += 1, time_since_update += 1,
+ * mark_missed(); no Kalman predict.  Tracks deleted here leave the list at the next ssb_update. */
+int ssb_increment_ages(ssb_tracker *t, ssb_stream_t stream);
 
 /* ---- ReID weights (OSNet-x0.25, BN folded by the host; see weights.py) --- */
 int ssb_reid_num_tensors(void);

@@ -160,7 +160,11 @@ def preprocess_crops(img, boxes):
     for x1, y1, x2, y2 in np.asarray(boxes).reshape(-1, 4):
         crop = np.ascontiguousarray(img[int(y1):int(y2), int(x1):int(x2)])
         if crop.shape[0] == 0 or crop.shape[1] == 0:
-            raise ValueError("degenerate crop (zero area): undefined upstream")
+            # zero-area crop: an upstream crash ("the kernel must define behaviour").
+            # Defined here and in stem_tc_kernel (csrc/reid_tc.cu, crop_ok): the network input is
+            # all zeros AFTER normalisation (i.e. the mean colour); the detection stays in the frame.
+            out.append(torch.zeros(1, 3, REID_H, REID_W))
+            continue
         t = torch.from_numpy(crop).permute(2, 0, 1).unsqueeze(0).to(torch.float32)
         t = F.interpolate(t, size=(REID_H, REID_W), mode="bilinear",
                           align_corners=False)

@@ -355,6 +355,15 @@ class Tracker:
         for track in self.tracks:
             track.predict()
 
+    def increment_ages(self):
+        """Upstream Tracker.increment_ages (its stream loop calls StrongSORT.increment_ages() on frames
+        without detections, SURVEY A.2 caller side): age and time_since_update advance and every
+        track is marked missed; no Kalman predict.  Deleted tracks stay listed until the next update()."""
+        for track in self.tracks:
+            track.age += 1
+            track.time_since_update += 1
+            track.mark_missed()
+
     def camera_update(self, warp_matrix):
         """One warp per frame applied to every track (upstream estimates the same ECC warp once
         per track)."""
@@ -530,6 +539,9 @@ class StrongSORTOracle:
         if len(outputs) > 0:
             return np.stack(outputs, axis=0)
         return np.zeros((0, 7), dtype=np.float64)
+
+    def increment_ages(self):
+        self.tracker.increment_ages()
 
     # introspection used by the parity tests ------------------------------
     def track_table(self):

@@ -18,7 +18,7 @@ SYMBOLS = [
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
-    "ssb_gallery_export", "ssb_gallery_cross_match",
+    "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_increment_ages",
 ]
 
 SSB_CNT_N = 8
@@ -61,6 +61,7 @@ def load():
     lib.ssb_create.argtypes = [C.POINTER(SsbConfig), vp, i64, C.POINTER(vp)]
     lib.ssb_destroy.argtypes = [vp]
     lib.ssb_reset.argtypes = [vp, vp]
+    lib.ssb_increment_ages.argtypes = [vp, vp]
     lib.ssb_reid_num_tensors.restype = i32
     lib.ssb_reid_tensor_sizes.argtypes = [C.POINTER(i64)]
     lib.ssb_reid_set_weights.argtypes = [vp, vp, C.POINTER(i64), i32]

@@ -22,6 +22,36 @@ void ssb_set_error(const char *fmt, ...) {
 }
 
 extern "C" const char *ssb_last_error(void) { return g_err; }
+
+// ---- per-device one-time guards (see ssb_common.cuh) ---------------------------------------
+#include <mutex>
+static std::mutex g_dev_mu;
+static int g_next_key = 0;
+static unsigned char g_dev_done[64][256];
+static int g_dev_sms[64];
+int ssb_new_key() {
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    return g_next_key < 255 ? g_next_key++ : 255;
+}
+bool ssb_first_on_device(int key) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || key < 0 || key >= 255) return true;      // out of table: always (re)apply
+    std::lock_guard<std::mutex> lk(g_dev_mu);
+    if (g_dev_done[dev][key]) return false;
+    g_dev_done[dev][key] = 1;
+    return true;
+}
+int ssb_num_sms() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && g_dev_sms[dev] > 0) return g_dev_sms[dev];
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+    if (dev >= 0 && dev < 64) g_dev_sms[dev] = n;
+    return n;
+}
 long long g_ssb_launches = 0;
 extern "C" int ssb_version(void) { return 100; }
 extern "C" int64_t ssb_launch_count(void) { return (int64_t)g_ssb_launches; }

@@ -12,6 +12,9 @@
 #include "ssb_common.cuh"
 
 #define NMS_MAX_WH 7680.0f
+// ultralytics keeps at most max_nms = 30000 candidates (highest scores) before torchvision.ops.nms;
+// the suppression matrix and its grids are sized by min(A, NMS_MAX_CAND)
+#define NMS_MAX_CAND 30000
 
 struct NmsScratch {
     float *conf;        // [A]
@@ -37,8 +40,9 @@ static size_t nms_carve(char *base, int A, NmsScratch *s) {
     t.sbox = (float *)take((size_t)A * 16);
     t.sarea = (float *)take((size_t)A * 4);
     t.count = (int *)take(64);
-    const size_t words = ((size_t)A + 63) / 64;
-    t.mask = (unsigned long long *)take((size_t)A * words * 8);
+    const size_t Mc = A < NMS_MAX_CAND ? A : NMS_MAX_CAND;
+    const size_t words = (Mc + 63) / 64;
+    t.mask = (unsigned long long *)take(Mc * words * 8);
     if (s) *s = t;
     return off;
 }
@@ -108,6 +112,7 @@ __global__ void nms_rank_kernel(const float *__restrict__ pred, int A, int agnos
         const float sj = s.conf[s.cand[j]];
         rank += (sj > sc) || (sj == sc && j < k);
     }
+    if (rank >= NMS_MAX_CAND) return;        // beyond max_nms: never a candidate
     s.order[rank] = k;
     // xywh -> xyxy (float32), then the class offset
     const float x = pred[a], y = pred[(size_t)A + a];
@@ -121,7 +126,7 @@ __global__ void nms_rank_kernel(const float *__restrict__ pred, int A, int agnos
 
 // suppression bit matrix over score-sorted boxes: bit (i, j) = IoU(i, j) > thr, j > i
 __global__ void nms_mask_kernel(float iou_thres, NmsScratch s) {
-    const int M = s.count[0];
+    const int M = min(s.count[0], NMS_MAX_CAND);
     const int words = (M + 63) / 64;
     const int i = blockIdx.y * blockDim.y + threadIdx.y;
     const int wj = blockIdx.x * blockDim.x + threadIdx.x;
@@ -152,7 +157,7 @@ nms_scan_kernel(const float *__restrict__ pred, int nc, int n_extra, int A, int 
     extern __shared__ unsigned long long s_removed[];
     __shared__ int s_keep_n;
     __shared__ int s_cur_keep;
-    const int M = s.count[0];
+    const int M = min(s.count[0], NMS_MAX_CAND);
     const int words = (M + 63) / 64;
     for (int w = threadIdx.x; w < words; w += blockDim.x) s_removed[w] = 0ull;
     if (threadIdx.x == 0) s_keep_n = 0;
@@ -201,8 +206,9 @@ extern "C" int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extr
     // the candidate count lives on the device: grids are sized for the worst case
     nms_rank_kernel<<<(A + 127) / 128, 128, 0, st>>>(pred_dev, A, agnostic, s);
     SSB_CHECK_LAUNCH();
-    const int words = (A + 63) / 64;
-    dim3 mb(32, 8), mg((words + 31) / 32, (A + 7) / 8);
+    const int Mc = A < NMS_MAX_CAND ? A : NMS_MAX_CAND;
+    const int words = (Mc + 63) / 64;
+    dim3 mb(32, 8), mg((words + 31) / 32, (Mc + 7) / 8);
     nms_mask_kernel<<<mg, mb, 0, st>>>(iou_thres, s);
     SSB_CHECK_LAUNCH();
     nms_scan_kernel<<<1, 256, (size_t)words * 8, st>>>(pred_dev, num_classes, num_extra, A, max_det, s, out_dev, count_dev);

@@ -350,7 +350,6 @@ fc_kernel(const float *__restrict__ v, const float *__restrict__ wts, const floa
 // ---------------------------------------------------------------------------
 // host orchestration
 // ---------------------------------------------------------------------------
-static bool g_pw_attr_done = false;
 
 template <int CG>
 static int launch_pw_t(const float *in, int P, int cin, const float *w, const float *b,
@@ -362,7 +361,8 @@ static int launch_pw_t(const float *in, int P, int cin, const float *w, const fl
 }
 
 static int reid_init_attrs() {
-    if (!g_pw_attr_done) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key)) {
         const int big = 128 * 1024;
         SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_conv_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
@@ -371,7 +371,6 @@ static int reid_init_attrs() {
         SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_conv_kernel<24>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_conv_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, big));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(reid_stem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-        g_pw_attr_done = true;
     }
     return 0;
 }
@@ -561,6 +560,7 @@ extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, con
     }
     if (((uintptr_t)blob_dev & 127) != 0) { ssb_set_error("tc blob must be 128-byte aligned"); return -1; }
     t->w_tc = (const unsigned char *)blob_dev;
+    SSB_CHECK_CUDA(cudaMemset(t->tc_status, 0, 64 * sizeof(int)));      // the workspace arrives uninitialised
     t->have_tc3 = n_blocks == 16;
     t->use_tc = t->have_tc3 ? 2 : 1;
     return 0;

@@ -656,11 +656,9 @@ using Blk5 = BlkCfg<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1>;
 template <class C>
 int launch_block(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,
                  cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(osblock_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-        attr = true;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n * C::NB);
     cfg.blockDim = dim3(OSB_THREADS);
@@ -1170,11 +1168,9 @@ using PwT2 = PwCfg<96, 96, 32, 16, true>;     // after conv3: 32x16x96 -> 16x8x9
 
 template <class C>
 int launch_pw_tc(const float *x, float *y, const unsigned char *w, int n, int *status, int sms, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-        attr = true;
-    }
     constexpr int HO = C::POOL ? C::H / 2 : C::H, WO = C::POOL ? C::W / 2 : C::W;
     const long long total = (long long)n * HO * WO;
     const int per = C::POOL ? 32 : 128;
@@ -1216,16 +1212,7 @@ int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, i
     return -1;
 }
 
-static int g_sms = 0;
-static int num_sms() {
-    if (!g_sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sms, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sms <= 0) g_sms = 148;
-    }
-    return g_sms;
-}
+static int num_sms() { return ssb_num_sms(); }
 
 // which: 0 = transition after conv2, 1 = transition after conv3, 2 = tail (conv5+GAP+fc)
 int64_t ssb_reid_tc_aux_bytes(int which) {
@@ -1240,11 +1227,9 @@ int64_t ssb_reid_tc_aux_bytes(int which) {
 
 int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *boxes, const unsigned char *wsec,
                      float *out, int n, int *status, cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
-        attr = true;
-    }
     stem_tc_kernel<<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
     SSB_CHECK_LAUNCH();
     return 0;
@@ -1256,11 +1241,9 @@ int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w,
         case 0: return launch_pw_tc<PwT1>(x, y, w, n, status, num_sms(), st);
         case 1: return launch_pw_tc<PwT2>(x, y, w, n, status, num_sms(), st);
         case 2: {
-            static bool attr = false;
-            if (!attr) {
+            static const int key = ssb_new_key();
+            if (ssb_first_on_device(key))
                 SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
-                attr = true;
-            }
             tail_tc_kernel<<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
             SSB_CHECK_LAUNCH();
             return 0;

@@ -736,11 +736,9 @@ using K5 = B3<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1, 7>;
 template <class C>
 int launch3(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,
             cudaStream_t st) {
-    static bool attr = false;
-    if (!attr) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(osblock3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
-        attr = true;
-    }
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(n * C::NB);
     cfg.blockDim = dim3(K3_THREADS);

@@ -107,6 +107,13 @@ struct ssb_tracker {
 };
 
 void ssb_set_error(const char *fmt, ...);
+// cudaFuncSetAttribute opt-ins (and cached device properties) are PER DEVICE: a guard must fire once per
+// (device, kernel), not once per process.  ssb_new_key() hands out a key per call site (use a function-local
+// static so each template instantiation gets its own); ssb_first_on_device(key) is true exactly once per
+// (current device, key).  Both are thread-safe.
+int ssb_new_key();
+bool ssb_first_on_device(int key);
+int ssb_num_sms();      // SM count of the current device (cached per device)
 #define SSB_CHECK_CUDA(expr)                                                        \
     do {                                                                            \
         cudaError_t _e = (expr);                                                    \

@@ -68,11 +68,9 @@ extern "C" int ssb_tc_probe(const void *a_dev, int a_rows, int shift, const void
         return -1;
     }
     const size_t smem = (size_t)(k / 8) * (a_rows + n) * 16 + 256;
-    static bool attr = false;
-    if (!attr) {
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(tc_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
     if (smem > 200 * 1024) { ssb_set_error("tc_probe: operands exceed shared memory"); return -1; }
     tc_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __half *)a_dev, a_rows, shift,
                                                             (const __half *)b_dev, n, k, d_dev, status_dev);

@@ -999,7 +999,7 @@ __global__ void update_matched_kernel(TrackTable tt, FrameScratch fs, SsbDims d)
 // Single block; the per-new-track feature copies use all warps.
 // ---------------------------------------------------------------------------
 __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H, int W,
-                                double *out, int *counts) {
+                                double *out, int *counts, const int *tc_status) {
     __shared__ int s_w[33];
     __shared__ int s_nnew;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5, nw = blockDim.x >> 5;
@@ -1117,8 +1117,25 @@ __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H
         counts[SSB_CNT_MATCHES_A] = fs.cnt[FC_N_MATCH_A];
         counts[SSB_CNT_MATCHES_B] = fs.cnt[FC_N_MATCH] - fs.cnt[FC_N_MATCH_A];
         counts[SSB_CNT_NEW] = n_new;
-        counts[SSB_CNT_ERROR] = tt.scalars[SC_ERROR];
+        // bit 0: table overflow; bit 1: a tensor-core barrier wait of the ReID kernels timed out
+        // (their device status word) -- the embeddings of this frame cannot be trusted
+        counts[SSB_CNT_ERROR] = (tt.scalars[SC_ERROR] ? 1 : 0) | ((tc_status && *tc_status) ? 2 : 0);
     }
+}
+
+// StrongSORT.increment_ages() of upstream (called by its stream loop on frames WITHOUT detections):
+// for every track  age += 1, time_since_update += 1, mark_missed()  -- no Kalman predict.  Tracks
+// deleted here stay in the list until the next update() drops them (upstream filters the list only at
+// the end of Tracker.update); until then they sit among the unconfirmed tracks, exactly as upstream.
+__global__ void increment_ages_kernel(TrackTable tt, SsbDims d) {
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= tt.scalars[SC_N_TRACKS]) return;
+    const int s = tt.order[p];
+    tt.age[s] += 1;
+    const int tsu = tt.tsu[s] + 1;
+    tt.tsu[s] = tsu;
+    if (tt.state[s] == SSB_TENTATIVE) tt.state[s] = SSB_DELETED;
+    else if (tsu > d.max_age) tt.state[s] = SSB_DELETED;
 }
 
 // gallery partial_fit (A.5/A.6): every confirmed track appends its current
@@ -1176,19 +1193,23 @@ __global__ void export_tracks_kernel(TrackTable tt, SsbDims d, int *ids, int *st
 // ---------------------------------------------------------------------------
 // host-side launchers
 // ---------------------------------------------------------------------------
-static int g_lsap_smem_limit = 0;   // bytes of dynamic smem opted in
+static int g_lsap_smem_limit_dev[64];   // bytes of dynamic smem opted in, per device
 
 static int lsap_prepare(int L, size_t *dyn_bytes, size_t *cost_bytes) {
-    if (!g_lsap_smem_limit) {
-        int dev = 0, maxopt = 0;
-        SSB_CHECK_CUDA(cudaGetDevice(&dev));
+    int dev = 0;
+    SSB_CHECK_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) { ssb_set_error("device index %d out of range", dev); return -3; }
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key) || !g_lsap_smem_limit_dev[dev]) {
+        int maxopt = 0;
         SSB_CHECK_CUDA(cudaDeviceGetAttribute(&maxopt, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         int want = maxopt - 2048;
         SSB_CHECK_CUDA(cudaFuncSetAttribute(lsap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(assign_stage_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(assign_stage_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, want));
-        g_lsap_smem_limit = want;
+        g_lsap_smem_limit_dev[dev] = want;
     }
+    const int g_lsap_smem_limit = g_lsap_smem_limit_dev[dev];
     size_t fixed = (size_t)L * (3 * 8 + 4 * 4 + 2) + 64;
     if (fixed + 1024 > (size_t)g_lsap_smem_limit) {
         ssb_set_error("LSAP dimension %d exceeds shared memory", L);
@@ -1250,7 +1271,7 @@ int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const 
         update_matched_kernel<<<max_match, 128, 0, st>>>(tt, fs, d);
         SSB_CHECK_LAUNCH();
     }
-    bookkeep_kernel<<<1, 256, 0, st>>>(tt, fs, d, h, w, out, counts);
+    bookkeep_kernel<<<1, 256, 0, st>>>(tt, fs, d, h, w, out, counts, t->tc_status);
     SSB_CHECK_LAUNCH();
     int Tafter = Tmax + n;
     if (Tafter > d.S) Tafter = d.S;
@@ -1343,6 +1364,14 @@ extern "C" int ssb_lsap(const double *cost_dev, int nr, int nc, int32_t *col4row
 
 int ssb_launch_reset(ssb_tracker *t, cudaStream_t st) {
     reset_table_kernel<<<(t->dims.S + 127) / 128, 128, 0, st>>>(t->tt, t->dims);
+    SSB_CHECK_LAUNCH();
+    SSB_CHECK_CUDA(cudaMemsetAsync(t->tc_status, 0, 64 * sizeof(int), st));     // workspace memory is uninitialised
+    return 0;
+}
+
+extern "C" int ssb_increment_ages(ssb_tracker *t, ssb_stream_t stream) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    increment_ages_kernel<<<(t->dims.S + 127) / 128, 128, 0, (cudaStream_t)stream>>>(t->tt, t->dims);
     SSB_CHECK_LAUNCH();
     return 0;
 }

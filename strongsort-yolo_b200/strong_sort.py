@@ -136,7 +136,7 @@ class StrongSORT:
         self._track_hint = 0
 
     # ------------------------------------------------------------------
-    def _stage_image(self, img):
+    def _stage_image(self, img, caller=None):
         torch = self._torch
         if torch.is_tensor(img):
             if img.dtype != torch.uint8 or img.dim() != 3 or img.shape[2] != 3:
@@ -144,7 +144,8 @@ class StrongSORT:
             if img.is_cuda:
                 if img.device != self.device:
                     img = img.to(self.device)
-                self.stream.wait_stream(torch.cuda.current_stream(self.device))
+                if caller is not None:
+                    self._after_producer(img, self.stream, caller)
                 return img.contiguous()
             src = img.contiguous()
         else:
@@ -156,6 +157,28 @@ class StrongSORT:
             self._img_dev = torch.empty(tuple(src.shape), dtype=torch.uint8, device=self.device)
         self._img_dev.copy_(src, non_blocking=True)      # on self.stream (set by caller)
         return self._img_dev
+
+    def _after_producer(self, t, stream, caller):
+        """A CUDA tensor handed in by the caller may still be pending on the caller's stream (e.g.
+        YoloNMS output): order our stream after it and keep the allocator from recycling it.
+        ``caller`` is the stream that was current BEFORE our own stream context was entered."""
+        stream.wait_stream(caller)
+        t.record_stream(stream)
+
+    @staticmethod
+    def _raise_on_error(cnt):
+        err = int(cnt[CNT_ERROR])
+        if err & 2:
+            raise _lib.SsbError("a tensor-core barrier wait timed out inside the ReID kernels "
+                                "(device status word set): this frame's embeddings are invalid")
+        if err & 1:
+            raise _lib.SsbError("track table overflow: raise max_tracks / max_dets")
+
+    def increment_ages(self):
+        """Upstream ``StrongSORT.increment_ages()``: what its stream loop calls instead of ``update``
+        on a frame without detections (ages advance, tracks are marked missed, no Kalman predict)."""
+        _lib.check(self._lib.ssb_increment_ages(self._h, C.c_void_p(self.stream.cuda_stream)),
+                   "ssb_increment_ages")
 
     def update(self, dets, ori_img, features=None):
         """dets: [N,6] (x1,y1,x2,y2,conf,cls) torch CPU tensor / ndarray (or a
@@ -175,9 +198,11 @@ class StrongSORT:
             raise ValueError(f"{n} detections exceed max_dets={self.cfg.max_dets}")
         H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
         st = C.c_void_p(self.stream.cuda_stream)
+        caller = torch.cuda.current_stream(self.device)      # the stream the caller's tensors were produced on
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             if n:
                 if d.is_cuda:
+                    self._after_producer(d, self.stream, caller)
                     self._dets_dev[:n].copy_(d, non_blocking=True)
                 else:
                     self._dets_pin[:n].copy_(d)
@@ -186,10 +211,12 @@ class StrongSORT:
             img_dev = None
             if features is not None:
                 f = torch.as_tensor(features, dtype=torch.float32).reshape(n, self.cfg.feat_dim)
+                if f.is_cuda:
+                    self._after_producer(f, self.stream, caller)
                 self._feats_dev[:n].copy_(f, non_blocking=False)
                 feats_ptr = _lib.ptr(self._feats_dev)
             elif n:
-                img_dev = self._stage_image(ori_img)
+                img_dev = self._stage_image(ori_img, caller)
             pitch = 3 * W
             _lib.check(lib.ssb_update(
                 self._h, _lib.ptr(self._dets_dev), n,
@@ -200,8 +227,7 @@ class StrongSORT:
         self.stream.synchronize()
         cnt = self._counts_np
         self.last_counts = cnt.copy()
-        if cnt[CNT_ERROR]:
-            raise _lib.SsbError("track table overflow: raise max_tracks / max_dets")
+        self._raise_on_error(cnt)
         self._track_hint = int(cnt[CNT_TRACKS])
         m = int(cnt[CNT_OUT_ROWS])
         rows = self._rows_np[:m].copy()
@@ -233,8 +259,9 @@ class StrongSORT:
         b = torch.as_tensor(np.asarray(boxes_xyxy_int, dtype=np.int32).reshape(-1, 4))
         n = int(b.shape[0])
         H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
+        caller = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-            img_dev = self._stage_image(ori_img)
+            img_dev = self._stage_image(ori_img, caller)
             bd = b.to(self.device)
             out = torch.empty((n, self.cfg.feat_dim), dtype=torch.float32, device=self.device)
             _lib.check(self._lib.ssb_reid(self._h, _lib.ptr(img_dev), H, W, 3 * W, _lib.ptr(bd), n,
@@ -270,8 +297,7 @@ class StrongSORT:
         buf = self._p_pin[slot].numpy()
         cnt = buf[:32].view(np.int32)
         self.last_counts = cnt.copy()
-        if cnt[CNT_ERROR]:
-            raise _lib.SsbError("track table overflow: raise max_tracks / max_dets")
+        self._raise_on_error(cnt)
         self._track_hint = int(cnt[CNT_TRACKS])
         m = int(cnt[CNT_OUT_ROWS])
         rows = buf[_HDR_BYTES:].view(np.float64).reshape(-1, _lib.SSB_OUT_COLS)[:m].copy()
@@ -296,10 +322,12 @@ class StrongSORT:
             raise ValueError(f"{n} detections exceed max_dets={self.cfg.max_dets}")
         H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
         pst = self._pstreams[slot]
+        caller = torch.cuda.current_stream(self.device)
         with torch.cuda.device(self.device), torch.cuda.stream(pst):
             pst.wait_event(self._p_assoc_done[slot])                  # slot free (frame k-2 associated)
             if n:
                 if d.is_cuda:
+                    self._after_producer(d, pst, caller)
                     self._p_dets[slot][:n].copy_(d, non_blocking=True)
                 else:
                     self._p_dets_pin[slot][:n].copy_(d)
@@ -307,7 +335,7 @@ class StrongSORT:
             img_dev = None
             if n:
                 if torch.is_tensor(ori_img) and ori_img.is_cuda:
-                    pst.wait_stream(torch.cuda.current_stream(self.device))
+                    self._after_producer(ori_img, pst, caller)
                     img_dev = ori_img.contiguous()
                 else:
                     src = ori_img if torch.is_tensor(ori_img) else torch.from_numpy(np.ascontiguousarray(ori_img))

@@ -134,18 +134,109 @@ def test_c1_end_to_end_vs_golden_and_oracle(oracle_extractor, golden_dir):
 
 
 def test_c2_end_to_end_vs_oracle(oracle_extractor):
-    """Config C2 (1080p, 100 dets/frame), CUDA OSNet vs the fp32 oracle OSNet."""
+    """Config C2 (1080p, 100 dets/frame), CUDA OSNet vs the fp32 oracle OSNet, 60 frames: tracks are
+    long confirmed, galleries hold tens of real embeddings, drops / spurious detections create and
+    delete tentative tracks.  Rows bit-exact every frame, the table every 10 frames."""
     from strongsort_yolo_b200.strong_sort import StrongSORT
     st = synth.make_stream("C2")
     ora = ss.StrongSORTOracle(oracle_extractor)
     gpu = StrongSORT()
-    for f in range(12):
+    for f in range(60):
         fr = st.next_frame()
         want = ora.update(fr.dets, fr.img)
         got = gpu.update(fr.dets, fr.img)
         assert_rows_equal(got, want)
-    assert int(gpu.last_counts[3]) == ora.tracker._next_id
+        assert int(gpu.last_counts[3]) == ora.tracker._next_id, f"frame {f}: next id"
+        if f % 10 == 9:
+            assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-6, feat_tol=1e-3)
+    assert ora.track_table()["gallery_len"].max() >= 50
+
+
+def test_c2_end_to_end_occlusion_max_age5_vs_oracle(oracle_extractor):
+    """Real embeddings through the deletion / re-identification paths: max_age=5, a third of the
+    objects vanish for 10 frames (their tracks age out and are deleted, galleries dropped), then
+    return and get NEW ids; two frames without detections in between."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C2", n_persistent=60)
+    ora = ss.StrongSORTOracle(oracle_extractor, max_age=5)
+    gpu = StrongSORT(max_age=5)
+    for f in range(40):
+        fr = st.next_frame()
+        keep = np.ones(len(fr.dets), bool)
+        if 12 <= f < 22:
+            keep = fr.gt_ids % 3 != 0
+        if f in (28, 29):
+            keep[:] = False
+        d = fr.dets[keep]
+        want = ora.update(d, fr.img)
+        got = gpu.update(d, fr.img)
+        assert_rows_equal(got, want)
+        assert int(gpu.last_counts[3]) == ora.tracker._next_id, f"frame {f}: next id"
+        if f % 8 == 7:
+            assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-6, feat_tol=1e-3)
+    assert ora.tracker._next_id > 75          # the returning objects were re-issued ids
+
+
+def test_c4_end_to_end_vs_oracle(oracle_extractor):
+    """Config C4 (4K, 500 dets/frame, 256 persistent + 244 flickers) with the CUDA OSNet in the loop."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C4")
+    ora = ss.StrongSORTOracle(oracle_extractor)
+    gpu = StrongSORT(max_tracks=2048, max_dets=640)
+    for f in range(8):
+        fr = st.next_frame()
+        want = ora.update(fr.dets, fr.img)
+        got = gpu.update(fr.dets, fr.img)
+        assert_rows_equal(got, want)
+        assert int(gpu.last_counts[3]) == ora.tracker._next_id, f"frame {f}: next id"
     assert_tables_equal(gpu.export_tracks(), ora.track_table(), rtol=1e-6, feat_tol=1e-3)
+
+
+def test_increment_ages_matches_oracle():
+    """Upstream's stream loop calls increment_ages() instead of update() on frames without
+    detections: ages advance, tracks are marked missed, NO Kalman predict; deleted tracks leave the
+    list at the next update."""
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.SyntheticStream(width=1280, height=720, n_persistent=20, seed=5, render=False)
+    bank = FeatureBank(seed=11)
+    ora = ss.StrongSORTOracle(None, max_age=4)
+    gpu = StrongSORT(max_age=4, max_tracks=128, max_dets=64)
+    img = np.zeros((720, 1280, 3), dtype=np.uint8)
+    for f in range(40):
+        fr = st.next_frame()
+        if f in (2, 10, 11, 20, 21, 22, 23, 24, 25, 30):        # "no detections" frames (incl. > max_age in a row)
+            ora.increment_ages()
+            gpu.increment_ages()
+        else:
+            feats = bank(fr.gt_ids)
+            want = ora.update(fr.dets, img, features=feats)
+            got = gpu.update(fr.dets, img, features=feats)
+            assert_rows_equal(got, want)
+        gpu.stream.synchronize()
+        gpu._track_hint = len(ora.tracker.tracks)     # export_tracks sizes its view from the hint
+        assert_tables_equal(gpu.export_tracks(), ora.track_table())
+    assert ora.tracker._next_id > 21
+
+
+def test_update_accepts_cuda_tensors_from_another_stream():
+    """dets / img / features produced on the caller's stream are ordered before the tracker's
+    private stream (the copy used to race the producer)."""
+    import torch
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1")
+    frames = [st.next_frame() for _ in range(6)]
+    a = StrongSORT(max_tracks=64, max_dets=32)
+    want = [a.update(f.dets, f.img) for f in frames]
+    b = StrongSORT(max_tracks=64, max_dets=32)
+    side = torch.cuda.Stream()
+    big = torch.empty(64 << 20, dtype=torch.uint8, device="cuda")
+    for f, w in zip(frames, want):
+        with torch.cuda.stream(side):
+            big.fill_(1)                                    # keeps `side` busy before the producers
+            d = torch.from_numpy(f.dets).cuda(non_blocking=True) + 0.0
+            im = torch.from_numpy(f.img).cuda(non_blocking=True).clone()
+            got = b.update(d, im)
+        np.testing.assert_array_equal(got, w)
 
 
 def test_pipelined_update_equals_synchronous():
