@@ -477,9 +477,34 @@ static int reid_block(ssb_tracker *t, int b, const float *cur, float *nxt, int n
     return reid_block_simt(t, b, cur, nxt, n, Hc, Wc, B, st);
 }
 
+// mode 3 (default): every activation between kernels is a pair of fp16 operand planes (reid_tc4.cu):
+// stem -> K0 -> K1 -> transition -> K2 -> K3 -> transition -> K4 -> K5 -> tail, 11 launches
+static int reid_forward_planes(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+                               int n, float *feats_out, cudaStream_t st) {
+    float *A, *Bf;
+    (void)reid_bufs(t, slot, n, &A, &Bf);
+    const unsigned char *W = t->w_tc;
+    int rc = ssb_reid_tc_stem(img, h, w, pitch, boxes, W + t->w_tc_off[9], A, n, t->tc_status, st, 1);
+    if (rc) return rc;
+    float *cur = A, *nxt = Bf;
+    for (int b = 0; b < 6; b++) {
+        rc = ssb_reid_tc4_block(b, cur, nxt, W + t->w_tc_off[10 + b], n, t->tc_status, st);
+        if (rc) return rc;
+        { float *tmp = cur; cur = nxt; nxt = tmp; }
+        if (b == 1 || b == 3) {
+            const int a = b == 1 ? 0 : 1;
+            rc = ssb_reid_tc_aux(a, cur, nxt, W + t->w_tc_off[6 + a], n, t->tc_status, st, 1);
+            if (rc) return rc;
+            { float *tmp = cur; cur = nxt; nxt = tmp; }
+        }
+    }
+    return ssb_reid_tc_aux(2, cur, feats_out, W + t->w_tc_off[8], n, t->tc_status, st, 1);
+}
+
 int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
                      int n, float *feats_out, cudaStream_t st) {
     if (n <= 0) return 0;
+    if (t->use_tc == 3) return reid_forward_planes(t, slot, img, h, w, pitch, boxes, n, feats_out, st);
     { int rc = reid_init_attrs(); if (rc) return rc; }
     const float *W = t->w_blob;
     const int64_t *off = t->w_off;
@@ -562,15 +587,15 @@ extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, con
     t->w_tc = (const unsigned char *)blob_dev;
     SSB_CHECK_CUDA(cudaMemset(t->tc_status, 0, 64 * sizeof(int)));      // the workspace arrives uninitialised
     t->have_tc3 = n_blocks == 16;
-    t->use_tc = t->have_tc3 ? 2 : 1;
+    t->use_tc = t->have_tc3 ? 3 : 1;
     return 0;
 }
 
 extern "C" int ssb_reid_use_tc(ssb_tracker *t, int enable) {
     if (!t) { ssb_set_error("null handle"); return -1; }
     if (enable && !t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
-    if (enable < 0 || enable > 2) { ssb_set_error("ReID mode must be 0 (simt), 1 (tc, 9-tap) or 2 (tc, pointwise + depthwise)"); return -1; }
-    if (enable == 2 && !t->have_tc3) { ssb_set_error("pointwise/depthwise tensor-core weights (sections 10..15) not set"); return -1; }
+    if (enable < 0 || enable > 3) { ssb_set_error("ReID mode must be 0 (simt), 1 (tc, 9-tap), 2 (tc, pointwise + depthwise) or 3 (operand planes + halo exchange)"); return -1; }
+    if (enable >= 2 && !t->have_tc3) { ssb_set_error("pointwise/depthwise tensor-core weights (sections 10..15) not set"); return -1; }
     t->use_tc = enable;
     return 0;
 }
@@ -586,6 +611,16 @@ extern "C" int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, flo
     float *A, *Bf;
     const ReidBufs B = reid_bufs(t, 0, n, &A, &Bf);
     const int Hc = block < 2 ? 64 : (block < 4 ? 32 : 16), Wc = Hc / 2;
+    if (use_tc == 3) {          // operand-plane kernels: convert in, run, convert out
+        if (!t->w_tc || !t->have_tc3) { ssb_set_error("pointwise/depthwise tensor-core weights (sections 10..15) not set"); return -1; }
+        cudaStream_t st = (cudaStream_t)stream;
+        const int cin = kBlocks[block][0], cout = kBlocks[block][1];
+        int rc = ssb_reid_nhwc_to_planes(x_dev, A, n, Hc * Wc, cin, st);
+        if (rc) return rc;
+        rc = ssb_reid_tc4_block(block, A, Bf, t->w_tc + t->w_tc_off[10 + block], n, t->tc_status, st);
+        if (rc) return rc;
+        return ssb_reid_planes_to_nhwc(Bf, y_dev, n, Hc * Wc, cout, st);
+    }
     return reid_block(t, block, x_dev, y_dev, n, Hc, Wc, B, use_tc, (cudaStream_t)stream);
 }
 

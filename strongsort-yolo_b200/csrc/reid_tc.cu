@@ -700,7 +700,9 @@ struct PwCfg {
     static_assert(2 * COUT <= 512, "TMEM columns");
 };
 
-template <class C>
+// PLANES: input and output are hi/lo fp16 operand planes [crop][hl][C/8][H*W][8] (reid_tc4.cu) instead of
+// float32 NHWC: staging is a plain 16-byte copy (no split), the epilogue writes operand rows directly.
+template <class C, bool PLANES>
 __global__ void __launch_bounds__(OSB_THREADS, 1)
 pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
              const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status) {
@@ -717,7 +719,8 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     const long long total_out = (long long)n_crops * HO * WO;
     const int ntiles = (int)((total_out + OUT_PER_TILE - 1) / OUT_PER_TILE);
 
-    if (warp == 0) tc::tmem_alloc(s_tmem, 512);
+    constexpr int PW_TM = 2 * C::COUT <= 128 ? 128 : 256;     // two accumulator buffers
+    if (warp == 0) tc::tmem_alloc(s_tmem, PW_TM);
     if (tid == 0) {
         tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::mbar_init(bar + 2, 1);
         tc::fence_mbar_init();
@@ -756,11 +759,25 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
                 }
                 v[j] = f;
             }
-            if (wr) {
+            if (wr && !PLANES) {
                 float *dst = y + o * C::COUT + c0;
 #pragma unroll
                 for (int j = 0; j < 16; j += 4)
                     *reinterpret_cast<float4 *>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (wr && PLANES) {
+                const int n = (int)(o / (HO * WO)), pix = (int)(o - (long long)n * HO * WO);
+                unsigned char *yb = reinterpret_cast<unsigned char *>(y) + (size_t)n * (4 * C::COUT * HO * WO);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    __align__(16) __half2 h[4];
+                    __align__(16) __half2 l[4];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) split_hl2(v[j * 8 + q], v[j * 8 + q + 1], h[q >> 1], l[q >> 1]);
+                    unsigned char *dst = yb + (size_t)(c0 / 8 + j) * (HO * WO) * 16 + (size_t)pix * 16;
+                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+                    *reinterpret_cast<uint4 *>(dst + 2 * C::COUT * HO * WO) = *reinterpret_cast<uint4 *>(l);
+                }
             }
         }
         tc::fence_before_sync();
@@ -771,8 +788,40 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
         const int buf = it & 1;
         unsigned char *stg = sStg + buf * C::STG_B;
         constexpr int F4 = C::CIN / 4;
+        if (PLANES) {
+            // one 16-byte operand row per item: (hl, chunk) plane x tile row m; the row's pixel is the same
+            // for all planes, so consecutive m of a warp read 32-byte window pairs of one plane
+            constexpr int XCH = C::CIN / 8;
+            const unsigned char *xb = reinterpret_cast<const unsigned char *>(x);
+#pragma unroll 4
+            for (int idx = tid; idx < 128 * 2 * XCH; idx += OSB_THREADS) {
+                const int m = idx & 127, c2 = idx >> 7;
+                const int hl = c2 / XCH, ch = c2 - hl * XCH;
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                long long o;
+                int ipx;
+                if (C::POOL) {
+                    o = (long long)tile * 32 + (m >> 2);
+                    const int q = m & 3;
+                    const int n = (int)(o / (HO * WO)), rem = (int)(o - (long long)n * HO * WO);
+                    const int oy = rem / WO, ox = rem - oy * WO;
+                    ipx = (2 * oy + (q >> 1)) * C::W + 2 * ox + (q & 1);
+                    if (o < total_out)
+                        v = *reinterpret_cast<const uint4 *>(xb + (size_t)n * (4 * C::CIN * C::H * C::W) + (size_t)hl * (2 * C::CIN * C::H * C::W) +
+                                                             (size_t)ch * (C::H * C::W) * 16 + (size_t)ipx * 16);
+                } else {
+                    o = (long long)tile * 128 + m;
+                    const int n = (int)(o / (C::H * C::W));
+                    ipx = (int)(o - (long long)n * C::H * C::W);
+                    if (o < total_out)
+                        v = *reinterpret_cast<const uint4 *>(xb + (size_t)n * (4 * C::CIN * C::H * C::W) + (size_t)hl * (2 * C::CIN * C::H * C::W) +
+                                                             (size_t)ch * (C::H * C::W) * 16 + (size_t)ipx * 16);
+                }
+                *reinterpret_cast<uint4 *>(stg + hl * C::STG_HALF_B + ch * 2048 + m * 16) = v;
+            }
+        }
 #pragma unroll 2
-        for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
+        for (int idx = tid; idx < (PLANES ? 0 : 128 * F4); idx += OSB_THREADS) {
             const int m = idx / F4, f4 = idx - m * F4;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (C::POOL) {
@@ -824,7 +873,7 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     if (!ok && tid == 0) atomicExch(status, 2);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, PW_TM);
 }
 
 // ---------------------------------------------------------------------------
@@ -843,6 +892,7 @@ struct TailCfg {
     static constexpr int G_TOTAL = G_FCB + 512 * 4;
 };
 
+template <bool PLANES>
 __global__ void __launch_bounds__(OSB_THREADS, 1)
 tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
                const unsigned char *__restrict__ wblob, int *__restrict__ status) {
@@ -864,13 +914,20 @@ tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
     if (tid == 0) {
-        tc::mbar_arrive_expect_tx(bar + 1, C::W_B);
-        tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 1);
+        // PLANES: a crop's operand planes [hl][16 chunks][128 px][8] ARE the staging layout: two 32 KB bulk copies
+        tc::mbar_arrive_expect_tx(bar + 1, C::W_B + (PLANES ? C::STG_B : 0));
+        tc::bulk_g2s(sW, wblob + C::G_W, C::W_B / 2, bar + 1);
+        tc::bulk_g2s(sW + C::W_B / 2, wblob + C::G_W + C::W_B / 2, C::W_B / 2, bar + 1);
+        if (PLANES) {
+            const unsigned char *xb = reinterpret_cast<const unsigned char *>(x) + (size_t)crop * C::STG_B;
+            tc::bulk_g2s(stg, xb, C::STG_HALF_B, bar + 1);
+            tc::bulk_g2s(stg + C::STG_HALF_B, xb + C::STG_HALF_B, C::STG_HALF_B, bar + 1);
+        }
     }
     const float *xin = x + (size_t)crop * C::PX * C::CIN;
     constexpr int F4 = C::CIN / 4;
 #pragma unroll 4
-    for (int idx = tid; idx < 128 * F4; idx += OSB_THREADS) {
+    for (int idx = tid; idx < (PLANES ? 0 : 128 * F4); idx += OSB_THREADS) {
         const int m = idx / F4, f4 = idx - m * F4;
         const float4 v = *reinterpret_cast<const float4 *>(xin + (size_t)m * C::CIN + f4 * 4);
         __align__(8) __half2 h[2], l[2];
@@ -957,7 +1014,9 @@ struct StemCfg {
     static constexpr int PLANE_B = MAP_PX * 16;
     static constexpr int MAP_HALF_B = 2 * PLANE_B, MAP_B = 2 * MAP_HALF_B;
     static constexpr int W_HALF_B = 16 * 16 * 16 * 2, W_B = 2 * W_HALF_B;     // [tap][2][16][8]
-    static constexpr int CONV_B = CROWS * 64 * 16 * 4;
+    static constexpr int CP = 20;                   // floats per conv pixel in sConv (16 + 4 pad: the pooling stage's
+                                                    // stride-2 column walk then touches distinct banks)
+    static constexpr int CONV_B = CROWS * 64 * CP * 4;
     static constexpr int OFF_MAP = 0, OFF_W = MAP_B, OFF_CONV = OFF_W + W_B;
     static constexpr int OFF_BIAS = OFF_CONV + CONV_B, OFF_MISC = OFF_BIAS + 64;
     static constexpr int SMEM_B = OFF_MISC + 64;
@@ -966,6 +1025,7 @@ struct StemCfg {
     static_assert(SMEM_B <= 232448, "shared memory");
 };
 
+template <bool PLANES>
 __global__ void __launch_bounds__(OSB_THREADS, 1)
 stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const int *__restrict__ boxes,
                const unsigned char *__restrict__ wblob, float *__restrict__ out, int *__restrict__ status,
@@ -1123,7 +1183,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
         if (lcy < C::CROWS && cx < 64) {
             const int gcy = cy0 + lcy;
             const bool inside = gcy >= 0 && gcy < 128;
-            float *o = sConv + ((size_t)lcy * 64 + cx) * 16;
+            float *o = sConv + ((size_t)lcy * 64 + cx) * C::CP;
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
                 float4 r;
@@ -1138,8 +1198,36 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     tc::fence_before_sync();
     __syncthreads();
     stamp();                                   // conv drained
-    // ---- maxpool 3x3 s2 p1 -> out[crop][py][px][16]
-    for (int o = tid; o < C::PR * 32 * 4; o += OSB_THREADS) {
+    // ---- maxpool 3x3 s2 p1 -> operand planes [crop][hl][2 chunks][64*32 px][8] (PLANES) ...
+    if (PLANES) {
+        unsigned char *ob = reinterpret_cast<unsigned char *>(out) + (size_t)crop * (4 * 16 * 2048);
+        for (int o = tid; o < C::PR * 32 * 2; o += OSB_THREADS) {
+            const int px = o & 31, ch = (o >> 5) & 1, pr = o >> 6;
+            float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                const int lcy = 2 * pr + dy;
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    const int cx = 2 * px - 1 + dx;
+                    if (cx < 0 || cx >= 64) continue;
+                    const float *src = sConv + ((size_t)lcy * 64 + cx) * C::CP + ch * 8;
+                    const float4 v0 = *reinterpret_cast<const float4 *>(src), v1 = *reinterpret_cast<const float4 *>(src + 4);
+                    m0.x = fmaxf(m0.x, v0.x); m0.y = fmaxf(m0.y, v0.y); m0.z = fmaxf(m0.z, v0.z); m0.w = fmaxf(m0.w, v0.w);
+                    m1.x = fmaxf(m1.x, v1.x); m1.y = fmaxf(m1.y, v1.y); m1.z = fmaxf(m1.z, v1.z); m1.w = fmaxf(m1.w, v1.w);
+                }
+            }
+            __align__(16) __half2 h[4];
+            __align__(16) __half2 l[4];
+            split_hl2(m0.x, m0.y, h[0], l[0]); split_hl2(m0.z, m0.w, h[1], l[1]);
+            split_hl2(m1.x, m1.y, h[2], l[2]); split_hl2(m1.z, m1.w, h[3], l[3]);
+            unsigned char *dst = ob + (size_t)ch * 2048 * 16 + (size_t)((py0 + pr) * 32 + px) * 16;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+            *reinterpret_cast<uint4 *>(dst + 2 * 16 * 2048) = *reinterpret_cast<uint4 *>(l);
+        }
+    }
+    // ... or float32 out[crop][py][px][16]
+    for (int o = tid; o < (PLANES ? 0 : C::PR * 32 * 4); o += OSB_THREADS) {
         const int c4 = o & 3, px = (o >> 2) & 31, pr = o >> 7;
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
@@ -1149,7 +1237,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
             for (int dx = 0; dx < 3; dx++) {
                 const int cx = 2 * px - 1 + dx;
                 if (cx < 0 || cx >= 64) continue;
-                const float4 v = *reinterpret_cast<const float4 *>(sConv + ((size_t)lcy * 64 + cx) * 16 + c4 * 4);
+                const float4 v = *reinterpret_cast<const float4 *>(sConv + ((size_t)lcy * 64 + cx) * C::CP + c4 * 4);
                 m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
             }
         }
@@ -1166,17 +1254,17 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
 using PwT1 = PwCfg<64, 64, 64, 32, true>;     // after conv2: 64x32x64 -> 32x16x64
 using PwT2 = PwCfg<96, 96, 32, 16, true>;     // after conv3: 32x16x96 -> 16x8x96
 
-template <class C>
+template <class C, bool PLANES>
 int launch_pw_tc(const float *x, float *y, const unsigned char *w, int n, int *status, int sms, cudaStream_t st) {
     static const int key = ssb_new_key();
     if (ssb_first_on_device(key))
-        SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_tc_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(pw_tc_kernel<C, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
     constexpr int HO = C::POOL ? C::H / 2 : C::H, WO = C::POOL ? C::W / 2 : C::W;
     const long long total = (long long)n * HO * WO;
     const int per = C::POOL ? 32 : 128;
     int tiles = (int)((total + per - 1) / per);
     int grid = tiles < sms ? tiles : sms;
-    pw_tc_kernel<C><<<grid, OSB_THREADS, C::SMEM_B, st>>>(x, y, w, n, status);
+    pw_tc_kernel<C, PLANES><<<grid, OSB_THREADS, C::SMEM_B, st>>>(x, y, w, n, status);
     SSB_CHECK_LAUNCH();
     return 0;
 }
@@ -1226,25 +1314,35 @@ int64_t ssb_reid_tc_aux_bytes(int which) {
 }
 
 int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *boxes, const unsigned char *wsec,
-                     float *out, int n, int *status, cudaStream_t st) {
+                     float *out, int n, int *status, cudaStream_t st, int planes) {
     static const int key = ssb_new_key();
-    if (ssb_first_on_device(key))
-        SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
-    stem_tc_kernel<<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
+    if (ssb_first_on_device(key)) {
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
+    }
+    if (planes)
+        stem_tc_kernel<true><<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
+    else
+        stem_tc_kernel<false><<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
     SSB_CHECK_LAUNCH();
     return 0;
 }
 
 int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w, int n, int *status,
-                    cudaStream_t st) {
+                    cudaStream_t st, int planes) {
     switch (which) {
-        case 0: return launch_pw_tc<PwT1>(x, y, w, n, status, num_sms(), st);
-        case 1: return launch_pw_tc<PwT2>(x, y, w, n, status, num_sms(), st);
+        case 0: return planes ? launch_pw_tc<PwT1, true>(x, y, w, n, status, num_sms(), st)
+                              : launch_pw_tc<PwT1, false>(x, y, w, n, status, num_sms(), st);
+        case 1: return planes ? launch_pw_tc<PwT2, true>(x, y, w, n, status, num_sms(), st)
+                              : launch_pw_tc<PwT2, false>(x, y, w, n, status, num_sms(), st);
         case 2: {
             static const int key = ssb_new_key();
-            if (ssb_first_on_device(key))
-                SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
-            tail_tc_kernel<<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
+            if (ssb_first_on_device(key)) {
+                SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
+                SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
+            }
+            if (planes) tail_tc_kernel<true><<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
+            else tail_tc_kernel<false><<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
             SSB_CHECK_LAUNCH();
             return 0;
         }

@@ -156,7 +156,12 @@ int64_t ssb_reid_tc3_block_bytes(int b);
 int ssb_reid_tc3_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
                        cudaStream_t st);
 int64_t ssb_reid_tc_aux_bytes(int which);
+// planes != 0: activations are hi/lo fp16 operand planes [crop][hl][C/8][H*W][8] (reid_tc4.cu) instead of float32 NHWC
 int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w, int n, int *status,
-                    cudaStream_t st);
+                    cudaStream_t st, int planes = 0);
 int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *boxes, const unsigned char *wsec,
-                     float *out, int n, int *status, cudaStream_t st);
+                     float *out, int n, int *status, cudaStream_t st, int planes = 0);
+int64_t ssb_reid_tc4_block_bytes(int b);
+int ssb_reid_tc4_block(int b, const void *x, void *y, const unsigned char *w, int n, int *status, cudaStream_t st);
+int ssb_reid_nhwc_to_planes(const float *x, void *y, int n, int hw, int c, cudaStream_t st);
+int ssb_reid_planes_to_nhwc(const void *x, float *y, int n, int hw, int c, cudaStream_t st);

@@ -97,12 +97,13 @@ class StrongSORT:
             pass
 
     def set_reid_backend(self, name):
-        """'tc': OSBlocks on the tcgen05 tensor cores, LightConv = pointwise GEMM + fp32 depthwise
-        (csrc/reid_tc3.cu); 'tc9': LightConv as 9 shifted tcgen05 GEMMs (csrc/reid_tc.cu);
-        'simt': fp32 CUDA-core baseline."""
-        modes = {"simt": 0, "tc9": 1, "tc": 2}
+        """'tc' (default): tcgen05 OSBlocks on fp16 hi/lo operand planes with DSMEM halo exchange
+        (csrc/reid_tc4.cu); 'tc3': round-1 pointwise GEMM + fp32 depthwise kernel on float32 NHWC
+        activations with recomputed halos (csrc/reid_tc3.cu); 'tc9': LightConv as 9 shifted tcgen05
+        GEMMs (csrc/reid_tc.cu); 'simt': fp32 CUDA-core baseline.  The last three are A/B baselines."""
+        modes = {"simt": 0, "tc9": 1, "tc3": 2, "tc": 3}
         if name not in modes:
-            raise ValueError("reid_backend must be 'tc', 'tc9' or 'simt'")
+            raise ValueError("reid_backend must be 'tc', 'tc3', 'tc9' or 'simt'")
         _lib.check(self._lib.ssb_reid_use_tc(self._h, modes[name]), "ssb_reid_use_tc")
         self.reid_backend = name
 
@@ -115,8 +116,8 @@ class StrongSORT:
 
     def reid_block(self, block, x, use_tc):
         """One OSBlock on a float32 NHWC array [n,H,W,cin] (parity tests); use_tc: False/0 simt,
-        1 'tc9' kernel, True/2 'tc' kernel."""
-        use_tc = 2 if use_tc is True else int(use_tc)
+        1 'tc9' kernel, 2 'tc3' kernel, True/3 'tc' kernel (operand planes; converted in and out)."""
+        use_tc = 3 if use_tc is True else int(use_tc)
         torch = self._torch
         couts = [64, 64, 96, 96, 128, 128]
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):

@@ -20,12 +20,13 @@ def trk():
     return StrongSORT(max_tracks=64, max_dets=64, reid_backend="simt")
 
 
-@pytest.mark.parametrize("mode", [2, 1], ids=["pwdw", "tap9"])
+@pytest.mark.parametrize("mode", [3, 2, 1], ids=["planes", "pwdw", "tap9"])
 @pytest.mark.parametrize("block", [0, 1, 2, 3, 4, 5])
 def test_osblock_tc_matches_simt(trk, block, mode):
     H, W, cin = SHAPES[block]
     rng = np.random.default_rng(100 + block)
     x = np.maximum(rng.normal(0.5, 1.0, (5, H, W, cin)), 0).astype(np.float32)
+    x[:, :, :, 0] += np.linspace(0, 2, H, dtype=np.float32)[None, :, None]     # a row gradient: band mix-ups show
     ref = trk.reid_block(block, x, use_tc=False)
     got = trk.reid_block(block, x, use_tc=mode)
     assert trk.reid_tc_status() == 0, "a tensor-core barrier wait timed out"
@@ -34,7 +35,7 @@ def test_osblock_tc_matches_simt(trk, block, mode):
     assert err < 1e-4, f"block {block}: max error {err:.3e} of the activation scale"
 
 
-@pytest.mark.parametrize("backend", ["tc", "tc9"])
+@pytest.mark.parametrize("backend", ["tc", "tc3", "tc9"])
 def test_embeddings_tc_vs_oracle(trk, golden_dir, oracle_extractor, backend):
     g = np.load(os.path.join(golden_dir, "reid_kat.npz"))
     trk.set_reid_backend(backend)
@@ -48,7 +49,7 @@ def test_embeddings_tc_vs_oracle(trk, golden_dir, oracle_extractor, backend):
     assert rel.max() < 1e-3
 
 
-@pytest.mark.parametrize("backend", ["tc", "tc9"])
+@pytest.mark.parametrize("backend", ["tc", "tc3", "tc9"])
 def test_c2_frame_tc_vs_simt_embeddings(trk, backend):
     from strongsort_yolo_b200 import synth
     st = synth.make_stream("C1")

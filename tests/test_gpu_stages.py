@@ -180,7 +180,7 @@ def test_lsap_empty_and_nan(lib):
     assert (c4r.cpu().numpy() == -1).all()
 
 
-@pytest.mark.parametrize("backend", ["tc", "tc9", "simt"])
+@pytest.mark.parametrize("backend", ["tc", "tc3", "tc9", "simt"])
 def test_reid_embeddings_kat(golden_dir, backend):
     from strongsort_yolo_b200.strong_sort import StrongSORT
     g = np.load(os.path.join(golden_dir, "reid_kat.npz"))

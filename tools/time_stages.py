@@ -49,7 +49,7 @@ def main():
     boxes = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
     feats = torch.zeros((n, 512), dtype=torch.float32, device="cuda")
     _lib.check(lib.ssb_crop_boxes(P(dets), n, 1080, 1920, P(boxes), ST()))
-    for backend in ("tc", "tc9", "simt"):
+    for backend in ("tc", "tc3", "tc9", "simt"):
         trk.set_reid_backend(backend)
         out[f"reid_{backend}_n{n}"] = timeit(lambda: _lib.check(lib.ssb_reid(
             trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST())))
@@ -59,7 +59,7 @@ def main():
     shapes = [(64, 32, 16), (64, 32, 64), (32, 16, 64), (32, 16, 96), (16, 8, 96), (16, 8, 128)]
     for b, (hh, ww, cin) in enumerate(shapes):
         x = np.maximum(np.random.default_rng(b).normal(0.5, 1, (n, hh, ww, cin)), 0).astype(np.float32)
-        for mode, tag in ((2, ""), (1, "_tap9")):
+        for mode, tag in ((3, ""), (2, "_tc3"), (1, "_tap9")):
             trk.reid_block(b, x, mode)
             lib.ssb_reid_tc_debug(P(dbg))
             trk.reid_block(b, x, mode)
