@@ -159,6 +159,16 @@ int ssb_kf_gating(const double *mean_dev, const double *cov_dev, int n_tracks,
 int ssb_appearance_cost(const float *gallery_dev, const int32_t *counts_dev,
                         int n_tracks, int budget, const float *feats_dev, int n_dets,
                         int dim, float *cost_out_dev, ssb_stream_t stream);
+/* the same cost on the tensor cores (the tracker's default path, csrc/appearance.cu): the arrays are first
+ * re-laid as fp16 hi/lo operand planes into scratch_dev (>= ssb_appearance_tc_scratch_bytes(n_tracks) bytes);
+ * dim == 512, budget <= 128, n_dets <= 512; status_dev int32[1] receives a non-zero code on a barrier timeout */
+int64_t ssb_appearance_tc_scratch_bytes(int n_tracks);
+int ssb_appearance_cost_tc(const float *gallery_dev, const int32_t *counts_dev, int n_tracks, int budget,
+                           const float *feats_dev, int n_dets, int dim, float *cost_out_dev,
+                           void *scratch_dev, int32_t *status_dev, ssb_stream_t stream);
+/* A/B switch of the tracker's appearance stage: 1 (default) tensor-core kernel on the operand planes the
+ * tracker maintains, 0 the fp32 SIMT kernel on the float32 gallery */
+int ssb_appearance_use_tc(ssb_tracker *t, int enable);
 /* 1 - IoU: track tlwh float64 [n_tracks,4], det tlwh float32 [n_dets,4]       */
 int ssb_iou_cost(const double *track_tlwh_dev, int n_tracks, const float *det_tlwh_dev,
                  int n_dets, double *cost_out_dev, ssb_stream_t stream);
@@ -210,6 +220,12 @@ int ssb_gallery_cross_match(const float *local_feat_dev, const int32_t *local_id
                             int self_rank, int t_max, int dim, float max_dist,
                             int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
                             float *match_dist_out_dev, ssb_stream_t stream);
+
+/* per-stage timing of ssb_associate (bench.py's stage split): CUDA events between its kernels.
+ * ms_out9: prep (norms, KF predict, lists) | appearance | gate | LSAP A + lists | IoU | LSAP B + lists |
+ * KF / EMA update | bookkeeping | gallery append.  ssb_profile_read synchronises on the last event.   */
+int ssb_profile_enable(ssb_tracker *t, int on);
+int ssb_profile_read(ssb_tracker *t, float *ms_out9);
 
 /* ---- introspection for tests: copy the live track table (list order) ----- */
 /* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];

@@ -19,6 +19,8 @@ SYMBOLS = [
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
     "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_increment_ages",
+    "ssb_profile_enable", "ssb_profile_read",
+    "ssb_appearance_tc_scratch_bytes", "ssb_appearance_cost_tc", "ssb_appearance_use_tc",
 ]
 
 SSB_CNT_N = 8
@@ -81,6 +83,12 @@ def load():
     lib.ssb_kf_update.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.ssb_kf_gating.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     lib.ssb_appearance_cost.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp]
+    lib.ssb_profile_enable.argtypes = [vp, i32]
+    lib.ssb_profile_read.argtypes = [vp, C.POINTER(C.c_float)]
+    lib.ssb_appearance_tc_scratch_bytes.argtypes = [i32]
+    lib.ssb_appearance_tc_scratch_bytes.restype = i64
+    lib.ssb_appearance_cost_tc.argtypes = [vp, vp, i32, i32, vp, i32, i32, vp, vp, vp, vp]
+    lib.ssb_appearance_use_tc.argtypes = [vp, i32]
     lib.ssb_iou_cost.argtypes = [vp, i32, vp, i32, vp, vp]
     lib.ssb_lsap.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.ssb_nms_scratch_bytes.argtypes = [i32]

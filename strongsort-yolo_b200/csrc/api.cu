@@ -107,6 +107,7 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     t.conf = k.take<float>(S);
     t.feat = k.take<float>(S * D);
     t.gallery = k.take<float>(S * B * D);
+    t.gal_planes = k.take<unsigned char>(S * (size_t)(2 * (D / 8) * SSB_GAL_ROWS * 16));
     t.gal_count = k.take<int>(S); t.gal_head = k.take<int>(S);
     t.order = k.take<int>(S); t.order_tmp = k.take<int>(S); t.free_stack = k.take<int>(S);
     t.scalars = k.take<int>(SC_COUNT);
@@ -116,6 +117,7 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     f.det_conf = k.take<float>(N); f.det_cls = k.take<float>(N);
     f.feats = k.take<float>(N * D);
     f.det_norm = k.take<float>(N);
+    f.det_planes = k.take<unsigned char>((size_t)2 * (D / 8) * SSB_DET_PLANES_MAX * 16);
     f.app_cost = k.take<float>(S * N);
     f.cost_a = k.take<double>(S * N);
     f.cost_b = k.take<double>(S * N);
@@ -139,6 +141,7 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     s1.det_box = k.take<int>(N * 4);
     s1.det_conf = k.take<float>(N); s1.det_cls = k.take<float>(N);
     s1.feats = k.take<float>(N * D); s1.det_norm = k.take<float>(N);
+    s1.det_planes = k.take<unsigned char>((size_t)2 * (D / 8) * SSB_DET_PLANES_MAX * 16);
     if (slot1) *slot1 = s1;
     if (tt) *tt = t;
     if (fs) *fs = f;
@@ -171,7 +174,7 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
     carve(cfg, t->ws_base, &t->tt, &t->fs, &t->reid_ws, &t->reid_ws_floats, &t->boxes_tmp, &t->tc_status,
           &t->slot[1], &t->reid_ws1);
     t->slot[0] = DetSlot{t->fs.det_tlwh, t->fs.det_xyah, t->fs.det_box, t->fs.det_conf, t->fs.det_cls,
-                         t->fs.feats, t->fs.det_norm};
+                         t->fs.feats, t->fs.det_norm, t->fs.det_planes};
     SsbDims &d = t->dims;
     d.S = cfg->max_tracks; d.N = cfg->max_dets; d.B = cfg->nn_budget; d.D = cfg->feat_dim;
     d.n_init = cfg->n_init; d.max_age = cfg->max_age;
@@ -191,8 +194,16 @@ extern "C" int ssb_destroy(ssb_tracker *t) {
         cudaEventDestroy(t->ev_fork);
         cudaEventDestroy(t->ev_join);
     }
+    if (t->prof_ev[0])
+        for (int i = 0; i < 12; i++) cudaEventDestroy(t->prof_ev[i]);
     free(t->w_off);
     free(t);
+    return 0;
+}
+
+extern "C" int ssb_appearance_use_tc(ssb_tracker *t, int enable) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    t->app_simt = enable ? 0 : 1;
     return 0;
 }
 

@@ -30,6 +30,8 @@ struct TrackTable {
     float *conf;       // [S]
     float *feat;       // [S][D]   EMA-smoothed unit feature (Track.features[-1])
     float *gallery;    // [S][B][D] ring of appended features (metric.samples[id])
+    unsigned char *gal_planes;  // [S][hl][D/8][SSB_GAL_ROWS][8] fp16: the same ring as unit vectors * 2^6 split into
+                                // hi/lo tensor-core operand planes at append time (appearance.cu); B <= SSB_GAL_ROWS only
     int *gal_count, *gal_head;  // [S]
     int *order;        // [S] list position -> slot  (== Tracker.tracks order)
     int *order_tmp;    // [S]
@@ -45,6 +47,7 @@ struct FrameScratch {
     float *det_cls;    // [N]
     float *feats;      // [N][D] raw embeddings
     float *det_norm;      // [N] L2 norm of each raw embedding
+    unsigned char *det_planes;  // [hl][D/8][npad][8] fp16: unit embeddings * 2^6 as hi/lo operand planes, npad = 128/256/512
     float *app_cost;   // [S][N] f32 nearest-neighbour cosine distance
     double *cost_a;    // [S][N] gated + clamped stage-A cost
     double *cost_b;    // [S][N] clamped IoU cost
@@ -66,7 +69,10 @@ struct DetSlot {
     float *det_tlwh, *det_xyah;
     int *det_box;
     float *det_conf, *det_cls, *feats, *det_norm;
+    unsigned char *det_planes;
 };
+#define SSB_GAL_ROWS 128          // gallery rows per slot in the operand planes (tensor-core path: nn_budget <= 128)
+#define SSB_DET_PLANES_MAX 512    // detections per frame the tensor-core appearance kernel handles (TMEM: 4 x 128 columns)
 
 struct SsbDims {
     int S, N, B, D;
@@ -98,6 +104,10 @@ struct ssb_tracker {
     int have_tc3;             // sections 10..15 present
     int use_tc;               // 0: fp32 SIMT baseline, 1: tcgen05 OSBlocks with 9 shifted GEMMs per LightConv (reid_tc.cu),
                               // 2: tcgen05 pointwise + fp32 CUDA-core depthwise (reid_tc3.cu)
+    // optional per-stage timing of ssb_associate (ssb_profile_enable): events recorded between the kernels
+    cudaEvent_t prof_ev[12];
+    int prof_on, prof_have;
+    int app_simt;             // 1: force the fp32 SIMT appearance kernel (A/B baseline; ssb_appearance_use_tc)
     int *tc_status;           // device int: !=0 -> an mbarrier wait timed out
     DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
     // ssb_update embeds the two halves of a frame's crops on two streams (fork / join by events):
@@ -140,12 +150,19 @@ inline FrameScratch ssb_slot_view(const ssb_tracker *t, int slot) {
     const DetSlot &d = t->slot[slot & 1];
     f.det_tlwh = d.det_tlwh; f.det_xyah = d.det_xyah; f.det_box = d.det_box;
     f.det_conf = d.det_conf; f.det_cls = d.det_cls; f.feats = d.feats; f.det_norm = d.det_norm;
+    f.det_planes = d.det_planes;
     return f;
 }
 int ssb_launch_appearance(const float *gallery, const int *gal_count, const int *gal_head,
                           const int *row_slot_list, const int *order, const int *n_rows_dev,
                           int max_rows, int budget, const float *feats, int n_dets, int dim,
                           float *cost, int ld, cudaStream_t st);
+// tensor-core appearance cost on the operand planes (appearance.cu); n_dets <= SSB_DET_PLANES_MAX, budget <= SSB_GAL_ROWS
+int ssb_launch_appearance_tc(const unsigned char *gal_planes, const int *gal_count, const int *row_pos_list,
+                             const int *order, const int *n_rows_dev, int max_rows, int budget,
+                             const unsigned char *det_planes, int n_dets, float *cost, int ld, int *status,
+                             cudaStream_t st);
+inline int ssb_det_npad(int n) { return n <= 128 ? 128 : (n <= 256 ? 256 : 512); }
 int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch,
                      const int *boxes, int n, float *feats_out, cudaStream_t st);
 int64_t ssb_reid_ws_floats(int max_dets);

@@ -11,6 +11,8 @@
 #include <math.h>
 #include <stdio.h>
 
+#include <cuda_fp16.h>
+
 #include "ssb_common.cuh"
 
 #define KF_WP (1.0 / 20)
@@ -129,7 +131,7 @@ __global__ void crop_boxes_kernel(const float *__restrict__ dets, int n, int H, 
 
 // L2 norm of every raw embedding (float64 accumulation, rounded to float32)
 __global__ void det_norm_kernel(const float *__restrict__ feats, int n, int D,
-                                float *__restrict__ norm_out) {
+                                float *__restrict__ norm_out, unsigned char *__restrict__ planes, int npad) {
     int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (w >= n) return;
     double s = 0;
@@ -140,6 +142,27 @@ __global__ void det_norm_kernel(const float *__restrict__ feats, int n, int D,
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) norm_out[w] = (float)sqrt(s);
+    // tensor-core appearance cost (appearance.cu): the unit embedding * 2^6 as hi/lo fp16 operand planes
+    // [hl][D/8][npad][8]; lane l writes chunks 2l and 2l+1
+    if (planes) {
+        const float nrm = (float)sqrt(__shfl_sync(0xffffffffu, s, 0));
+        for (int c = lane; c < D / 8; c += 32) {
+            const float4 a = *reinterpret_cast<const float4 *>(feats + (size_t)w * D + c * 8);
+            const float4 b = *reinterpret_cast<const float4 *>(feats + (size_t)w * D + c * 8 + 4);
+            const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+            __align__(16) __half h[8];
+            __align__(16) __half l[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const float u = (v[j] / nrm) * 64.0f;
+                h[j] = __float2half_rn(u);
+                l[j] = __float2half_rn(u - __half2float(h[j]));
+            }
+            unsigned char *dst = planes + ((size_t)c * npad + w) * 16;
+            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+            *reinterpret_cast<uint4 *>(dst + (size_t)(D / 8) * npad * 16) = *reinterpret_cast<uint4 *>(l);
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1149,6 +1172,27 @@ __global__ void gallery_append_kernel(TrackTable tt, SsbDims d) {
     const float *f = tt.feat + (size_t)s * d.D;
     float *g = tt.gallery + ((size_t)s * d.B + head) * d.D;
     for (int i = threadIdx.x; i < d.D; i += blockDim.x) g[i] = f[i];
+    if (d.B <= SSB_GAL_ROWS && d.D == 512) {
+        // the same sample as a tensor-core operand row: re-normalised like _cosine_distance does
+        // (a / ||a||, float32), * 2^6, hi/lo fp16; thread i owns elements 4i .. 4i+3 (128 threads)
+        __shared__ float s_ss[4];
+        const float4 v = *reinterpret_cast<const float4 *>(f + threadIdx.x * 4);
+        float ss = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if ((threadIdx.x & 31) == 0) s_ss[threadIdx.x >> 5] = ss;
+        __syncthreads();
+        const float nrm = sqrtf((s_ss[0] + s_ss[1]) + (s_ss[2] + s_ss[3]));
+        const float u[4] = {(v.x / nrm) * 64.0f, (v.y / nrm) * 64.0f, (v.z / nrm) * 64.0f, (v.w / nrm) * 64.0f};
+        __align__(8) __half h[4];
+        __align__(8) __half l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) { h[j] = __float2half_rn(u[j]); l[j] = __float2half_rn(u[j] - __half2float(h[j])); }
+        const int chunk = threadIdx.x >> 1, half8 = (threadIdx.x & 1) * 8;
+        unsigned char *dst = tt.gal_planes + (size_t)s * (2 * 64 * SSB_GAL_ROWS * 16) + ((size_t)chunk * SSB_GAL_ROWS + head) * 16 + half8;
+        *reinterpret_cast<uint2 *>(dst) = *reinterpret_cast<uint2 *>(h);
+        *reinterpret_cast<uint2 *>(dst + 64 * SSB_GAL_ROWS * 16) = *reinterpret_cast<uint2 *>(l);
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
         tt.gal_head[s] = (head + 1) % d.B;
@@ -1240,9 +1284,14 @@ int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const 
     size_t dyn = 0, cost_b = 0;
     int rc = lsap_prepare(L, &dyn, &cost_b);
     if (rc) return rc;
+#define SSB_PROF(i) do { if (t->prof_on) SSB_CHECK_CUDA(cudaEventRecord(t->prof_ev[i], st)); } while (0)
+    SSB_PROF(0);
 
+    // tensor-core appearance cost whenever the operand planes can hold the problem (else the fp32 SIMT kernel)
+    const bool app_tc = d.B <= SSB_GAL_ROWS && n <= SSB_DET_PLANES_MAX && d.D == 512 && !t->app_simt;
     if (n > 0) {
-        det_norm_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(fs.feats, n, d.D, fs.det_norm);
+        det_norm_kernel<<<(n * 32 + 127) / 128, 128, 0, st>>>(fs.feats, n, d.D, fs.det_norm,
+                                                              app_tc ? fs.det_planes : nullptr, ssb_det_npad(n));
         SSB_CHECK_LAUNCH();
     }
     if (Tmax > 0) {
@@ -1251,34 +1300,48 @@ int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const 
     }
     build_lists_kernel<<<1, 256, 0, st>>>(tt, fs);
     SSB_CHECK_LAUNCH();
+    SSB_PROF(1);
     if (Tmax > 0 && n > 0) {
-        rc = ssb_launch_appearance(tt.gallery, tt.gal_count, tt.gal_head, fs.conf_list, tt.order,
-                                   fs.cnt + FC_N_CONF, Tmax, d.B, fs.feats, n, d.D, fs.app_cost, n, st);
+        if (app_tc)
+            rc = ssb_launch_appearance_tc(tt.gal_planes, tt.gal_count, fs.conf_list, tt.order, fs.cnt + FC_N_CONF,
+                                          Tmax, d.B, fs.det_planes, n, fs.app_cost, n, t->tc_status, st);
+        else
+            rc = ssb_launch_appearance(tt.gallery, tt.gal_count, tt.gal_head, fs.conf_list, tt.order,
+                                       fs.cnt + FC_N_CONF, Tmax, d.B, fs.feats, n, d.D, fs.app_cost, n, st);
         if (rc) return rc;
+        SSB_PROF(2);
         gate_cost_kernel<<<Tmax, 128, 0, st>>>(tt, fs, d, n);
         SSB_CHECK_LAUNCH();
-    }
+    } else SSB_PROF(2);
+    SSB_PROF(3);
     assign_stage_a_kernel<<<1, 256, dyn, st>>>(tt, fs, d, n, L, cost_b);
     SSB_CHECK_LAUNCH();
+    SSB_PROF(4);
     if (Tmax > 0 && n > 0) {
         iou_cost_kernel<<<Tmax, 128, 0, st>>>(tt, fs, d);
         SSB_CHECK_LAUNCH();
     }
+    SSB_PROF(5);
     assign_stage_b_kernel<<<1, 256, dyn, st>>>(tt, fs, d, L, cost_b);
     SSB_CHECK_LAUNCH();
+    SSB_PROF(6);
     const int max_match = Tmax < n ? Tmax : n;
     if (max_match > 0) {
         update_matched_kernel<<<max_match, 128, 0, st>>>(tt, fs, d);
         SSB_CHECK_LAUNCH();
     }
+    SSB_PROF(7);
     bookkeep_kernel<<<1, 256, 0, st>>>(tt, fs, d, h, w, out, counts, t->tc_status);
     SSB_CHECK_LAUNCH();
+    SSB_PROF(8);
     int Tafter = Tmax + n;
     if (Tafter > d.S) Tafter = d.S;
     if (Tafter > 0) {
         gallery_append_kernel<<<Tafter, 128, 0, st>>>(tt, d);
         SSB_CHECK_LAUNCH();
     }
+    SSB_PROF(9);
+    if (t->prof_on) t->prof_have = 1;
     return 0;
 }
 
@@ -1366,6 +1429,25 @@ int ssb_launch_reset(ssb_tracker *t, cudaStream_t st) {
     reset_table_kernel<<<(t->dims.S + 127) / 128, 128, 0, st>>>(t->tt, t->dims);
     SSB_CHECK_LAUNCH();
     SSB_CHECK_CUDA(cudaMemsetAsync(t->tc_status, 0, 64 * sizeof(int), st));     // workspace memory is uninitialised
+    return 0;
+}
+
+// per-stage timing of the association (bench.py's stage split): events between the kernels of ssb_associate.
+// ms_out[9]: prep (norms, KF predict, lists) | appearance | gate | LSAP A + lists | IoU | LSAP B + lists |
+//            KF/EMA update | bookkeeping | gallery append.  Synchronises on the last event.
+extern "C" int ssb_profile_enable(ssb_tracker *t, int on) {
+    if (!t) { ssb_set_error("null handle"); return -1; }
+    if (on && !t->prof_ev[0])
+        for (int i = 0; i < 12; i++) SSB_CHECK_CUDA(cudaEventCreate(&t->prof_ev[i]));
+    t->prof_on = on ? 1 : 0;
+    t->prof_have = 0;
+    return 0;
+}
+extern "C" int ssb_profile_read(ssb_tracker *t, float *ms_out9) {
+    if (!t || !ms_out9) { ssb_set_error("null argument"); return -1; }
+    if (!t->prof_have) { ssb_set_error("no profiled frame yet"); return -1; }
+    SSB_CHECK_CUDA(cudaEventSynchronize(t->prof_ev[9]));
+    for (int i = 0; i < 9; i++) SSB_CHECK_CUDA(cudaEventElapsedTime(&ms_out9[i], t->prof_ev[i], t->prof_ev[i + 1]));
     return 0;
 }
 

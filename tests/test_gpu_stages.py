@@ -122,6 +122,15 @@ def test_appearance_cost(lib, T, B, N):
     _lib.check(lib.ssb_appearance_cost(P(gal_d), P(counts_d), T, B, P(feats_d), N, D, P(out), ST()))
     ref = np.stack([ss._nn_cosine_distance(gal[t, :counts[t]], feats) for t in range(T)])
     np.testing.assert_allclose(out.cpu().numpy(), ref, rtol=0, atol=2e-6)
+    if B <= 128 and N <= 512:       # the tracker's default: tcgen05 kernel on hi/lo fp16 operand planes
+        out2 = torch.full((T, N), -1.0, dtype=torch.float32, device="cuda")
+        scratch = torch.empty(int(lib.ssb_appearance_tc_scratch_bytes(T)), dtype=torch.uint8, device="cuda")
+        status = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(lib.ssb_appearance_cost_tc(P(gal_d), P(counts_d), T, B, P(feats_d), N, D, P(out2), P(scratch),
+                                              P(status), ST()))
+        torch.cuda.synchronize()
+        assert int(status.item()) == 0, "tensor-core barrier timeout"
+        np.testing.assert_allclose(out2.cpu().numpy(), ref, rtol=0, atol=2e-6)
 
 
 def _lsap_cases():
