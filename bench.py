@@ -11,15 +11,22 @@ every detection crop + Kalman predict + gated appearance cost + IoU cost + two
 linear assignments + track-table update.  Seeded random-weight OSNet (no
 pretrained file exists offline) and synthetic frames -- "data": "synthetic".
 
-  value  : frames/s with frames and detections already resident in HBM, through the
+One step = detector post-process of that frame's raw YOLOv8 head (DFL decode + class-aware NMS +
+scale_boxes, synthetic ``[144, 5040]`` head of the 384x640 letterboxed frame -- the backbone itself is
+out of scope) + ``StrongSORT.update``.
+
+  value  : frames/s with frames and raw heads already resident in HBM, through the
            two-stage pipeline (``update_pipelined``: the OSNet of frame k on one stream
            overlaps the association of frame k-1 on another; identical results), K frames
            timed as a whole with CUDA events; inputs rotate through W+K distinct frames
-           (>= 5x the L2), ``config.serial_flushed_ms_per_step`` is the one-frame-at-a-
+           (>= 5x the L2), ``detail.serial_flushed_ms_per_step`` is the one-frame-at-a-
            time figure with a 256 MiB L2 flush between steps
-  e2e    : frames/s through the public synchronous ``StrongSORT.update`` with HOST inputs
-           (pinned frame + dets), H2D and the D2H of the result rows inside
-           the timed region, one synchronisation per frame
+  e2e    : frames/s through the public synchronous ``StrongSORT.update`` with the frame in
+           pinned HOST memory (the raw head is what the detector backbone leaves on the device):
+           H2D of the frame and the D2H of the result rows inside the timed region, one
+           synchronisation per frame; ``e2e.streaming`` is the same through the public
+           one-frame-latency call ``update_pipelined`` (H2D of frame k+1 overlaps frame k)
+  stages : per-stage microseconds of one serial frame (CUDA events between the kernels)
   roofline     : ReID forward (``ssb_reid``, the dominant kernels) timed alone with CUDA
                  events; algorithmic flops 2*82.3e6*N per frame vs the measured
                  bf16 peak in MEASURED_PEAKS.json; traffic = DRAM bytes of the same
@@ -71,19 +78,34 @@ def load_peaks():
     return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
 
 
-def gen_frames(stream_id, count, pin):
-    """Pre-generate `count` frames of the C2 stream (host arrays; pinned torch
-    tensors when `pin`)."""
+NET_HW = (384, 640)                    # 1080p letterboxed for the detector (stride-32 multiple)
+NUM_CLASSES = 80
+
+
+def gen_frames(stream_id, count, pin, heads=True):
+    """Pre-generate `count` frames of the stream: host images (pinned torch tensors when `pin`), the
+    detections a detector would report (class = identity mod 80, so that class-aware NMS keeps
+    overlapping objects apart) and -- for the 1080p workload -- the RAW YOLOv8 head [144, 5040] whose
+    decode + NMS + scale_boxes reproduces them (the backbone's output)."""
     import torch
-    from strongsort_yolo_b200 import synth
+    from strongsort_yolo_b200 import synth, yolo
     st = synth.make_stream(CFG, stream_id=stream_id)
-    imgs, dets = [], []
+    rng = np.random.default_rng(1000 + stream_id)
+    imgs, dets, raws = [], [], []
     for _ in range(count):
         fr = st.next_frame()
+        d = fr.dets.copy()
+        d[:, 5] = np.where(fr.gt_ids >= 0, fr.gt_ids % NUM_CLASSES, NUM_CLASSES - 1)
         t = torch.from_numpy(fr.img)
         imgs.append(t.pin_memory() if pin else t)
-        dets.append(fr.dets)
-    return imgs, dets
+        dets.append(d)
+        if heads and CFG == "C2":
+            g, px, py = yolo.letterbox_params(NET_HW, fr.img.shape[:2])
+            dn = d.copy()
+            dn[:, [0, 2]] = dn[:, [0, 2]] * g + px
+            dn[:, [1, 3]] = dn[:, [1, 3]] * g + py
+            raws.append(yolo.synth_raw_head_v8(dn, NUM_CLASSES, NET_HW[0], NET_HW[1], rng=rng))
+    return imgs, dets, raws
 
 
 class ClockSampler:
@@ -205,6 +227,17 @@ class ClockSampler:
         return out
 
 
+def base_config(world):
+    """Identical in both arms (the driver compares the two `config` objects)."""
+    cfg = {"workload": WORKLOAD, "streams_per_gpu": 1,
+           "frame": [2160, 3840, 3] if CFG == "C4" else [1080, 1920, 3],
+           "dets_per_frame_nominal": 500 if CFG == "C4" else 100,
+           "detector_postprocess": "none (detections fed directly)" if CFG == "C4" else
+           "raw YOLOv8 head [144,5040] -> DFL decode -> class-aware NMS (conf 0.3, iou 0.4) -> scale_boxes",
+           "reid": "OSNet-x0.25, seeded random weights, BN calibrated on synthetic crops"}
+    return cfg
+
+
 def pick_threads(img, dets):
     """More threads is not faster for this oracle (small convs: 128 threads ran
     60x slower than 16 on the GPU box's host).  Time one ReID batch at a few
@@ -230,10 +263,11 @@ def pick_threads(img, dets):
     return best
 
 
-def run_oracle(frames_img, frames_dets, warm, timed, threads):
-    """CPU oracle fps over frames [warm, warm+timed) after `warm` untimed frames."""
+def run_oracle(frames_img, frames_dets, frames_raw, warm, timed, threads):
+    """CPU oracle seconds per frame over frames [warm, warm+timed): detector post-process restatement
+    (decode + NMS + scale_boxes, when raw heads are given) + the StrongSORT restatement."""
     import torch
-    from oracle import osnet_torch, strongsort_np
+    from oracle import nms_np, osnet_torch, strongsort_np, yolo_decode_np
     from strongsort_yolo_b200 import weights
     torch.set_num_threads(threads)
     ora = strongsort_np.StrongSORTOracle(
@@ -242,42 +276,265 @@ def run_oracle(frames_img, frames_dets, warm, timed, threads):
     for i in range(warm + timed):
         img = frames_img[i].numpy() if hasattr(frames_img[i], "numpy") else frames_img[i]
         t0 = time.perf_counter()
-        ora.update(frames_dets[i], img)
+        if frames_raw:
+            pred = yolo_decode_np.decode_v8(frames_raw[i], NUM_CLASSES, 0, NET_HW[0], NET_HW[1])
+            rows = nms_np.yolo_nms(pred, NUM_CLASSES, 0, 0.3, 0.4, 1000, False)
+            d = nms_np.scale_boxes(rows, NET_HW, img.shape[:2])[:, :6]
+        else:
+            d = frames_dets[i]
+        ora.update(d, img)
         dt = time.perf_counter() - t0
         if i >= warm:
             per.append(dt)
     return per
 
 
+def _ref_worker(job):
+    """One CPU stream of the reference arm (its own process: N streams run concurrently at --gpus N)."""
+    global CFG, METRIC, WORKLOAD
+    stream_id, cfg, warm, steps, threads = job
+    CFG = cfg
+    METRIC, WORKLOAD = WORKLOADS[CFG]
+    imgs, dets, raws = gen_frames(stream_id, warm + steps, pin=False)
+    t0 = time.perf_counter()
+    per = run_oracle(imgs, dets, raws, warm, steps, threads)
+    return float(np.sum(per)), time.perf_counter() - t0
+
+
 def impl_reference(args, rank):
-    """The reference arm: the CPU oracle on the host cores (the reference's own
-    StrongSORT code is absent from /root/reference -- SURVEY.md section 0)."""
+    """The reference arm: the CPU restatement of the same path (detector post-process + StrongSORT with the
+    fp32 torch OSNet) on the host cores -- the reference's own StrongSORT code is absent from /root/reference
+    (SURVEY.md section 0).  At --gpus N it runs N independent CPU streams CONCURRENTLY (one process each,
+    host threads divided between them), the like-for-like counterpart of N GPU streams."""
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
-    steps, warm = min(args.steps, 60), min(args.warmup, 5)
-    from strongsort_yolo_b200 import synth
-    st = synth.make_stream(CFG, stream_id=0)
-    imgs, dets = [], []
-    for _ in range(warm + steps):
-        fr = st.next_frame()
-        imgs.append(fr.img); dets.append(fr.dets)
-    cores = pick_threads(imgs[0], dets[0])
-    per = run_oracle(imgs, dets, warm, steps, cores)
-    ms = 1000.0 * float(np.mean(per))
-    fps = 1000.0 / ms
+    from multiprocessing import get_context
+    n_streams = max(1, args.gpus)
+    steps, warm = min(args.steps, 40), min(max(args.warmup, 1), 3)
+    imgs, dets, raws = gen_frames(0, 2, pin=False)
+    host = os.cpu_count() or 1
+    best = pick_threads(imgs[0].numpy(), dets[0])
+    threads = max(1, min(best, host // n_streams))
+    if n_streams == 1:
+        busy, wall = _ref_worker((0, CFG, warm, steps, threads))
+        walls = [busy]
+    else:
+        with get_context("spawn").Pool(n_streams) as pool:
+            res = pool.map(_ref_worker, [(i, CFG, warm, steps, threads) for i in range(n_streams)])
+        walls = [r[0] for r in res]
+    sec = max(walls)                          # slowest stream's timed seconds for `steps` frames
+    fps = n_streams * steps / sec
+    ms = 1000.0 * sec / steps
     line = {
         "impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32+f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "CPU restatement of StrongSORT (reference code absent); "
-                   "1 stream on the host cores regardless of --gpus"},
-        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": int(torch.get_num_threads()),
-                         "kind": "port", "sample": f"{steps} frames after {warm} warm-up frames of the C2 stream"},
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32 (torch OSNet, cosine) + f64 (Kalman, gating, LSAP)",
+        "data": "synthetic", "config": base_config(n_streams),
+        "detail": {"note": "CPU restatement of the path (reference StrongSORT code absent from the snapshot); "
+                           f"{n_streams} concurrent CPU stream(s), {threads} torch threads each on {host} host threads"},
+        "cpu_baseline": {"value": fps, "unit": UNIT, "cores": int(threads * n_streams),
+                         "kind": "port", "sample": f"{steps} frames after {warm} warm-up frames per stream, "
+                         f"{n_streams} stream(s) concurrently"},
         "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
+
+
+class DetectorPost:
+    """decode + NMS + scale_boxes of one frame's raw head on `stream`; returns the device rows and the
+    detection count (one 4-byte read-back: the tracker's C-ABI takes n as a host integer)."""
+
+    def __init__(self, device, frame_hw):
+        from strongsort_yolo_b200 import yolo
+        self.dec = yolo.YoloV8Decode(NUM_CLASSES, 0, NET_HW[0], NET_HW[1], device=str(device))
+        self.nms = yolo.YoloNMS(num_classes=NUM_CLASSES, max_anchors=self.dec.A, device=str(device))
+        self.frame_hw = frame_hw
+        import torch
+        self._cnt_pin = torch.zeros(4, dtype=torch.int32).pin_memory()
+
+    def __call__(self, raw_dev, stream):
+        import torch
+        with torch.cuda.stream(stream):
+            pred = self.dec(raw_dev, stream)
+            self.nms(pred, stream)
+            out, cnt = self.nms.scale_boxes(NET_HW, self.frame_hw, stream)
+            rows = out[:256, :6].clone()        # the NMS buffer is reused by the next frame while this one is in flight
+            self._cnt_pin.copy_(cnt, non_blocking=True)
+        stream.synchronize()
+        m = int(self._cnt_pin[0])
+        return rows[:m] if m <= 256 else out[:m, :6].clone()
+
+
+def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W, want_cpu):
+    """All measurements of one workload (CFG) on this rank's GPU; returns a dict."""
+    import ctypes as C
+    import torch
+    from strongsort_yolo_b200 import _lib
+    from strongsort_yolo_b200 import dist as ssb_dist
+    from strongsort_yolo_b200.strong_sort import StrongSORT, _HDR_BYTES
+    total = W + K
+    imgs, dets, raws = gen_frames(rank, total, pin=True)
+    use_post = bool(raws)
+    H, Wd = imgs[0].shape[0], imgs[0].shape[1]
+    trk_kw = dict(max_tracks=2048, max_dets=640) if CFG == "C4" else {}
+    imgs_dev = [im.to(device) for im in imgs]
+    dets_dev = [torch.from_numpy(d.astype(np.float32)).to(device) for d in dets]
+    raws_dev = [torch.from_numpy(r).to(device) for r in raws]
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
+    res = {}
+
+    # ---------------- (a) serial: one frame at a time, L2 flushed between steps; stage split -------------
+    trk = StrongSORT(device=str(device), **trk_kw)
+    post = DetectorPost(device, (H, Wd)) if use_post else None
+    st = trk.stream
+
+    def frame_dets(i, stream):
+        return post(raws_dev[i], stream) if use_post else dets_dev[i]
+
+    for i in range(W):
+        trk.update(frame_dets(i, st), imgs_dev[i])
+    barrier()
+    KS = min(K, 30)
+    _lib.check(lib.ssb_profile_enable(trk._h, 1))
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(KS)]
+    stage_ms = np.zeros((KS, 9), dtype=np.float64)
+    buf = (C.c_float * 9)()
+    for k in range(KS):
+        with torch.cuda.stream(st):
+            flush.fill_(k & 0xFF)                      # L2 flush, outside the timed events
+            ev[k][0].record(st)
+        d = frame_dets(W + k, st)
+        ev[k][1].record(st)
+        trk.update(d, imgs_dev[W + k])
+        ev[k][2].record(st)
+        st.synchronize()
+        _lib.check(lib.ssb_profile_read(trk._h, buf))
+        stage_ms[k] = np.asarray(list(buf))
+    _lib.check(lib.ssb_profile_enable(trk._h, 0))
+    barrier()
+    post_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    serial_ms = float(np.mean([e[0].elapsed_time(e[2]) for e in ev]))
+    names = ["prep", "appearance", "gate", "lsap_a", "iou", "lsap_b", "kf_ema_update", "bookkeep", "gallery_append"]
+    stages = {n: float(1000.0 * np.median(stage_ms[:, j])) for j, n in enumerate(names)}
+    assoc_us = float(sum(stages.values()))
+    res["serial_ms"] = serial_ms
+    del trk
+
+    # ---------------- (b) value: two-stage pipeline, device-resident inputs, K frames as a whole ----------
+    trk = StrongSORT(device=str(device), **trk_kw)
+    st = trk.stream
+    sptr = C.c_void_p(st.cuda_stream)
+    gal = ssb_dist.SharedGallery(trk) if args.shared_gallery else None
+    pstream = torch.cuda.Stream(device=device)          # detector post-process of the next frame
+    for i in range(W):
+        trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+        if gal is not None:
+            gal.step()
+    trk.flush_pipelined()
+    barrier()
+    clocks = ClockSampler(device.index)
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = lib.ssb_launch_count()
+    e0.record(st)
+    for k in range(K):
+        trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+        if gal is not None:
+            gal.step()                     # export + exchange + cross-stream match, inside the timed region
+    trk.flush_pipelined()
+    if gal is not None:
+        st.wait_stream(gal.stream)
+    e1.record(st)
+    barrier()
+    launches = int(lib.ssb_launch_count() - l0)
+    t_ms = max_over_ranks(e0.elapsed_time(e1))
+    res["clocks"] = clocks.stop()
+    res["ms_per_step"] = t_ms / K
+    res["value"] = world * K / (t_ms / 1000.0)
+    res["launches"] = launches
+    final_next_id = int(trk.last_counts[3])
+    res["n_cross"] = len(gal.report()) if gal is not None else None
+
+    # ---------------- ReID alone: roofline of the dominant kernels ------------------------------------
+    i0 = W + K // 2
+    n0 = int(dets_dev[i0].shape[0])
+    boxes = torch.zeros((n0, 4), dtype=torch.int32, device=device)
+    feats = torch.zeros((n0, 512), dtype=torch.float32, device=device)
+    with torch.cuda.stream(st):
+        _lib.check(lib.ssb_crop_boxes(_lib.ptr(dets_dev[i0]), n0, H, Wd, _lib.ptr(boxes), sptr))
+        reps = 20
+        rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for r in range(3 + reps):
+            if r >= 3:
+                flush.fill_(r)
+                rev[r - 3][0].record(st)
+            _lib.check(lib.ssb_reid(trk._h, _lib.ptr(imgs_dev[i0]), H, Wd, 3 * Wd, _lib.ptr(boxes),
+                                    n0, _lib.ptr(feats), sptr))
+            if r >= 3:
+                rev[r - 3][1].record(st)
+    st.synchronize()
+    res["reid_ms"] = float(np.mean([a.elapsed_time(b) for a, b in rev]))
+    res["reid_n"] = n0
+    res["tc_status"] = trk.reid_tc_status()
+    del trk
+
+    # ---------------- e2e: frame in pinned host memory through StrongSORT.update ------------------------
+    trk2 = StrongSORT(device=str(device), **trk_kw)
+    for i in range(W):
+        trk2.update(frame_dets(i, trk2.stream), imgs[i])
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(trk2.stream)
+    t0 = time.perf_counter()
+    n_seen = 0
+    for k in range(K):
+        d = frame_dets(W + k, trk2.stream)
+        n_seen += int(d.shape[0])
+        trk2.update(d, imgs[W + k])
+    e1.record(trk2.stream)
+    barrier()
+    e2e_s = max_over_ranks(max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1000.0))
+    res["e2e"] = world * K / e2e_s
+    res["same_ids"] = int(trk2.last_counts[3]) == final_next_id
+    res["dets_per_frame"] = n_seen / K
+    res["h2d"] = int(imgs[0].numel() + (0 if use_post else np.mean([len(d) for d in dets]) * 24))
+    res["d2h"] = int(trk2._out_bytes + (16 if use_post else 0))
+    del trk2
+
+    # ---------------- e2e, streaming call: update_pipelined with host frames -----------------------------
+    trk3 = StrongSORT(device=str(device), **trk_kw)
+    for i in range(W):
+        trk3.update_pipelined(frame_dets(i, pstream), imgs[i])
+    trk3.flush_pipelined()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        trk3.update_pipelined(frame_dets(W + k, pstream), imgs[W + k])
+    trk3.flush_pipelined()
+    torch.cuda.synchronize()
+    res["e2e_streaming"] = world * K / max_over_ranks(time.perf_counter() - t0)
+    res["same_ids_streaming"] = int(trk3.last_counts[3]) == final_next_id
+    del trk3
+
+    res.update(stages_us=stages, assoc_us=assoc_us, post_us=1000.0 * post_ms, frames=total,
+               frame_bytes=int(imgs[0].numel()), H=H, W=Wd, use_post=use_post)
+
+    # ---------------- CPU baseline (rank 0, N=1 only) ---------------------------------------------------
+    if want_cpu:
+        img0 = imgs[0].numpy()
+        cores = pick_threads(img0, dets[0])
+        warm_c, timed_c = 3, args.cpu_frames
+        per = run_oracle(imgs, dets, raws, warm_c, timed_c, cores)
+        one = run_oracle(imgs, dets, raws, 1, 2, 1)
+        res["cpu"] = {"value": 1.0 / float(np.mean(per)), "unit": UNIT, "cores": int(cores),
+                      "kind": "port", "host_cores": os.cpu_count(),
+                      "single_thread_value": 1.0 / float(np.mean(one)),
+                      "sample": f"{timed_c} frames after {warm_c} warm-up frames of the same stream "
+                                "(detector post-process + tracker), thread count = fastest of {4,8,16,32,64,all}; "
+                                "single_thread_value: 2 frames after 1 warm-up at 1 thread; "
+                                "CPU restatement of StrongSORT (reference code absent from the snapshot)"}
+    return res
 
 
 def main():
@@ -290,11 +547,10 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=20)
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
                     help="C2 (default, the BASELINE.json metric) or C4 (4K, 500 dets/frame)")
+    ap.add_argument("--no-c4", action="store_true", help="skip the appended C4 block of the N=1 line")
     ap.add_argument("--shared-gallery", action="store_true",
-                    help="config C5's optional exchange: all-gather every stream's confirmed-track features over "
-                         "NCCL after each frame and match across streams (read-only), inside the timed region")
-    ap.add_argument("--only-device", action="store_true",
-                    help="profiling aid: run only the device-resident timed loop (for ncu launch lists)")
+                    help="config C5's optional exchange: every stream's confirmed-track features exchanged after each "
+                         "frame and matched across streams (read-only), inside the timed region")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -320,17 +576,9 @@ def main():
             ge.build()
         if world > 1:
             dist.barrier()
-    import ctypes as C
     from strongsort_yolo_b200 import _lib
-    from strongsort_yolo_b200.strong_sort import StrongSORT, _HDR_BYTES
     lib = _lib.load()
     peaks, peak_src = load_peaks()
-
-    K, W = args.steps, max(args.warmup, 3)
-    total = W + K
-    imgs, dets = gen_frames(rank, total, pin=True)
-    n_per = [len(d) for d in dets]
-    H, Wd = imgs[0].shape[0], imgs[0].shape[1]
 
     def barrier():
         torch.cuda.synchronize()
@@ -341,109 +589,14 @@ def main():
     def max_over_ranks(x):
         return ssb_dist.max_over_ranks(x, device)
 
-    # ---------------- value: device-resident inputs, per-step events ----------
-    trk_kw = dict(max_tracks=2048, max_dets=640) if CFG == "C4" else {}
-    trk = StrongSORT(device=str(device), **trk_kw)
-    st = trk.stream
-    imgs_dev = [im.to(device) for im in imgs]
-    dets_dev = [torch.from_numpy(d).to(device) for d in dets]
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
-    out_rows = C.c_void_p(trk._out_dev.data_ptr() + _HDR_BYTES)
-    sptr = C.c_void_p(st.cuda_stream)
-    hint = 0
+    K, W = args.steps, max(args.warmup, 3)
+    want_cpu = rank == 0 and world == 1 and not args.no_cpu_baseline
+    r = run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W, want_cpu)
 
-    def step_device(i):
-        nonlocal hint
-        _lib.check(lib.ssb_update(trk._h, _lib.ptr(dets_dev[i]), n_per[i], _lib.ptr(imgs_dev[i]), H, Wd,
-                                  3 * Wd, None, out_rows, _lib.ptr(trk._out_dev), hint, sptr), "ssb_update")
-
-    def read_hint():
-        nonlocal hint
-        st.synchronize()
-        hint = int(trk._out_dev[:32].view(torch.int32)[1].item())
-
-    # (a) serial reference: one frame at a time, per-step events, L2 flushed between steps
-    with torch.cuda.stream(st):
-        for i in range(W):
-            step_device(i)
-            read_hint()
-    barrier()
-    KS = min(K, 30)
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(KS)]
-    with torch.cuda.stream(st):
-        for k in range(KS):
-            flush.fill_(k & 0xFF)                      # L2 flush, outside the timed pair
-            ev[k][0].record(st)
-            step_device(W + k)
-            ev[k][1].record(st)
-            read_hint()                                # sizes the next frame's grids (exact)
-    barrier()
-    serial_ms = sum(a.elapsed_time(b) for a, b in ev) / KS
-    del trk
-
-    # (b) value: the two-stage pipeline (embedding of frame k on one stream overlaps the
-    # association of frame k-1 on another), device-resident inputs, K frames timed as a whole.
-    # Inputs rotate through W+K distinct frames (>= 5x the 126 MB L2), no flush needed.
-    trk = StrongSORT(device=str(device), **trk_kw)
-    st = trk.stream
-    sptr = C.c_void_p(st.cuda_stream)
-    gal = ssb_dist.SharedGallery(trk) if args.shared_gallery else None
-    for i in range(W):
-        trk.update_pipelined(dets_dev[i], imgs_dev[i])
-        if gal is not None:
-            gal.step()
-    trk.flush_pipelined()
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    l0 = lib.ssb_launch_count()
-    e0.record(st)
-    for k in range(K):
-        trk.update_pipelined(dets_dev[W + k], imgs_dev[W + k])
-        if gal is not None:
-            gal.step()                     # export + NCCL all-gather + cross-stream match, on the tracker's stream
-    trk.flush_pipelined()
-    if gal is not None:
-        st.wait_stream(gal.stream)         # the exchange of the last frame ends inside the timed region
-    e1.record(st)
-    barrier()
-    launches = int(lib.ssb_launch_count() - l0)
-    t_steps_ms = e0.elapsed_time(e1)
-    clk = clocks.stop()
-    t_steps_ms = max_over_ranks(t_steps_ms)
-    ms_per_step = t_steps_ms / K
-    value = world * K / (t_steps_ms / 1000.0)
-    final_next_id = int(trk.last_counts[3])
-
-    if args.only_device:
-        if rank == 0:
-            print(json.dumps({"only_device": True, "ms_per_step": ms_per_step, "value": value,
-                              "serial_flushed_ms_per_step": serial_ms,
-                              "gpu_launches": launches, "steps": K, "warmup": W}), flush=True)
-        return
-
-    # ---------------- ReID alone: roofline of the dominant kernels ------------
-    i0 = W + K // 2
-    boxes = torch.zeros((n_per[i0], 4), dtype=torch.int32, device=device)
-    feats = torch.zeros((n_per[i0], 512), dtype=torch.float32, device=device)
-    with torch.cuda.stream(st):
-        _lib.check(lib.ssb_crop_boxes(_lib.ptr(dets_dev[i0]), n_per[i0], H, Wd, _lib.ptr(boxes), sptr))
-        reps = 20
-        rev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for r in range(3 + reps):
-            if r >= 3:
-                flush.fill_(r)
-                rev[r - 3][0].record(st)
-            _lib.check(lib.ssb_reid(trk._h, _lib.ptr(imgs_dev[i0]), H, Wd, 3 * Wd, _lib.ptr(boxes),
-                                    n_per[i0], _lib.ptr(feats), sptr))
-            if r >= 3:
-                rev[r - 3][1].record(st)
-    st.synchronize()
-    reid_ms = float(np.mean([a.elapsed_time(b) for a, b in rev]))
-    reid_flops = 2.0 * REID_MACS_PER_CROP * n_per[i0]
-    achieved_tf = reid_flops / (reid_ms * 1e-3) / 1e12
+    reid_flops = 2.0 * REID_MACS_PER_CROP * r["reid_n"]
+    achieved_tf = reid_flops / (r["reid_ms"] * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
+    hbm = float(peaks.get("hbm_gbs", 6570.6))
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "reid_traffic_bytes.json")
     if os.path.exists(tpath):
@@ -451,68 +604,66 @@ def main():
             traffic = json.load(open(tpath)).get("dram_bytes_per_reid_forward")
         except Exception:
             traffic = None
+    n_conf = 256 if CFG == "C4" else 100
+    app_bytes = (n_conf * 128 + 128 * ((r["reid_n"] + 127) // 128)) * 512 * 4      # operand planes the kernel streams
+    app_gbs = app_bytes / max(r["stages_us"]["appearance"], 1e-3) / 1e3
 
-    # ---------------- e2e: host buffers through StrongSORT.update -------------
-    n_cross = len(gal.report()) if gal is not None else None
-    trk2 = StrongSORT(device=str(device), **trk_kw)
-    for i in range(W):
-        trk2.update(dets[i], imgs[i])
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(trk2.stream)
-    t0 = time.perf_counter()
-    for k in range(K):
-        rows = trk2.update(dets[W + k], imgs[W + k])
-    e1.record(trk2.stream)
-    barrier()
-    e2e_s = max(time.perf_counter() - t0, e0.elapsed_time(e1) / 1000.0)
-    e2e_s = max_over_ranks(e2e_s)
-    e2e_fps = world * K / e2e_s
-    same_ids = int(trk2.last_counts[3]) == final_next_id
-    h2d = int(imgs[0].numel() + np.mean(n_per) * 24)
-    d2h = int(trk2._out_bytes)
-
-    # ---------------- CPU baseline (rank 0, N=1 only) --------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        img0 = imgs[0].numpy()
-        cores = pick_threads(img0, dets[0])
-        warm_c, timed_c = 5, args.cpu_frames
-        per = run_oracle(imgs, dets, warm_c, timed_c, cores)
-        cpu = {"value": 1.0 / float(np.mean(per)), "unit": UNIT, "cores": int(torch.get_num_threads()),
-               "kind": "port", "host_cores": os.cpu_count(),
-               "sample": f"{timed_c} frames after {warm_c} warm-up frames of the same C2 stream, "
-                         "thread count = fastest of {4,8,16,32,64,all}; "
-                         "CPU restatement of StrongSORT (reference code absent from the snapshot)"}
+    # ---- appended C4 block (N=1 only): BASELINE.json configs[3] through the same code
+    c4 = None
+    if world == 1 and CFG == "C2" and not args.no_c4:
+        CFG = "C4"
+        METRIC, WORKLOAD = WORKLOADS[CFG]
+        K4, W4 = min(K, 30), min(W, 5)
+        r4 = run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K4, W4, False)
+        c4 = {"workload": WORKLOAD, "metric": METRIC, "value": r4["value"], "unit": UNIT, "steps": K4, "warmup": W4,
+              "ms_per_step": r4["ms_per_step"], "e2e": r4["e2e"], "e2e_streaming": r4["e2e_streaming"],
+              "reid_ms": r4["reid_ms"], "assoc_us": r4["assoc_us"], "stages_us": r4["stages_us"],
+              "serial_flushed_ms_per_step": r4["serial_ms"], "dets_per_frame": r4["dets_per_frame"],
+              "e2e_ids_equal_device_run": bool(r4["same_ids"])}
+        CFG = "C2"
+        METRIC, WORKLOAD = WORKLOADS[CFG]
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32 (ReID, appearance) + f64 (Kalman, gating, LSAP)",
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None,
+            "dtype": "fp16 hi/lo operand pairs (~22-bit mantissa) with fp32 accumulate on tcgen05 (ReID convs, appearance "
+                     "cost) + fp32 (depthwise, decode, NMS) + f64 (Kalman, gating, IoU, LSAP)",
             "data": "synthetic",
-            "config": {"workload": WORKLOAD, "streams": world, "frame": [H, Wd, 3],
-                       "dets_per_frame": float(np.mean(n_per)),
-                       "l2": f"not flushed: inputs rotate through {W + K} distinct frames "
-                             f"({(W + K) * imgs[0].numel() / 1e6:.0f} MB > 126 MB L2)",
-                       "pipeline": "embedding(k) on stream 1 overlaps association(k-1) on stream 2 "
-                                   "(ssb_embed / ssb_associate); results identical to the serial path",
-                       "serial_flushed_ms_per_step": serial_ms,
-                       "weights": "seeded random OSNet-x0.25, BN calibrated on synthetic crops",
-                       "e2e_ids_equal_device_run": bool(same_ids),
-                       **({"shared_gallery": "per frame: export + all-gather (NCCL) of [256,512] f32 + ids per rank + "
-                                             "cross-stream cosine match, read-only, on a side stream; inside the timed region",
-                           "cross_stream_matches_last_frame_rank0": n_cross} if gal is not None else {})},
-            "e2e": {"value": e2e_fps, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": launches,
-            "clocks": clk,
+            "config": base_config(world),
+            "detail": {"streams": world, "dets_per_frame": r["dets_per_frame"],
+                       "l2": f"not flushed: inputs rotate through {r['frames']} distinct frames "
+                             f"({r['frames'] * r['frame_bytes'] / 1e6:.0f} MB > 126 MB L2)",
+                       "pipeline": "detector post-process + embedding of frame k on stream 1 overlap the association of "
+                                   "frame k-1 on stream 2 (ssb_embed / ssb_associate); results identical to the serial path",
+                       "serial_flushed_ms_per_step": r["serial_ms"],
+                       "e2e_ids_equal_device_run": bool(r["same_ids"]),
+                       "e2e_streaming_ids_equal_device_run": bool(r["same_ids_streaming"]),
+                       "reid_tc_status": r["tc_status"],
+                       **({"shared_gallery": "per frame: export of [256,512] f32 + ids per rank, one packed exchange, "
+                                             "cross-stream cosine match (read-only) on a side stream; inside the timed region",
+                           "cross_stream_matches_last_frame_rank0": r["n_cross"]} if args.shared_gallery else {})},
+            "e2e": {"value": r["e2e"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
+                    "call": "StrongSORT.update(dets, img) -- synchronous, host frame",
+                    "streaming": {"value": r["e2e_streaming"], "unit": UNIT,
+                                  "call": "StrongSORT.update_pipelined(dets, img) -- one frame of latency, host frame"}},
+            "gpu_launches": r["launches"],
+            "clocks": r["clocks"],
+            "stages": {"unit": "us per frame (serial, L2 flushed)", "detector_postprocess": r["post_us"],
+                       "reid_forward": 1000.0 * r["reid_ms"], **r["stages_us"], "association_total": r["assoc_us"]},
             "roofline": {"bound": "tensor", "kernel": "OSNet ReID forward (all kernels of ssb_reid)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
                          "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
-                         "reid_ms": reid_ms, "flops_per_launch": reid_flops},
+                         "reid_ms": r["reid_ms"], "flops_per_launch": reid_flops},
+            "roofline_cost": {"bound": "hbm", "kernel": "appearance_tc_kernel (cosine-NN cost over the gallery)",
+                              "achieved": app_gbs, "peak": hbm, "unit": "GB/s", "frac": app_gbs / hbm,
+                              "bytes_per_launch": app_bytes, "us": r["stages_us"]["appearance"]},
         }
-        if cpu is not None:
-            line["cpu_baseline"] = cpu
+        if "cpu" in r:
+            line["cpu_baseline"] = r["cpu"]
+        if c4 is not None:
+            line["configs"] = {"C4": c4}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

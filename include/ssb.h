@@ -186,6 +186,12 @@ int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_
                  float *out_dev, int32_t *count_dev, void *scratch_dev,
                  ssb_stream_t stream);
 
+/* ultralytics scale_boxes: the first count_dev[0] rows of an ssb_yolo_nms output (cols floats per row, box in
+ * columns 0..3, network-input pixels) back to the original w0 x h0 frame: subtract the letterbox padding,
+ * divide by the gain, clip.  In place. */
+int ssb_yolo_scale_boxes(float *rows_dev, int cols, const int32_t *count_dev, int max_det, float gain,
+                         float pad_x, float pad_y, int w0, int h0, ssb_stream_t stream);
+
 /* YOLOv8 detect / pose head decode: raw float32 [4*16 + nc + 3*kpts, A] (DFL bins,
  * class logits, keypoint x,y,vis) for a network input of in_h x in_w (multiples of 32; A =
  * ssb_yolo_num_anchors, stride-8/16/32 levels concatenated) -> pred float32 [4 + nc + 3*kpts, A],

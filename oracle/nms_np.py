@@ -29,3 +29,20 @@ def yolo_nms(pred, nc, n_extra, conf_thres, iou_thres, max_det, agnostic):
     c = x[:, 5:6] * (0.0 if agnostic else MAX_WH)
     i = torchvision.ops.nms(x[:, :4] + c, x[:, 4], iou_thres)[:max_det]
     return x[i].numpy().astype(np.float32)
+
+
+def scale_boxes(rows, net_hw, frame_hw):
+    """ultralytics ops.scale_boxes + clip_boxes restated (third-party, not vendored): NMS rows in
+    network-input pixels -> original frame pixels (float32 arithmetic, in the library's order)."""
+    rows = np.array(rows, dtype=np.float32, copy=True)
+    gain = min(net_hw[0] / frame_hw[0], net_hw[1] / frame_hw[1])
+    pad_x = round((net_hw[1] - frame_hw[1] * gain) / 2 - 0.1)
+    pad_y = round((net_hw[0] - frame_hw[0] * gain) / 2 - 0.1)
+    b = torch.as_tensor(rows[:, :4])
+    b[:, 0] -= pad_x; b[:, 2] -= pad_x
+    b[:, 1] -= pad_y; b[:, 3] -= pad_y
+    b /= gain
+    b[:, 0].clamp_(0, frame_hw[1]); b[:, 2].clamp_(0, frame_hw[1])
+    b[:, 1].clamp_(0, frame_hw[0]); b[:, 3].clamp_(0, frame_hw[0])
+    rows[:, :4] = b.numpy()
+    return rows

@@ -215,3 +215,27 @@ extern "C" int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extr
     SSB_CHECK_LAUNCH();
     return 0;
 }
+
+// ultralytics scale_boxes (ops.py; SURVEY.md C.2 "boxes are scaled back from letterbox to the original
+// frame"): x -= pad_x, y -= pad_y, / gain (float32, IEEE division), clip to [0, w0] x [0, h0]; in place
+// on the first count[0] rows of the NMS output.
+__global__ void scale_boxes_kernel(float *__restrict__ rows, int cols, const int *__restrict__ count, int max_det,
+                                   float gain, float pad_x, float pad_y, float w0, float h0) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = min(count[0], max_det);
+    if (i >= m) return;
+    float *b = rows + (size_t)i * cols;
+    b[0] = fminf(fmaxf((b[0] - pad_x) / gain, 0.f), w0);
+    b[1] = fminf(fmaxf((b[1] - pad_y) / gain, 0.f), h0);
+    b[2] = fminf(fmaxf((b[2] - pad_x) / gain, 0.f), w0);
+    b[3] = fminf(fmaxf((b[3] - pad_y) / gain, 0.f), h0);
+}
+
+extern "C" int ssb_yolo_scale_boxes(float *rows_dev, int cols, const int32_t *count_dev, int max_det, float gain,
+                                    float pad_x, float pad_y, int w0, int h0, ssb_stream_t stream) {
+    if (!rows_dev || !count_dev || cols < 4 || max_det < 1 || !(gain > 0.f)) { ssb_set_error("bad scale_boxes argument"); return -1; }
+    scale_boxes_kernel<<<(max_det + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rows_dev, cols, count_dev, max_det, gain,
+                                                                              pad_x, pad_y, (float)w0, (float)h0);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}

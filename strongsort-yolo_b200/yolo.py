@@ -49,11 +49,29 @@ class YoloNMS:
             C.c_void_p(st.cuda_stream)), "ssb_yolo_nms")
         return self._out, self._count
 
+    def scale_boxes(self, net_hw, frame_hw, stream=None):
+        """ultralytics ``scale_boxes``: the NMS rows (network-input pixels) back to the original frame,
+        in place on the device (letterbox gain / padding of ``LetterBox(center=True)``)."""
+        g, px, py = letterbox_params(net_hw, frame_hw)
+        st = stream if stream is not None else self._torch.cuda.current_stream(self.device)
+        _lib.check(self._lib.ssb_yolo_scale_boxes(_lib.ptr(self._out), 6 + self.n_extra, _lib.ptr(self._count),
+                                                  self.max_det, g, px, py, int(frame_hw[1]), int(frame_hw[0]),
+                                                  C.c_void_p(st.cuda_stream)), "ssb_yolo_scale_boxes")
+        return self._out, self._count
+
     def detect(self, pred):
         """Convenience: synchronous, returns float32 ndarray [M, 6+extra]."""
         out, cnt = self(pred)
         m = int(cnt[0].item())
         return out[:m].cpu().numpy()
+
+
+def letterbox_params(net_hw, frame_hw):
+    """(gain, pad_x, pad_y) of ultralytics' scale_boxes for a frame letterboxed into the network input."""
+    gain = min(net_hw[0] / frame_hw[0], net_hw[1] / frame_hw[1])
+    pad_x = round((net_hw[1] - frame_hw[1] * gain) / 2 - 0.1)
+    pad_y = round((net_hw[0] - frame_hw[0] * gain) / 2 - 0.1)
+    return float(gain), float(pad_x), float(pad_y)
 
 
 class YoloV8Decode:
@@ -137,31 +155,42 @@ def synth_raw_head_v8(dets, num_classes, in_h, in_w, rng=None, kpts=None):
     raw = np.zeros((64 + num_classes + 3 * nk, A), dtype=np.float32)
     raw[:64] = rng.normal(0, 0.1, (64, A))
     raw[64:64 + num_classes] = rng.uniform(-6.0, -3.5, (num_classes, A))       # sigmoid < 0.03
+    used = set()
     for i, (x1, y1, x2, y2, conf, cls) in enumerate(dets):
         cx, cy = (x1 + x2) / 2, (y1 + y2) / 2
+        placed = False
         for s, gh, gw, b0 in levels:
-            gx, gy = int(floor(cx / s)), int(floor(cy / s))
-            if not (0 <= gx < gw and 0 <= gy < gh):
-                continue
-            ax, ay = (gx + 0.5) * s, (gy + 0.5) * s
-            d = np.array([ax - x1, ay - y1, x2 - ax, y2 - ay], dtype=np.float64) / s
-            if d.min() < 0 or d.max() > 14.5:
-                continue
-            a = b0 + gy * gw + gx
-            for side in range(4):
-                j, f = int(floor(d[side])), d[side] - floor(d[side])
-                logit = np.full(16, -12.0)
-                f = min(max(f, 1e-4), 1 - 1e-4)
-                logit[j], logit[j + 1] = log(1 - f), log(f)              # softmax -> (1-f, f)
-                raw[side * 16:(side + 1) * 16, a] = logit
-            p = min(max(float(conf), 1e-4), 1 - 1e-4)
-            raw[64 + int(cls), a] = log(p / (1 - p))
-            if nk:
-                kp = np.asarray(kpts)[i]
-                raw[64 + num_classes + 0:64 + num_classes + 3 * nk:3, a] = (kp[:, 0] / s - (gx + 0.5 - 0.5)) / 2
-                raw[64 + num_classes + 1:64 + num_classes + 3 * nk:3, a] = (kp[:, 1] / s - (gy + 0.5 - 0.5)) / 2
-                raw[64 + num_classes + 2:64 + num_classes + 3 * nk:3, a] = 4.0
-            break
+            gx0, gy0 = int(floor(cx / s)), int(floor(cy / s))
+            # the cell holding the centre first, then its neighbours inside the box (a free anchor per detection)
+            for dgy, dgx in ((0, 0), (0, 1), (0, -1), (1, 0), (-1, 0), (1, 1), (-1, -1), (1, -1), (-1, 1)):
+                gx, gy = gx0 + dgx, gy0 + dgy
+                if not (0 <= gx < gw and 0 <= gy < gh):
+                    continue
+                a = b0 + gy * gw + gx
+                if a in used:
+                    continue
+                ax, ay = (gx + 0.5) * s, (gy + 0.5) * s
+                d = np.array([ax - x1, ay - y1, x2 - ax, y2 - ay], dtype=np.float64) / s
+                if d.min() < 0 or d.max() > 14.5:
+                    continue
+                used.add(a)
+                for side in range(4):
+                    j, f = int(floor(d[side])), d[side] - floor(d[side])
+                    logit = np.full(16, -12.0)
+                    f = min(max(f, 1e-4), 1 - 1e-4)
+                    logit[j], logit[j + 1] = log(1 - f), log(f)              # softmax -> (1-f, f)
+                    raw[side * 16:(side + 1) * 16, a] = logit
+                p = min(max(float(conf), 1e-4), 1 - 1e-4)
+                raw[64 + int(cls), a] = log(p / (1 - p))
+                if nk:
+                    kp = np.asarray(kpts)[i]
+                    raw[64 + num_classes + 0:64 + num_classes + 3 * nk:3, a] = (kp[:, 0] / s - (gx + 0.5 - 0.5)) / 2
+                    raw[64 + num_classes + 1:64 + num_classes + 3 * nk:3, a] = (kp[:, 1] / s - (gy + 0.5 - 0.5)) / 2
+                    raw[64 + num_classes + 2:64 + num_classes + 3 * nk:3, a] = 4.0
+                placed = True
+                break
+            if placed:
+                break
     return raw
 
 

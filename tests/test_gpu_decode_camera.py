@@ -46,6 +46,36 @@ def test_decode_then_nms_recovers_detections():
     np.testing.assert_array_equal(rows[:, 5], want[:, 5])
 
 
+def test_c2_head_decode_nms_scale_recovers_frame_detections():
+    """The bench's detector post-process chain on a 1080p frame letterboxed to 384x640: raw v8 head ->
+    decode -> NMS -> scale_boxes gives the frame's detections back (bit-exact vs the CPU restatement of
+    scale_boxes; within the DFL round trip of the detections that generated the head)."""
+    import torch
+    rng = np.random.default_rng(3)
+    net, frame = (384, 640), (1080, 1920)
+    fr = synth.make_stream("C2", render=False).next_frame()
+    g, px, py = yolo.letterbox_params(net, frame)
+    fr.dets[:, 5] = np.where(fr.gt_ids >= 0, fr.gt_ids % 80, 79)       # one class per identity: class-aware NMS keeps overlaps
+    d = fr.dets.copy()
+    d[:, [0, 2]] = d[:, [0, 2]] * g + px
+    d[:, [1, 3]] = d[:, [1, 3]] * g + py
+    raw = yolo.synth_raw_head_v8(d, 80, net[0], net[1], rng=rng)
+    dec = yolo.YoloV8Decode(80, 0, net[0], net[1])
+    nms = yolo.YoloNMS(num_classes=80, max_anchors=dec.A)
+    nms(dec(torch.as_tensor(raw).cuda()))
+    unscaled = nms._out.clone()
+    out, cnt = nms.scale_boxes(net, frame)
+    m = int(cnt[0].item())
+    got = out[:m].cpu().numpy()
+    want = nms_np.scale_boxes(unscaled[:m].cpu().numpy(), net, frame)
+    np.testing.assert_array_equal(got, want)
+    assert m == len(fr.dets)
+    order = np.argsort(-fr.dets[:, 4], kind="stable")
+    np.testing.assert_allclose(got[:, :4], fr.dets[order, :4], rtol=0, atol=0.05)
+    np.testing.assert_allclose(got[:, 4], fr.dets[order, 4], rtol=0, atol=1e-5)
+    np.testing.assert_array_equal(got[:, 5], fr.dets[order, 5])
+
+
 def test_camera_update_matches_oracle_and_tracking_continues():
     from strongsort_yolo_b200.strong_sort import StrongSORT
     st = synth.make_stream("C1", render=False)
