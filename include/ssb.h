@@ -84,6 +84,11 @@ int ssb_reset(ssb_tracker *t, ssb_stream_t stream);
  * mark_missed(); no Kalman predict.  Tracks deleted here leave the list at the next ssb_update. */
 int ssb_increment_ages(ssb_tracker *t, ssb_stream_t stream);
 
+/* The reference's --count reduction (yolo_multi_model.py:284-300: per track id the most frequent class of
+ * its label lines -- smallest class on ties --, then the number of ids per class) over the device track
+ * table: out_dev int32 [80]; ids of deleted tracks keep counting.  Classes >= 80 share the last bin. */
+int ssb_class_counts(ssb_tracker *t, int32_t *out_dev, ssb_stream_t stream);
+
 /* ---- ReID weights (OSNet-x0.25, BN folded by the host; see weights.py) --- */
 int ssb_reid_num_tensors(void);
 /* fills sizes[ssb_reid_num_tensors()] with the element count of each folded

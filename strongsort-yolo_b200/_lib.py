@@ -19,7 +19,7 @@ SYMBOLS = [
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
     "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_increment_ages",
-    "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes",
+    "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes", "ssb_class_counts",
     "ssb_appearance_tc_scratch_bytes", "ssb_appearance_cost_tc", "ssb_appearance_use_tc",
 ]
 
@@ -64,6 +64,7 @@ def load():
     lib.ssb_destroy.argtypes = [vp]
     lib.ssb_reset.argtypes = [vp, vp]
     lib.ssb_increment_ages.argtypes = [vp, vp]
+    lib.ssb_class_counts.argtypes = [vp, vp, vp]
     lib.ssb_reid_num_tensors.restype = i32
     lib.ssb_reid_tensor_sizes.argtypes = [C.POINTER(i64)]
     lib.ssb_reid_set_weights.argtypes = [vp, vp, C.POINTER(i64), i32]

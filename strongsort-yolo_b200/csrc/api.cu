@@ -109,6 +109,7 @@ static size_t carve(const ssb_config *c, char *base, TrackTable *tt, FrameScratc
     t.gallery = k.take<float>(S * B * D);
     t.gal_planes = k.take<unsigned char>(S * (size_t)(2 * (D / 8) * SSB_GAL_ROWS * 16));
     t.gal_count = k.take<int>(S); t.gal_head = k.take<int>(S);
+    t.cls_hist = k.take<int>(S * SSB_NCLS); t.dead_count = k.take<int>(SSB_NCLS);
     t.order = k.take<int>(S); t.order_tmp = k.take<int>(S); t.free_stack = k.take<int>(S);
     t.scalars = k.take<int>(SC_COUNT);
     FrameScratch f;

@@ -33,6 +33,8 @@ struct TrackTable {
     unsigned char *gal_planes;  // [S][hl][D/8][SSB_GAL_ROWS][8] fp16: the same ring as unit vectors * 2^6 split into
                                 // hi/lo tensor-core operand planes at append time (appearance.cu); B <= SSB_GAL_ROWS only
     int *gal_count, *gal_head;  // [S]
+    int *cls_hist;     // [S][SSB_NCLS] classes of the rows this track has been REPORTED with (the reference's label lines)
+    int *dead_count;   // [SSB_NCLS] majority class of every reported track that has since been deleted
     int *order;        // [S] list position -> slot  (== Tracker.tracks order)
     int *order_tmp;    // [S]
     int *free_stack;   // [S]
@@ -71,6 +73,7 @@ struct DetSlot {
     float *det_conf, *det_cls, *feats, *det_norm;
     unsigned char *det_planes;
 };
+#define SSB_NCLS 80               // class histogram width of the --count reduction (COCO; larger ids share the last bin)
 #define SSB_GAL_ROWS 128          // gallery rows per slot in the operand planes (tensor-core path: nn_budget <= 128)
 #define SSB_DET_PLANES_MAX 512    // detections per frame the tensor-core appearance kernel handles (TMEM: 4 x 128 columns)
 

@@ -1021,6 +1021,31 @@ __global__ void update_matched_kernel(TrackTable tt, FrameScratch fs, SsbDims d)
 // drop deleted tracks (order preserved), output rows (A.2), counters.
 // Single block; the per-new-track feature copies use all warps.
 // ---------------------------------------------------------------------------
+// the reference's --count reduction for one track (yolo_multi_model.py:284-300): the most frequent class of
+// its label lines, the SMALLEST class on ties (Counter(sorted(list)).most_common(1)); -1 when never reported
+__device__ int hist_majority(int *h, bool clear) {
+    int best = -1, bn = 0;
+    for (int c = 0; c < SSB_NCLS; c++) {
+        const int v = h[c];
+        if (v > bn) { bn = v; best = c; }
+        if (clear) h[c] = 0;
+    }
+    return best;
+}
+
+__global__ void class_counts_kernel(TrackTable tt, int *out) {
+    __shared__ int s_cnt[SSB_NCLS];
+    for (int c = threadIdx.x; c < SSB_NCLS; c += blockDim.x) s_cnt[c] = tt.dead_count[c];
+    __syncthreads();
+    const int T = tt.scalars[SC_N_TRACKS];
+    for (int p = threadIdx.x; p < T; p += blockDim.x) {
+        const int maj = hist_majority(tt.cls_hist + (size_t)tt.order[p] * SSB_NCLS, false);
+        if (maj >= 0) atomicAdd(&s_cnt[maj], 1);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < SSB_NCLS; c += blockDim.x) out[c] = s_cnt[c];
+}
+
 __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H, int W,
                                 double *out, int *counts, const int *tc_status) {
     __shared__ int s_w[33];
@@ -1092,7 +1117,11 @@ __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H
     for (int p = b; p < e; p++) {
         const int s = tt.order[p];
         if (tt.state[s] != SSB_DELETED) tt.order_tmp[off++] = s;
-        else { tt.free_stack[free_base + offd] = s; offd++; tt.gal_count[s] = 0; tt.gal_head[s] = 0; }
+        else {
+            tt.free_stack[free_base + offd] = s; offd++; tt.gal_count[s] = 0; tt.gal_head[s] = 0;
+            const int maj = hist_majority(tt.cls_hist + (size_t)s * SSB_NCLS, true);    // --count: the id keeps counting
+            if (maj >= 0) atomicAdd(&tt.dead_count[maj], 1);
+        }
     }
     __syncthreads();
     for (int p = tid; p < keep_tot; p += blockDim.x) tt.order[p] = tt.order_tmp[p];
@@ -1127,6 +1156,8 @@ __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H
         o[6] = (double)tt.conf[s];
         o[7] = (double)tt.last_det[s];
         off2++;
+        const int c = tt.cls[s];
+        tt.cls_hist[(size_t)s * SSB_NCLS + (c < 0 ? 0 : (c >= SSB_NCLS ? SSB_NCLS - 1 : c))] += 1;
     }
     if (tid == 0) {
         tt.scalars[SC_N_TRACKS] = keep_tot;
@@ -1207,7 +1238,9 @@ __global__ void reset_table_kernel(TrackTable tt, SsbDims d) {
         tt.state[i] = SSB_DELETED;
         tt.gal_count[i] = 0; tt.gal_head[i] = 0;
         tt.order[i] = 0;
+        for (int c = 0; c < SSB_NCLS; c++) tt.cls_hist[(size_t)i * SSB_NCLS + c] = 0;
     }
+    if (i < SSB_NCLS) tt.dead_count[i] = 0;
     if (i == 0) {
         for (int k = 0; k < SC_COUNT; k++) tt.scalars[k] = 0;
         tt.scalars[SC_NEXT_ID] = 1;
@@ -1448,6 +1481,15 @@ extern "C" int ssb_profile_read(ssb_tracker *t, float *ms_out9) {
     if (!t->prof_have) { ssb_set_error("no profiled frame yet"); return -1; }
     SSB_CHECK_CUDA(cudaEventSynchronize(t->prof_ev[9]));
     for (int i = 0; i < 9; i++) SSB_CHECK_CUDA(cudaEventElapsedTime(&ms_out9[i], t->prof_ev[i], t->prof_ev[i + 1]));
+    return 0;
+}
+
+// --count of the reference (yolo_multi_model.py:284-300) as a reduction over the track table: out_dev[c] =
+// number of track ids whose label lines so far carry class c most often (ties: smallest class)
+extern "C" int ssb_class_counts(ssb_tracker *t, int32_t *out_dev, ssb_stream_t stream) {
+    if (!t || !out_dev) { ssb_set_error("null argument"); return -1; }
+    class_counts_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t->tt, out_dev);
+    SSB_CHECK_LAUNCH();
     return 0;
 }
 

@@ -181,6 +181,18 @@ class StrongSORT:
         _lib.check(self._lib.ssb_increment_ages(self._h, C.c_void_p(self.stream.cuda_stream)),
                    "ssb_increment_ages")
 
+    def class_counts(self):
+        """The reference's ``--count`` overlay numbers (yolo_multi_model.py:284-300) from the device track
+        table: {class id: number of track ids whose reported rows carry that class most often}."""
+        torch = self._torch
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            out = torch.zeros(80, dtype=torch.int32, device=self.device)
+            _lib.check(self._lib.ssb_class_counts(self._h, _lib.ptr(out), C.c_void_p(self.stream.cuda_stream)),
+                       "ssb_class_counts")
+            host = out.cpu()
+        self.stream.synchronize()
+        return {int(c): int(v) for c, v in enumerate(host.tolist()) if v}
+
     def update(self, dets, ori_img, features=None):
         """dets: [N,6] (x1,y1,x2,y2,conf,cls) torch CPU tensor / ndarray (or a
         CUDA tensor); ori_img: BGR uint8 HxWx3 ndarray (or torch tensor, CPU
@@ -362,9 +374,13 @@ class StrongSORT:
         return prev
 
     def flush_pipelined(self):
+        """Rows of the last submitted frame (None if nothing is in flight); drains the pipeline, so the
+        next ``update_pipelined`` call returns None again."""
         if not hasattr(self, "_pstream") or self._p_k == 0:
             return None
-        return self._pipe_collect((self._p_k - 1) & 1)
+        rows = self._pipe_collect((self._p_k - 1) & 1)
+        self._p_k = 0
+        return rows
 
     def export_tracks(self):
         """Live track table in list order (== Tracker.tracks of the oracle)."""

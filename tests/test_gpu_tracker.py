@@ -257,3 +257,37 @@ def test_pipelined_update_equals_synchronous():
     assert len(got) == len(want)
     for x, y in zip(got, want):
         np.testing.assert_array_equal(x, y)
+
+
+def test_class_counts_match_the_reference_count_logic():
+    """--count (reference yolo_multi_model.py:284-300: pandas over the labels file) as the device-side
+    reduction: per id the most frequent class of its label lines (smallest on ties), ids per class --
+    including ids whose tracks were deleted."""
+    from collections import Counter
+    from strongsort_yolo_b200.results import label_lines, results_from_tracks
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.SyntheticStream(width=1280, height=720, n_persistent=30, seed=21, render=False,
+                               drop_rate=0.05, spurious_rate=0.03)
+    bank = FeatureBank(seed=4)
+    rng = np.random.default_rng(0)
+    gpu = StrongSORT(max_age=4, max_tracks=256, max_dets=64)
+    img = np.zeros((720, 1280, 3), dtype=np.uint8)
+    lines = []
+    for f in range(50):
+        fr = st.next_frame()
+        keep = np.ones(len(fr.dets), bool)
+        if 15 <= f < 25:
+            keep = fr.gt_ids % 4 != 0                       # tracks die and their ids must keep counting
+        d, ids = fr.dets[keep].copy(), fr.gt_ids[keep]
+        base = np.where(ids >= 0, ids % 5, 7)
+        noise = rng.random(len(d)) < 0.3                    # a noisy classifier: ties and minority votes happen
+        d[:, 5] = np.where(noise, rng.integers(0, 9, len(d)), base)
+        rows = gpu.update(d, img, features=bank(ids))
+        lines += label_lines(results_from_tracks(rows, gpu.last_det_index, orig_shape=img.shape[:2]))
+    per_id = {}
+    for ln in lines:                                        # the reference's pandas logic, restated
+        _fid, cls, tid = ln.split()[:3]
+        per_id.setdefault(int(tid), []).append(int(cls))
+    want = Counter(Counter(sorted(v)).most_common(1)[0][0] for v in per_id.values())
+    assert len(per_id) > 30
+    assert gpu.class_counts() == dict(want)

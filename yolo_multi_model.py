@@ -24,7 +24,6 @@ import argparse
 import os
 import sys
 import time
-from collections import Counter
 from multiprocessing import get_context
 
 import numpy as np
@@ -66,6 +65,12 @@ def _frames(source):
 
 
 def process_video(args):
+    """One worker = one source = one GPU stream (reference :244-339 without the cv2 drawing / imshow /
+    VideoWriter).  The loop is a stream: frame k's host->device copy, detector
+    post-process and OSNet run while frame k-1 is being associated (``update_pipelined``), the labels
+    file is opened ONCE (the reference reopens it per frame, :39), and ``--count`` is a reduction over
+    the device track table (``class_counts``) instead of re-parsing the whole labels file with pandas
+    every frame (:288, O(frames^2))."""
     print(args)                                                       # reference :245
     source, track_, count_, gpu = args["source"], args["track"], args["count"], args["gpu"]
     import torch
@@ -73,40 +78,64 @@ def process_video(args):
     from strongsort_yolo_b200.results import Boxes, Results, label_lines, results_from_tracks
     from strongsort_yolo_b200.strong_sort import StrongSORT
     dev = f"cuda:{gpu}"
+    torch.cuda.set_device(gpu)
     name = os.path.splitext(os.path.basename(source.replace(":", "_")))[0]
     os.makedirs("output", exist_ok=True)
     labels_path = os.path.abspath(f"./output/{name}_labels.txt")
-    tracker = StrongSORT(device=dev) if track_ else None
-    nms = yolo.YoloNMS(num_classes=80, max_anchors=8400, device=dev)
-    rng = np.random.default_rng(0)
-    class_votes = {}            # track id -> Counter of classes (the --count overlay, :284-309)
-    t0, n_frames = time.time(), 0
     if not track_ and count_:
         print("[INFO] count works only when objects are tracking.. so use: --track --count")   # :281
         return
+    tracker = StrongSORT(device=dev) if track_ else None
+    nms = yolo.YoloNMS(num_classes=80, max_anchors=8400, device=dev)
+    rng = np.random.default_rng(0)
+    t0, n_frames, n_rows = time.time(), 0, 0
+    pending = []                 # (rows, det_index, shape) of frames whose results arrive one call later
+    pin = None
+
+    def emit(labels, rows, det_index, shape):
+        nonlocal n_rows
+        res = results_from_tracks(rows, det_index, orig_shape=shape)
+        lines = label_lines(res)
+        n_rows += len(lines)
+        labels.writelines(lines)
+
     with open(labels_path, "a") as labels:                            # opened once, not per frame
         for img, dets in _frames(source):
             n_frames += 1
-            # detector post-process on the GPU: decoded head -> conf filter -> NMS
+            # detector post-process on the GPU: decoded head -> conf filter -> class-aware NMS
             head = yolo.synth_head(dets, num_classes=80, num_anchors=8400, rng=rng)
             det = nms.detect(torch.as_tensor(head).to(dev))
-            if track_:
-                rows = tracker.update(det[:, :6], img)
-                res = results_from_tracks(rows, tracker.last_det_index, orig_shape=img.shape[:2])
-            else:
+            if not track_:
                 res = Results(Boxes(det[:, :4], det[:, 4], det[:, 5], None), {0: "person"})
-            labels.writelines(label_lines(res))
-            if count_ and res.boxes.id is not None:
-                for tid, c in zip(res.boxes.id, res.boxes.cls):
-                    class_votes.setdefault(int(tid), Counter())[int(c)] += 1
+                labels.writelines(label_lines(res))
+            elif len(det) == 0:
+                # upstream's stream loop: no detections -> increment_ages() instead of update()
+                rows = tracker.flush_pipelined()
+                if rows is not None and pending:
+                    emit(labels, rows, tracker.last_det_index, pending.pop(0))
+                tracker.increment_ages()
+            else:
+                if pin is None or tuple(pin.shape) != tuple(img.shape):
+                    pin = [torch.empty(img.shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
+                slot = pin[n_frames & 1]                              # the copy of frame k-1 may still be in flight
+                slot.copy_(torch.from_numpy(img))
+                rows = tracker.update_pipelined(det[:, :6], slot)     # rows of the PREVIOUS frame
+                pending.append(img.shape[:2])
+                if rows is not None:
+                    emit(labels, rows, tracker.last_det_index, pending.pop(0))
             if n_frames % 10 == 0:
                 el = time.time() - t0
                 print(f"[{name}] FPS: {10 / el:.2f}", flush=True)     # reference :320-328
                 t0 = time.time()
+                if count_:
+                    print(f"[{name}] count: {dict(sorted(tracker.class_counts().items()))}", flush=True)
+        if track_:
+            rows = tracker.flush_pipelined()
+            if rows is not None and pending:
+                emit(labels, rows, tracker.last_det_index, pending.pop(0))
     if count_:
-        per_class = Counter(v.most_common(1)[0][0] for v in class_votes.values())
-        print(f"[{name}] count: {dict(sorted(per_class.items()))}")
-    print(f"[{name}] {n_frames} frames -> {labels_path}")
+        print(f"[{name}] count: {dict(sorted(tracker.class_counts().items()))}")
+    print(f"[{name}] {n_frames} frames, {n_rows} label rows -> {labels_path}")
 
 
 if __name__ == "__main__":
