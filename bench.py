@@ -456,6 +456,34 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     final_next_id = int(trk.last_counts[3])
     res["n_cross"] = len(gal.report()) if gal is not None else None
 
+    # ---------------- config C5's optional exchange, same invocation (N > 1): overhead of the shared gallery ----
+    if world > 1 and not args.shared_gallery and CFG == "C2":
+        trkg = StrongSORT(device=str(device), **trk_kw)
+        galg = ssb_dist.SharedGallery(trkg)
+        K2 = min(K, 60)
+        for i in range(W):
+            trkg.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+            galg.step()
+        trkg.flush_pipelined()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record(trkg.stream)
+        for k in range(K2):
+            trkg.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+            galg.step()
+        trkg.flush_pipelined()
+        trkg.stream.wait_stream(galg.stream)
+        g1.record(trkg.stream)
+        barrier()
+        fps_g = world * K2 / (max_over_ranks(g0.elapsed_time(g1)) / 1000.0)
+        res["gallery"] = {"value": fps_g, "unit": UNIT, "steps": K2,
+                          "shared_gallery_overhead": 1.0 - fps_g / res["value"],
+                          "exchange": "one all_gather_into_tensor (NCCL over NVLink) of the packed export "
+                                      "[256 x 512 f32 features | 256 ids] per rank per frame, on a side stream",
+                          "nvlink_bytes_per_frame_per_rank": int((world - 1) * galg.t_max * (512 + 1) * 4),
+                          "cross_stream_matches_last_frame_rank0": len(galg.report())}
+        del trkg, galg
+
     # ---------------- ReID alone: roofline of the dominant kernels ------------------------------------
     i0 = W + K // 2
     n0 = int(dets_dev[i0].shape[0])
@@ -662,6 +690,8 @@ def main():
         }
         if "cpu" in r:
             line["cpu_baseline"] = r["cpu"]
+        if "gallery" in r:
+            line["shared_gallery"] = r["gallery"]
         if c4 is not None:
             line["configs"] = {"C4": c4}
         print(json.dumps(line), flush=True)

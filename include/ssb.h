@@ -238,6 +238,12 @@ int ssb_gallery_cross_match(const float *local_feat_dev, const int32_t *local_id
 int ssb_profile_enable(ssb_tracker *t, int on);
 int ssb_profile_read(ssb_tracker *t, float *ms_out9);
 
+/* the same match on the packed exchange layout: per rank [t_max * dim float32 | t_max int32 ids], so one
+ * collective moves a stream's whole export (dist.SharedGallery) */
+int ssb_gallery_cross_match_packed(const void *all_packed_dev, int n_ranks, int self_rank, int t_max, int dim,
+                                   float max_dist, int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
+                                   float *match_dist_out_dev, ssb_stream_t stream);
+
 /* ---- introspection for tests: copy the live track table (list order) ----- */
 /* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];
  * mean float64 [T,8]; cov [T,8,8]; feat float32 [T,dim]                     */

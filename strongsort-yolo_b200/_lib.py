@@ -18,7 +18,7 @@ SYMBOLS = [
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks", "ssb_debug_cost_ptrs", "ssb_tc_probe",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
-    "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_increment_ages",
+    "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_gallery_cross_match_packed", "ssb_increment_ages",
     "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes", "ssb_class_counts",
     "ssb_appearance_tc_scratch_bytes", "ssb_appearance_cost_tc", "ssb_appearance_use_tc",
 ]
@@ -103,6 +103,7 @@ def load():
     lib.ssb_camera_update.argtypes = [vp, C.POINTER(C.c_double), vp]
     lib.ssb_gallery_export.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ssb_gallery_cross_match.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp]
+    lib.ssb_gallery_cross_match_packed.argtypes = [vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp]
     lib.ssb_export_tracks.argtypes = [vp] * 11
     lib.ssb_tc_probe.argtypes = [vp, i32, i32, vp, i32, i32, vp, vp, vp]
     lib.ssb_debug_cost_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]

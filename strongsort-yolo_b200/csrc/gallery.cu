@@ -58,7 +58,8 @@ __global__ void gallery_copy_kernel(TrackTable tt, int D, int t_max, const int *
 __global__ void gallery_cross_match_kernel(const float *__restrict__ local, const int *__restrict__ local_ids,
                                            const float *__restrict__ all, const int *__restrict__ all_ids,
                                            int n_ranks, int self_rank, int t_max, int D, float max_dist,
-                                           int *__restrict__ m_rank, int *__restrict__ m_id, float *__restrict__ m_dist) {
+                                           int *__restrict__ m_rank, int *__restrict__ m_id, float *__restrict__ m_dist,
+                                           size_t feat_rank_stride, size_t ids_rank_stride) {
     const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
     __shared__ float s_d[32];
     __shared__ int s_j[32];
@@ -67,8 +68,9 @@ __global__ void gallery_cross_match_kernel(const float *__restrict__ local, cons
     if (local_ids[i] >= 0) {
         const float *f = local + (size_t)i * D;
         for (int j = warp; j < n_ranks * t_max; j += nw) {
-            if (j / t_max == self_rank || all_ids[j] < 0) continue;     // warp-uniform
-            const float *g = all + (size_t)j * D;
+            const int jr = j / t_max, jt = j - jr * t_max;
+            if (jr == self_rank || all_ids[jr * ids_rank_stride + jt] < 0) continue;     // warp-uniform
+            const float *g = all + jr * feat_rank_stride + (size_t)jt * D;
             float acc = 0.f;
             for (int k = lane * 4; k < D; k += 128) {
                 const float4 a = *reinterpret_cast<const float4 *>(f + k);
@@ -91,7 +93,7 @@ __global__ void gallery_cross_match_kernel(const float *__restrict__ local, cons
             if (s_j[w] >= 0 && (best_j < 0 || s_d[w] < best || (s_d[w] == best && s_j[w] < best_j))) { best = s_d[w]; best_j = s_j[w]; }
         const bool hit = best_j >= 0 && best <= max_dist;
         m_rank[i] = hit ? best_j / t_max : -1;
-        m_id[i] = hit ? all_ids[best_j] : -1;
+        m_id[i] = hit ? all_ids[(best_j / t_max) * ids_rank_stride + best_j % t_max] : -1;
         m_dist[i] = best_j >= 0 ? best : INFINITY;
     }
 }
@@ -123,7 +125,27 @@ extern "C" int ssb_gallery_cross_match(const float *local_feat_dev, const int32_
     }
     gallery_cross_match_kernel<<<t_max, 256, 0, (cudaStream_t)stream>>>(
         local_feat_dev, local_ids_dev, all_feat_dev, all_ids_dev, n_ranks, self_rank, t_max, dim, max_dist,
-        match_rank_out_dev, match_id_out_dev, match_dist_out_dev);
+        match_rank_out_dev, match_id_out_dev, match_dist_out_dev, (size_t)t_max * dim, (size_t)t_max);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+// The same match on the PACKED exchange buffer: per rank  [t_max * dim float32 features | t_max int32 ids]
+// (t_max * (dim + 1) 4-byte words), so that one collective (or one peer copy) moves a stream's whole export.
+extern "C" int ssb_gallery_cross_match_packed(const void *all_packed_dev, int n_ranks, int self_rank, int t_max, int dim,
+                                              float max_dist, int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
+                                              float *match_dist_out_dev, ssb_stream_t stream) {
+    if (!all_packed_dev || !match_rank_out_dev || !match_id_out_dev || !match_dist_out_dev) { ssb_set_error("null argument"); return -1; }
+    if (n_ranks < 1 || self_rank < 0 || self_rank >= n_ranks || t_max < 1 || dim % 128) {
+        ssb_set_error("bad gallery geometry (dim must be a multiple of 128)");
+        return -1;
+    }
+    const size_t L = (size_t)t_max * (dim + 1);
+    const float *base = (const float *)all_packed_dev;
+    const int *ids = (const int *)all_packed_dev + (size_t)t_max * dim;
+    gallery_cross_match_kernel<<<t_max, 256, 0, (cudaStream_t)stream>>>(
+        base + self_rank * L, ids + self_rank * L, base, ids, n_ranks, self_rank, t_max, dim, max_dist,
+        match_rank_out_dev, match_id_out_dev, match_dist_out_dev, L, L);
     SSB_CHECK_LAUNCH();
     return 0;
 }

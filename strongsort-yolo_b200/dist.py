@@ -60,6 +60,19 @@ def gather_tracks(local_feat, local_ids):
     return all_feat, all_ids
 
 
+def gather_packed(packed):
+    """ONE collective for a stream's whole export: packed [L] (features + ids as 4-byte words) -> [G, L]."""
+    import torch
+    import torch.distributed as dist
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return packed.unsqueeze(0)
+    world = dist.get_world_size()
+    flat = packed.contiguous().reshape(-1)
+    out = torch.empty(world * flat.numel(), dtype=packed.dtype, device=packed.device)
+    dist.all_gather_into_tensor(out, flat)                  # rank-major concatenation (NCCL and gloo)
+    return out.view(world, flat.numel())
+
+
 class SharedGallery:
     """Read-only cross-stream ReID gallery (BASELINE.json config C5): after a frame, ``step()`` exports
     this stream's confirmed tracks (csrc/gallery.cu), all-gathers every stream's export and matches
@@ -78,8 +91,13 @@ class SharedGallery:
         self.trk, self.t_max, self.max_dist = tracker, int(t_max), float(max_dist)
         dev, D = tracker.device, tracker.cfg.feat_dim
         z = lambda *shape, dt=torch.float32, fill=0: torch.full(shape, fill, dtype=dt, device=dev)
-        self._feat = [z(self.t_max, D) for _ in range(2)]
-        self._ids2 = [z(2 * self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
+        # packed export: [t_max * D features | t_max ids | t_max slot scratch] as 4-byte words; the first
+        # t_max * (D + 1) words are what travels (ONE all-gather per frame, 513 KiB per rank)
+        self._packed = [z(self.t_max * (D + 2), dt=torch.int32) for _ in range(2)]
+        self._feat = [p[:self.t_max * D].view(torch.float32).view(self.t_max, D) for p in self._packed]
+        self._ids2 = [p[self.t_max * D:] for p in self._packed]
+        for i2 in self._ids2:
+            i2.fill_(-1)
         self._count = [z(1, dt=torch.int32) for _ in range(2)]
         self._m_rank = [z(self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
         self._m_id = [z(self.t_max, dt=torch.int32, fill=-1) for _ in range(2)]
@@ -113,13 +131,14 @@ class SharedGallery:
                            "ssb_gallery_export")
             self.stream.wait_stream(trk.stream)
             with torch.cuda.stream(self.stream):
-                all_feat, all_ids = gather_tracks(feat, ids)
-                _lib.check(lib.ssb_gallery_cross_match(
-                    _lib.ptr(feat), _lib.ptr(ids), _lib.ptr(all_feat), _lib.ptr(all_ids),
-                    int(all_feat.shape[0]), self.rank if all_feat.shape[0] > 1 else 0, self.t_max,
-                    int(feat.shape[1]), self.max_dist, _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]),
-                    _lib.ptr(self._m_dist[b]), C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_cross_match")
-                self._all = (all_feat, all_ids)
+                D = int(feat.shape[1])
+                allp = gather_packed(self._packed[b][:self.t_max * (D + 1)])
+                G = int(allp.shape[0])
+                _lib.check(lib.ssb_gallery_cross_match_packed(
+                    _lib.ptr(allp), G, self.rank if G > 1 else 0, self.t_max, D, self.max_dist,
+                    _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]), _lib.ptr(self._m_dist[b]),
+                    C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_cross_match_packed")
+                self._all = allp
                 self._done[b].record(self.stream)
         self._last = b
         self._k += 1

@@ -41,6 +41,14 @@ def _worker(rank, world, port, q):
     for r in range(world):                                   # rank-major, bit-identical copies
         f_r, i_r = _export(r)
         assert np.array_equal(all_feat[r].numpy(), f_r) and np.array_equal(all_ids[r].numpy(), i_r)
+    # the packed layout SharedGallery exchanges with ONE collective: [T_MAX * D float32 | T_MAX int32] per rank
+    packed = torch.cat([torch.from_numpy(feat).reshape(-1).view(torch.int32), torch.from_numpy(ids)])
+    allp = dist.gather_packed(packed)
+    assert tuple(allp.shape) == (world, T_MAX * (D + 1))
+    for r in range(world):
+        f_r, i_r = _export(r)
+        assert np.array_equal(allp[r, :T_MAX * D].view(torch.float32).numpy().reshape(T_MAX, D), f_r)
+        assert np.array_equal(allp[r, T_MAX * D:].numpy(), i_r)
     m_rank, m_id, m_dist = gallery_np.cross_match(feat, ids, all_feat.numpy(), all_ids.numpy(), rank, 0.2)
     q.put((rank, m_rank.tolist(), m_id.tolist()))
     tdist.barrier()

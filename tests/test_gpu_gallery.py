@@ -69,6 +69,13 @@ def test_cross_match_matches_restatement(self_rank):
     live = all_ids[self_rank] >= 0
     np.testing.assert_allclose(m_dist.cpu().numpy()[live], w_dist[live], atol=2e-6)
     assert (w_rank[live] >= 0).sum() > 5            # the scenario does produce cross-stream matches
+    # the packed exchange layout ([T * D float32 | T int32 ids] per rank) gives the same answer
+    packed = torch.cat([af.reshape(G, -1).view(torch.int32), ai], dim=1).contiguous()
+    p_rank, p_id, p_dist = torch.zeros_like(m_rank), torch.zeros_like(m_id), torch.zeros_like(m_dist)
+    _lib.check(lib.ssb_gallery_cross_match_packed(P(packed), G, self_rank, T, D, 0.2, P(p_rank), P(p_id), P(p_dist),
+                                                  C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(p_rank, m_rank) and torch.equal(p_id, m_id) and torch.equal(p_dist, m_dist)
 
 
 def test_cross_match_against_committed_golden(golden_dir):
