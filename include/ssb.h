@@ -89,31 +89,14 @@ int ssb_increment_ages(ssb_tracker *t, ssb_stream_t stream);
  * table: out_dev int32 [80]; ids of deleted tracks keep counting.  Classes >= 80 share the last bin. */
 int ssb_class_counts(ssb_tracker *t, int32_t *out_dev, ssb_stream_t stream);
 
-/* ---- ReID weights (OSNet-x0.25, BN folded by the host; see weights.py) --- */
-int ssb_reid_num_tensors(void);
-/* fills sizes[ssb_reid_num_tensors()] with the element count of each folded
- * tensor in canonical order */
-int ssb_reid_tensor_sizes(int64_t *sizes);
-int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const int64_t *sizes, int n);
-
-/* tensor-core ReID (csrc/reid_tc.cu, csrc/reid_tc3.cu): fp16 hi/lo operand blob built by
- * weights.pack_tc(); block_offsets[n_blocks] are byte offsets of the sections, each
- * >= ssb_reid_tc_weight_bytes(i) bytes and 128-byte aligned: 0..5 OSBlocks with the LightConvs
- * as 9 shifted GEMMs, 6..7 transition layers, 8 tail, 9 stem, and (n_blocks == 16) 10..15 the
- * OSBlocks with pointwise-GEMM + fp32-depthwise LightConvs.  Setting them switches
- * ssb_reid/ssb_update to the tcgen05 path (mode 2 when sections 10..15 are present, else 1);
- * ssb_reid_use_tc(t, mode): 0 = fp32 SIMT baseline, 1 = 9-tap OSBlocks, 2 = pointwise/depthwise
- * OSBlocks.  ssb_reid_block's use_tc takes the same mode values. */
+/* ---- ReID weights (OSNet-x0.25, BN folded by the host; see weights.py) ---
+ * fp16 hi/lo operand blob built by weights.pack_tc(); block_offsets[16] are byte offsets of the sections,
+ * each >= ssb_reid_tc_weight_bytes(i) bytes and 128-byte aligned: 0..5 the OSBlocks in the 9-tap layout
+ * (used by the A/B baseline of libssb_dbg.so only), 6..7 transition layers, 8 tail, 9 stem, 10..15 the
+ * OSBlocks with pointwise-GEMM + fp32-depthwise LightConvs (csrc/reid_tc4.cu). */
 int64_t ssb_reid_tc_weight_bytes(int section);
 int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
                             int n_blocks);
-int ssb_reid_use_tc(ssb_tracker *t, int enable);
-/* one OSBlock on caller arrays (parity tests): x float32 NHWC [n][H][W][cin] */
-int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, float *y_dev, int n, int use_tc,
-                   ssb_stream_t stream);
-/* diagnostic: CTA 0 of every tensor-core OSBlock launch writes clock64() phase stamps into
- * buf_dev (int64[64], [0] = count); NULL switches it off (default) */
-int ssb_reid_tc_debug(void *buf_dev);
 /* copies the tensor-core path's device status word (0 = ok) to the host; synchronises */
 int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream);
 
@@ -250,19 +233,6 @@ int ssb_gallery_cross_match_packed(const void *all_packed_dev, int n_ranks, int 
 int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, int32_t *hits,
                       int32_t *age, int32_t *tsu, int32_t *gallery_len, double *mean,
                       double *cov, float *feat, ssb_stream_t stream);
-/* per-frame association trace of the LAST ssb_update (device buffers, valid
- * until the next update): appearance cost [nA_rows, n] float32 is NOT kept;
- * the gated/clamped stage-A cost matrix float64 [rows_a, n] and the stage-B
- * matrix [rows_b, cols_b] are.  dims_out int32 [4] = rows_a, cols_a, rows_b,
- * cols_b (device).                                                          */
-int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev, const double **cost_b_dev,
-                        const int32_t **dims_dev);
-
-/* ---- diagnostic: one tcgen05 GEMM tile in the operand layout of the ReID kernels
- * D[128][n] (f32) = A[shift:shift+128][k] (f16) * B[n][k]^T (f16); status!=0: timeout */
-int ssb_tc_probe(const void *a_dev, int a_rows, int shift, const void *b_dev, int n, int k,
-                 float *d_dev, int32_t *status_dev, ssb_stream_t stream);
-
 #ifdef __cplusplus
 }
 #endif

@@ -227,7 +227,6 @@ extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n,
     if (rc || n == 0) return rc;
     if (!img_dev) return 0;                         // caller supplies embeddings to ssb_associate
     if (pitch < 3 * w) { ssb_set_error("bad pitch"); return -1; }
-    if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
     return ssb_reid_forward(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
 }
 
@@ -269,7 +268,7 @@ extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const ui
                           int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
     if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
     if (!feats_dev && n > 0 && !img_dev) { ssb_set_error("null image"); return -1; }
-    if (!feats_dev && img_dev && n >= 48 && t->use_tc && t->w_blob && pitch >= 3 * w) {
+    if (!feats_dev && img_dev && n >= 48 && t->use_tc && t->w_tc && pitch >= 3 * w) {
         int rc = ssb_embed(t, 0, dets_dev, n, nullptr, h, w, pitch, stream);          // detection prep only
         if (rc) return rc;
         rc = reid_forward_split(t, img_dev, h, w, pitch, t->fs.det_box, n, t->fs.feats, (cudaStream_t)stream);
@@ -285,7 +284,6 @@ extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, in
                         const int32_t *boxes_dev, int n, float *feats_out_dev, ssb_stream_t stream) {
     if (!t || !img_dev || !feats_out_dev) { ssb_set_error("null argument"); return -1; }
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
-    if (!t->w_blob) { ssb_set_error("ReID weights not set (ssb_reid_set_weights)"); return -1; }
     if (n == 0) return 0;
     if (n >= 48 && t->use_tc && pitch >= 3 * w)
         return reid_forward_split(t, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
@@ -299,6 +297,7 @@ extern "C" int ssb_export_tracks(ssb_tracker *t, int32_t *ids, int32_t *state, i
     return ssb_launch_export(t, ids, state, hits, age, tsu, gallery_len, mean, cov, feat, (cudaStream_t)stream);
 }
 
+#ifdef SSB_BASELINES
 extern "C" int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev,
                                    const double **cost_b_dev, const int32_t **dims_dev) {
     if (!t) { ssb_set_error("null handle"); return -1; }
@@ -307,3 +306,4 @@ extern "C" int ssb_debug_cost_ptrs(ssb_tracker *t, const double **cost_a_dev,
     if (dims_dev) *dims_dev = t->fs.cnt + FC_ROWS_A;
     return 0;
 }
+#endif

@@ -10,6 +10,8 @@
 // baseline the tensor-core path (reid_tc.cu) is validated against.
 #include "ssb_common.cuh"
 
+#ifdef SSB_BASELINES        // A/B baselines: libssb_dbg.so only (build.py)
+
 // ---------------------------------------------------------------------------
 // architecture walk shared by host packer (weights.py mirrors it) and runtime
 // ---------------------------------------------------------------------------
@@ -64,12 +66,8 @@ extern "C" int ssb_reid_set_weights(ssb_tracker *t, const float *blob_dev, const
     return 0;
 }
 
-// per-crop activation floats: A,B,DS (131072 each), X1,T0,T1,PW,X2 (32768 each), small
 #define REID_BIG 131072
 #define REID_MID 32768
-int64_t ssb_reid_ws_floats(int max_dets) {
-    return (int64_t)max_dets * (3 * REID_BIG + 5 * REID_MID + 1024) + 1024;
-}
 
 // ---------------------------------------------------------------------------
 // stem: crop + resize + normalise + conv7x7 s2 + ReLU + maxpool3x3 s2  (fused)
@@ -477,34 +475,11 @@ static int reid_block(ssb_tracker *t, int b, const float *cur, float *nxt, int n
     return reid_block_simt(t, b, cur, nxt, n, Hc, Wc, B, st);
 }
 
-// mode 3 (default): every activation between kernels is a pair of fp16 operand planes (reid_tc4.cu):
-// stem -> K0 -> K1 -> transition -> K2 -> K3 -> transition -> K4 -> K5 -> tail, 11 launches
-static int reid_forward_planes(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
-                               int n, float *feats_out, cudaStream_t st) {
-    float *A, *Bf;
-    (void)reid_bufs(t, slot, n, &A, &Bf);
-    const unsigned char *W = t->w_tc;
-    int rc = ssb_reid_tc_stem(img, h, w, pitch, boxes, W + t->w_tc_off[9], A, n, t->tc_status, st, 1);
-    if (rc) return rc;
-    float *cur = A, *nxt = Bf;
-    for (int b = 0; b < 6; b++) {
-        rc = ssb_reid_tc4_block(b, cur, nxt, W + t->w_tc_off[10 + b], n, t->tc_status, st);
-        if (rc) return rc;
-        { float *tmp = cur; cur = nxt; nxt = tmp; }
-        if (b == 1 || b == 3) {
-            const int a = b == 1 ? 0 : 1;
-            rc = ssb_reid_tc_aux(a, cur, nxt, W + t->w_tc_off[6 + a], n, t->tc_status, st, 1);
-            if (rc) return rc;
-            { float *tmp = cur; cur = nxt; nxt = tmp; }
-        }
-    }
-    return ssb_reid_tc_aux(2, cur, feats_out, W + t->w_tc_off[8], n, t->tc_status, st, 1);
-}
-
-int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
-                     int n, float *feats_out, cudaStream_t st) {
+// modes 0 (fp32 SIMT), 1 (9-tap tcgen05 OSBlocks), 2 (round-1 pointwise/depthwise OSBlocks): float32 NHWC activations
+int ssb_reid_forward_baseline(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+                              int n, float *feats_out, cudaStream_t st) {
     if (n <= 0) return 0;
-    if (t->use_tc == 3) return reid_forward_planes(t, slot, img, h, w, pitch, boxes, n, feats_out, st);
+    if (!t->w_blob) { ssb_set_error("fp32 ReID weights not set (ssb_reid_set_weights)"); return -1; }
     { int rc = reid_init_attrs(); if (rc) return rc; }
     const float *W = t->w_blob;
     const int64_t *off = t->w_off;
@@ -561,36 +536,6 @@ int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w,
     return 0;
 }
 
-// ---- tensor-core weights + single-block entry point (parity tests) ------------
-extern "C" int64_t ssb_reid_tc_weight_bytes(int section) {
-    if (section >= 10) return ssb_reid_tc3_block_bytes(section - 10);
-    return section < 6 ? ssb_reid_tc_block_bytes(section) : ssb_reid_tc_aux_bytes(section - 6);
-}
-
-extern "C" int ssb_reid_set_weights_tc(ssb_tracker *t, const void *blob_dev, const int64_t *block_offsets,
-                                       int n_blocks) {
-    if (!t || !blob_dev || !block_offsets) { ssb_set_error("null argument"); return -1; }
-    if (n_blocks != 10 && n_blocks != 16) {
-        ssb_set_error("expected 10 sections (6 OSBlocks, 2 transitions, tail, stem) or 16 (+ 6 pointwise/depthwise OSBlocks), got %d", n_blocks);
-        return -1;
-    }
-    for (int b = 0; b < n_blocks; b++) {
-        if (block_offsets[b] % 128 != 0) { ssb_set_error("section %d offset not 128-byte aligned", b); return -1; }
-        const int64_t need = ssb_reid_tc_weight_bytes(b);
-        if (b < n_blocks - 1 && block_offsets[b + 1] - block_offsets[b] < need) {
-            ssb_set_error("section %d too small", b);
-            return -1;
-        }
-        t->w_tc_off[b] = block_offsets[b];
-    }
-    if (((uintptr_t)blob_dev & 127) != 0) { ssb_set_error("tc blob must be 128-byte aligned"); return -1; }
-    t->w_tc = (const unsigned char *)blob_dev;
-    SSB_CHECK_CUDA(cudaMemset(t->tc_status, 0, 64 * sizeof(int)));      // the workspace arrives uninitialised
-    t->have_tc3 = n_blocks == 16;
-    t->use_tc = t->have_tc3 ? 3 : 1;
-    return 0;
-}
-
 extern "C" int ssb_reid_use_tc(ssb_tracker *t, int enable) {
     if (!t) { ssb_set_error("null handle"); return -1; }
     if (enable && !t->w_tc) { ssb_set_error("tensor-core ReID weights not set"); return -1; }
@@ -624,13 +569,6 @@ extern "C" int ssb_reid_block(ssb_tracker *t, int block, const float *x_dev, flo
     return reid_block(t, block, x_dev, y_dev, n, Hc, Wc, B, use_tc, (cudaStream_t)stream);
 }
 
-extern "C" int ssb_reid_tc_status(ssb_tracker *t, int32_t *status_host, ssb_stream_t stream) {
-    if (!t || !status_host) { ssb_set_error("null argument"); return -1; }
-    SSB_CHECK_CUDA(cudaMemcpyAsync(status_host, t->tc_status, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
-    SSB_CHECK_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
-    return 0;
-}
-
 // diagnostic: CTA 0 of every tensor-core OSBlock launch writes clock64() phase stamps to
 // buf_dev[0..63] (buf_dev[0] = number of stamps); pass NULL to switch it off.
 extern long long *g_ssb_tc_dbg;
@@ -638,3 +576,5 @@ extern "C" int ssb_reid_tc_debug(void *buf_dev) {
     g_ssb_tc_dbg = (long long *)buf_dev;
     return 0;
 }
+
+#endif  // SSB_BASELINES

@@ -155,6 +155,7 @@ __device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint6
     tc::mma_f16_ss(d, ah, bl, idesc, 1);
 }
 
+#ifdef SSB_BASELINES        // the 9-tap OSBlock kernel is an A/B baseline: libssb_dbg.so only
 struct Pipe {           // one mbarrier, bulk-synchronous use: every thread waits every commit
     uint64_t *bar;
     uint32_t phase;
@@ -646,12 +647,14 @@ osblock_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
 // the six OSBlocks of osnet_x0_25 (stage 2: 64x32, stage 3: 32x16, stage 4: 16x8)
 // ---------------------------------------------------------------------------
 //               CIN MID MIDP COUT  H   W   R HALO NB DOWN NSTAGE
+#endif  // SSB_BASELINES (the shapes below also size the weight blob sections of the product build)
 using Blk0 = BlkCfg<16, 16, 16, 64, 64, 32, 16, 4, 4, true, 2>;
 using Blk1 = BlkCfg<64, 16, 16, 64, 64, 32, 16, 4, 4, false, 2>;
 using Blk2 = BlkCfg<64, 24, 32, 96, 32, 16, 8, 4, 4, true, 2>;
 using Blk3 = BlkCfg<96, 24, 32, 96, 32, 16, 8, 4, 4, false, 2>;
 using Blk4 = BlkCfg<96, 32, 32, 128, 16, 8, 16, 0, 1, true, 1>;
 using Blk5 = BlkCfg<128, 32, 32, 128, 16, 8, 16, 0, 1, false, 1>;
+#ifdef SSB_BASELINES
 
 template <class C>
 int launch_block(const float *x, float *y, const unsigned char *w, int n, int *status, long long *dbg,
@@ -675,7 +678,7 @@ int launch_block(const float *x, float *y, const unsigned char *w, int n, int *s
     g_ssb_launches++;
     return 0;
 }
-
+#endif  // SSB_BASELINES
 
 // ---------------------------------------------------------------------------
 // 1x1 conv + ReLU (+ 2x2 average pool) on the tensor cores: the two transition
@@ -1285,6 +1288,7 @@ int64_t ssb_reid_tc_block_bytes(int b) {
 
 long long *g_ssb_tc_dbg = nullptr;      // device buffer of 64 int64 (ssb_reid_tc_debug), usually null
 
+#ifdef SSB_BASELINES
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,
                       cudaStream_t st) {
     long long *dbg = g_ssb_tc_dbg;
@@ -1299,6 +1303,7 @@ int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, i
     ssb_set_error("bad OSBlock index %d", b);
     return -1;
 }
+#endif
 
 static int num_sms() { return ssb_num_sms(); }
 

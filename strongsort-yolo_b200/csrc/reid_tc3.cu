@@ -23,6 +23,7 @@
 // crop per CTA, the bands of a crop form a cluster (DSMEM reduction of the ChannelGate's
 // global average pool), gate folded into per-stream scaled copies of conv3's weights,
 // conv3 + downsample accumulated in TMEM, residual + ReLU in the final epilogue.
+#ifdef SSB_BASELINES        // round-1 OSBlock kernel, kept as an A/B baseline: libssb_dbg.so only
 #include <cooperative_groups.h>
 
 #include "ssb_common.cuh"
@@ -786,3 +787,5 @@ int ssb_reid_tc3_block(int b, const float *x, float *y, const unsigned char *w, 
     ssb_set_error("bad OSBlock index %d", b);
     return -1;
 }
+
+#endif  // SSB_BASELINES

@@ -3,6 +3,7 @@
 // moving the descriptor's start address).  tests/test_gpu_tc.py checks it
 // against a float32 matmul; it exists to pin the descriptor encodings of
 // tc_common.cuh on real hardware before the fused kernels rely on them.
+#ifdef SSB_BASELINES        // diagnostic: libssb_dbg.so only
 #include "ssb_common.cuh"
 #include "tc_common.cuh"
 
@@ -77,3 +78,5 @@ extern "C" int ssb_tc_probe(const void *a_dev, int a_rows, int shift, const void
     SSB_CHECK_LAUNCH();
     return 0;
 }
+
+#endif  // SSB_BASELINES

@@ -121,7 +121,8 @@ class SharedGallery:
         """export (tracker stream) -> all-gather -> match (side stream); results stay on the device
         (``report()`` waits for and reads them)."""
         C, torch, _lib = self._C, self._torch, self._lib_mod
-        lib, trk, b = _lib.load(), self.trk, self._k & 1
+        trk, b = self.trk, self._k & 1
+        lib = trk._lib                      # the library that owns the tracker handle
         feat, ids2, ids = self._feat[b], self._ids2[b], self._ids2[b][:self.t_max]
         with torch.cuda.device(trk.device):
             with torch.cuda.stream(trk.stream):

@@ -28,10 +28,13 @@ class StrongSORT:
     def __init__(self, model_weights=None, device="cuda:0", fp16=False,
                  max_dist=0.2, max_iou_distance=0.7, max_age=30, n_init=3,
                  nn_budget=100, mc_lambda=0.995, ema_alpha=0.9,
-                 max_tracks=1024, max_dets=512, reid_backend="tc"):
+                 max_tracks=1024, max_dets=512, reid_backend="tc", debug=False):
+        """``reid_backend`` other than "tc" and ``debug=True`` (``reid_block``, ``debug_costs``, phase stamps) load
+        libssb_dbg.so -- the product library libssb.so carries neither the baselines nor the diagnostics."""
         torch = _lib.require_cuda()
         self._torch = torch
-        self._lib = _lib.load()
+        self._debug = bool(debug) or reid_backend != "tc"
+        self._lib = _lib.load(debug=self._debug)
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise _lib.SsbError("StrongSORT(device=...) must be a CUDA device")
@@ -54,15 +57,16 @@ class StrongSORT:
             _lib.check(self._lib.ssb_create(C.byref(cfg), C.c_void_p(base), nbytes, C.byref(h)),
                        "ssb_create")
             self._h = h
-            # ReID weights
+            # ReID weights: fp16 hi/lo operand blob of the tensor-core kernels (+ the fp32 blob of the
+            # SIMT baseline when the debug library is loaded)
             sd = _weights.load_state_dict(model_weights)
-            blob, sizes = _weights.pack(_weights.fold(sd))
-            self._w_blob = torch.from_numpy(blob).to(self.device)
-            self._w_sizes = (C.c_int64 * len(sizes))(*[int(s) for s in sizes])
-            _lib.check(self._lib.ssb_reid_set_weights(self._h, _lib.ptr(self._w_blob),
-                                                      self._w_sizes, len(sizes)),
-                       "ssb_reid_set_weights")
-            # tensor-core OSBlocks: fp16 hi/lo operand blob (csrc/reid_tc.cu)
+            if self._debug:
+                blob, sizes = _weights.pack(_weights.fold(sd))
+                self._w_blob = torch.from_numpy(blob).to(self.device)
+                self._w_sizes = (C.c_int64 * len(sizes))(*[int(s) for s in sizes])
+                _lib.check(self._lib.ssb_reid_set_weights(self._h, _lib.ptr(self._w_blob),
+                                                          self._w_sizes, len(sizes)),
+                           "ssb_reid_set_weights")
             tc_blob, tc_off = _weights.pack_tc(_weights.fold(sd))
             self._w_tc = torch.from_numpy(tc_blob).to(self.device)
             self._w_tc_off = (C.c_int64 * len(tc_off))(*[int(o) for o in tc_off])
@@ -104,8 +108,16 @@ class StrongSORT:
         modes = {"simt": 0, "tc9": 1, "tc3": 2, "tc": 3}
         if name not in modes:
             raise ValueError("reid_backend must be 'tc', 'tc3', 'tc9' or 'simt'")
-        _lib.check(self._lib.ssb_reid_use_tc(self._h, modes[name]), "ssb_reid_use_tc")
+        if not self._debug:
+            if name != "tc":
+                raise _lib.SsbError("the baselines live in libssb_dbg.so: construct StrongSORT(debug=True)")
+        else:
+            _lib.check(self._lib.ssb_reid_use_tc(self._h, modes[name]), "ssb_reid_use_tc")
         self.reid_backend = name
+
+    def _need_debug(self, what):
+        if not self._debug:
+            raise _lib.SsbError(f"{what} needs libssb_dbg.so: construct StrongSORT(debug=True)")
 
     def reid_tc_status(self):
         """0 when no tensor-core barrier wait ever timed out."""
@@ -118,6 +130,7 @@ class StrongSORT:
         """One OSBlock on a float32 NHWC array [n,H,W,cin] (parity tests); use_tc: False/0 simt,
         1 'tc9' kernel, 2 'tc3' kernel, True/3 'tc' kernel (operand planes; converted in and out)."""
         use_tc = 3 if use_tc is True else int(use_tc)
+        self._need_debug("reid_block")
         torch = self._torch
         couts = [64, 64, 96, 96, 128, 128]
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
@@ -405,6 +418,7 @@ class StrongSORT:
 
     def debug_costs(self):
         """(cost_a [rows_a, cols_a], cost_b [rows_b, cols_b]) of the last update."""
+        self._need_debug("debug_costs")
         pa, pb, pd = C.c_void_p(), C.c_void_p(), C.c_void_p()
         _lib.check(self._lib.ssb_debug_cost_ptrs(self._h, C.byref(pa), C.byref(pb), C.byref(pd)),
                    "ssb_debug_cost_ptrs")

@@ -18,19 +18,44 @@ def lib():
     return _lib.load()
 
 
-def _declared():
-    src = open(os.path.join(ROOT, "include", "ssb.h")).read()
+@pytest.fixture(scope="module")
+def lib_dbg(lib):
+    from strongsort_yolo_b200 import _lib
+    return _lib.load(debug=True)
+
+
+def _declared(header="ssb.h"):
+    src = open(os.path.join(ROOT, "include", header)).read()
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     return sorted(set(re.findall(r"\b(ssb_[a-z0-9_]+)\s*\(", src)))
 
 
+def _exported(path):
+    import subprocess
+    out = subprocess.run(["nm", "-D", "--defined-only", path], capture_output=True, text=True, check=True).stdout
+    return sorted({ln.split()[-1] for ln in out.splitlines() if ln.split()[-1].startswith("ssb_") and " T " in ln})
+
+
 def test_exports_match_header(lib):
+    """libssb.so exports exactly the extern "C" entry points include/ssb.h declares -- the baselines and
+    diagnostics of include/ssb_debug.h are NOT in the product library."""
     from strongsort_yolo_b200 import _lib
     names = _declared()
     assert names, "no declarations parsed from include/ssb.h"
     assert sorted(_lib.SYMBOLS) == names
     for n in names:
         assert hasattr(lib, n), f"libssb.so does not export {n}"
+    extern_c = [n for n in _exported(_lib.LIB_PATH) if not n.startswith("_Z")]
+    assert sorted(set(extern_c) & set(_lib.DEBUG_SYMBOLS)) == []
+    assert set(names) <= set(extern_c)
+
+
+def test_debug_library_exports_the_debug_header(lib_dbg):
+    from strongsort_yolo_b200 import _lib
+    dbg = [n for n in _declared("ssb_debug.h") if n not in _declared()]
+    assert sorted(_lib.DEBUG_SYMBOLS) == dbg
+    for n in _lib.SYMBOLS + dbg:
+        assert hasattr(lib_dbg, n), f"libssb_dbg.so does not export {n}"
 
 
 def test_config_and_workspace_sizing(lib):
@@ -48,8 +73,9 @@ def test_config_and_workspace_sizing(lib):
     assert b"feat_dim" in lib.ssb_last_error()
 
 
-def test_weight_packing_matches_kernel_walk(lib, state_dict):
+def test_weight_packing_matches_kernel_walk(lib_dbg, state_dict):
     from strongsort_yolo_b200 import weights
+    lib = lib_dbg                                    # the fp32 blob belongs to the SIMT baseline
     tensors = weights.fold(state_dict)
     blob, sizes = weights.pack(tensors)
     n = lib.ssb_reid_num_tensors()

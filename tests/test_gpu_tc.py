@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ])
 def test_tc_probe_matches_matmul(N, K, a_rows, shift):
     from strongsort_yolo_b200 import _lib
-    lib = _lib.load()
+    lib = _lib.load(debug=True)          # ssb_tc_probe: include/ssb_debug.h
     rng = np.random.default_rng(N * 7 + K + shift)
     A = rng.normal(0, 1, (a_rows, K)).astype(np.float16)
     B = rng.normal(0, 1, (N, K)).astype(np.float16)

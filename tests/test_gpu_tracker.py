@@ -27,7 +27,7 @@ def _run_tracker_only(cfg, frames, seed, bank_seed, check_tables_every=1, **stre
     bank = FeatureBank(seed=bank_seed)
     ora = ss.StrongSORTOracle(None)
     ora.trace_enabled = True
-    gpu = StrongSORT(max_tracks=2048 if cfg == "C4" else 1024, max_dets=640)
+    gpu = StrongSORT(max_tracks=2048 if cfg == "C4" else 1024, max_dets=640, debug=True)     # debug_costs()
     img = np.zeros((st.H, st.W, 3), dtype=np.uint8)
     for f in range(frames):
         fr = st.next_frame()

@@ -18,9 +18,9 @@ from strongsort_yolo_b200.strong_sort import StrongSORT  # noqa: E402
 
 
 def main():
-    lib = _lib.load()
+    lib = _lib.load(debug=True)
     P = lambda t: C.c_void_p(t.data_ptr())
-    trk = StrongSORT()
+    trk = StrongSORT(debug=True)
     st = synth.make_stream("C2")
     fr = [st.next_frame() for _ in range(3)][-1]
     n = len(fr.dets)

@@ -16,8 +16,8 @@ from strongsort_yolo_b200.strong_sort import StrongSORT, _HDR_BYTES  # noqa: E40
 def main():
     cfg = sys.argv[1] if len(sys.argv) > 1 else "C2"
     nfr = int(sys.argv[2]) if len(sys.argv) > 2 else 16
-    lib = _lib.load()
-    trk = StrongSORT(max_tracks=2048, max_dets=640) if cfg == "C4" else StrongSORT()
+    lib = _lib.load(debug=True)
+    trk = StrongSORT(max_tracks=2048, max_dets=640) if cfg == "C4" else StrongSORT(debug=True)
     st = synth.make_stream(cfg)
     frames = [st.next_frame() for _ in range(nfr)]
     imgs = [torch.from_numpy(f.img).cuda() for f in frames]

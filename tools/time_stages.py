@@ -33,11 +33,11 @@ def timeit(fn, reps=30, warm=5):
 
 
 def main():
-    lib = _lib.load()
+    lib = _lib.load(debug=True)           # baselines + phase stamps: libssb_dbg.so
     P = lambda t: C.c_void_p(t.data_ptr())
     ST = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
     out = {}
-    trk = StrongSORT()
+    trk = StrongSORT(debug=True)
     st = synth.make_stream("C2")
     frames = [st.next_frame() for _ in range(8)]
     for fr in frames:
