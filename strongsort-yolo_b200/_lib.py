@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libssb.so")
+LIB_PATH = os.environ.get("SSB_LIB") or os.path.join(HERE, "libssb.so")     # SSB_LIB: a tools/build_variants.py A/B build
 LIB_DBG_PATH = os.path.join(HERE, "libssb_dbg.so")
 
 # every symbol include/ssb.h declares (tests/test_abi.py checks the export list)

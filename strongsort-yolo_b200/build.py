@@ -65,6 +65,14 @@ def _build_one(lib, objdir, flags, srcs, force, verbose):
     return lib
 
 
+def build_variant(name, flags, verbose=False):
+    """A/B build of the product library with extra -D flags -> variants/libssb_<name>.so (tools/build_variants.py)."""
+    out = os.path.join(HERE, "variants", f"libssb_{name}.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    prod = [f for f in sources() if f not in DBG_ONLY]
+    return _build_one(out, os.path.join(HERE, "build_var_" + name), list(flags), prod, False, verbose)
+
+
 def build(force=False, verbose=False, debug=True):
     prod = [f for f in sources() if f not in DBG_ONLY]
     _build_one(LIB, os.path.join(HERE, "build"), [], prod, force, verbose)

@@ -97,7 +97,6 @@ struct B4 {
     static_assert(MID <= MIDP && COUT == 4 * MID && MIDP <= 32 && COUT * (MIDP / 8) <= THREADS, "OSBlock channel plan");
     static_assert(CG % 2 == 0 && (CG / 2) % CPW == 0 && W % XL == 0, "depthwise warp tasks");
     static_assert(SEG * TPS <= NWARPS, "depthwise warp tasks fit the CTA");
-    static_assert((NT * CG) % GROUPS == 0, "pointwise drain units divide the groups");
     static_assert(WALL_B + XS_B < (1 << 20), "mbarrier tx count");
     // global weight blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
     static constexpr int G_PAR = rup128_4(WALL_B);
@@ -391,11 +390,12 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
             }
             // ---- pointwise result: TMEM -> fp32 T own rows (+ edge rows into the neighbours' rings)
             {
-                constexpr int UPT = (C::NT * C::CG) / C::GROUPS;
+                constexpr int NU = C::NT * C::CG, UPT = (NU + C::GROUPS - 1) / C::GROUPS;
                 uint32_t ra_[UPT][4], rb_[UPT][4];
 #pragma unroll
                 for (int i = 0; i < UPT; i++) {
                     const int u = grp + i * C::GROUPS;
+                    if (u >= NU) continue;                        // warp-uniform
                     const int t = u / C::CG, cgi = u - t * C::CG;
                     if (!tc::mbar_wait(bar_tile + t, tile_par)) ok = false;
                     tc::fence_after_sync();
@@ -408,6 +408,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
 #pragma unroll
                 for (int i = 0; i < UPT; i++) {
                     const int u = grp + i * C::GROUPS;
+                    if (u >= NU) continue;
                     const int t = u / C::CG, cgi = u - t * C::CG;
                     const int p = t * 128 + quad * 32 + lane;
                     const int lr = p / C::W, col = p % C::W;
@@ -687,11 +688,28 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
 // ---------------------------------------------------------------------------
 // the six OSBlocks of osnet_x0_25 (stage 2: 64x32, stage 3: 32x16, stage 4: 16x8)
 // ---------------------------------------------------------------------------
+// Band geometry is a compile-time choice (tools/build_variants.py A/Bs them on the GPU):
+//   stage 2: SSB_S2_R = 8  -> 8 bands x 256 px, 256 threads, two CTAs per SM (default)
+//            SSB_S2_R = 16 -> 4 bands x 512 px, 512 threads, one CTA per SM
+//   stage 3: SSB_S3_R = 16 -> 2 bands x 256 px (default);  8 -> 4 bands x 128 px
+#ifndef SSB_S2_R
+#define SSB_S2_R 8
+#endif
+#ifndef SSB_S2_SPLIT
+#define SSB_S2_SPLIT false
+#endif
+#ifndef SSB_S3_R
+#define SSB_S3_R 16
+#endif
+#ifndef SSB_S3_SPLIT
+#define SSB_S3_SPLIT (SSB_S3_R == 16)
+#endif
+constexpr int S2_THREADS = SSB_S2_R == 8 ? 256 : 512, S2_MINB = SSB_S2_R == 8 ? 2 : 1, S2_SEG = SSB_S2_R == 8 ? 2 : 3;
 //            CIN MID MIDP COUT  H   W   R  NB  DOWN SEG THREADS MINB SPLIT
-using K0 = B4<16, 16, 16, 64, 64, 32, 8, 8, true, 2, 256, 2, false>;
-using K1 = B4<64, 16, 16, 64, 64, 32, 8, 8, false, 2, 256, 2, false>;
-using K2 = B4<64, 24, 32, 96, 32, 16, 16, 2, true, 4, 512, 1, true>;
-using K3 = B4<96, 24, 32, 96, 32, 16, 16, 2, false, 4, 512, 1, true>;
+using K0 = B4<16, 16, 16, 64, 64, 32, SSB_S2_R, 64 / SSB_S2_R, true, S2_SEG, S2_THREADS, S2_MINB, SSB_S2_SPLIT>;
+using K1 = B4<64, 16, 16, 64, 64, 32, SSB_S2_R, 64 / SSB_S2_R, false, S2_SEG, S2_THREADS, S2_MINB, SSB_S2_SPLIT>;
+using K2 = B4<64, 24, 32, 96, 32, 16, SSB_S3_R, 32 / SSB_S3_R, true, 4, 512, 1, SSB_S3_SPLIT>;
+using K3 = B4<96, 24, 32, 96, 32, 16, SSB_S3_R, 32 / SSB_S3_R, false, 4, 512, 1, SSB_S3_SPLIT>;
 using K4 = B4<96, 32, 32, 128, 16, 8, 16, 1, true, 7, 512, 1, false>;
 using K5 = B4<128, 32, 32, 128, 16, 8, 16, 1, false, 7, 512, 1, false>;
 

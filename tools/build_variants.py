@@ -1,0 +1,82 @@
+"""Build A/B variants of libssb.so (compile-time band geometry of the OSBlock kernels, csrc/reid_tc4.cu) into
+strongsort-yolo_b200/variants/ and, on the GPU box, time the ReID forward of each:
+
+  python tools/build_variants.py build                   # here (nvcc cross-compiles)
+  python tools/build_variants.py time > gpurun_out/variants.json     # on the B200 box
+"""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+VARIANTS = {
+    "s2r8": [],                                             # the default geometry
+    "s2r8split": ["-DSSB_S2_SPLIT=true"],
+    "s2r16": ["-DSSB_S2_R=16", "-DSSB_S2_SPLIT=true"],
+    "s3r8": ["-DSSB_S3_R=8"],
+    "s3r16nosplit": ["-DSSB_S3_SPLIT=false"],
+}
+
+
+def build():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_b", os.path.join(ROOT, "strongsort-yolo_b200", "build.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    for name, flags in VARIANTS.items():
+        print(b.build_variant(name, flags))
+
+
+def time_one():
+    """(child process, SSB_LIB set) ReID forward of one C2 frame: median us over 30 warm launches + parity vs the KAT."""
+    import ctypes as C
+    import numpy as np
+    import torch
+    sys.path.insert(0, ROOT)
+    from strongsort_yolo_b200 import _lib, synth
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    lib = _lib.load()
+    trk = StrongSORT()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "reid_kat.npz"))
+    emb = trk.extract_features(g["img"], g["boxes"])
+    ref = g["emb"]
+    err = float(np.max(np.abs(emb - ref) / np.abs(ref).max(axis=1, keepdims=True)))
+    fr = synth.make_stream("C2").next_frame()
+    n = len(fr.dets)
+    img = torch.from_numpy(fr.img).cuda()
+    dets = torch.from_numpy(fr.dets).cuda()
+    boxes = torch.zeros((n, 4), dtype=torch.int32, device="cuda")
+    feats = torch.zeros((n, 512), dtype=torch.float32, device="cuda")
+    P = lambda t: C.c_void_p(t.data_ptr())
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.ssb_crop_boxes(P(dets), n, 1080, 1920, P(boxes), st))
+    fn = lambda: _lib.check(lib.ssb_reid(trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), st))
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(30)]
+    for a, b in ev:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    t = sorted(a.elapsed_time(b) * 1e3 for a, b in ev)
+    print(json.dumps({"median_us": t[len(t) // 2], "min_us": t[0], "kat_err": err, "status": trk.reid_tc_status(), "n": n}))
+
+
+def time_all():
+    out = {}
+    for name in VARIANTS:
+        lib = os.path.join(ROOT, "strongsort-yolo_b200", "variants", f"libssb_{name}.so")
+        if not os.path.exists(lib):
+            continue
+        env = dict(os.environ, SSB_LIB=lib)
+        try:
+            p = subprocess.run([sys.executable, __file__, "time_one"], env=env, capture_output=True, text=True, timeout=240)
+            out[name] = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else {"error": p.stderr[-400:]}
+        except Exception as e:          # a hung variant must not take the others down
+            out[name] = {"error": repr(e)}
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    {"build": build, "time": time_all, "time_one": time_one}[sys.argv[1] if len(sys.argv) > 1 else "build"]()
