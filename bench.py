@@ -478,8 +478,11 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
         fps_g = world * K2 / (max_over_ranks(g0.elapsed_time(g1)) / 1000.0)
         res["gallery"] = {"value": fps_g, "unit": UNIT, "steps": K2,
                           "shared_gallery_overhead": 1.0 - fps_g / res["value"],
-                          "exchange": "one all_gather_into_tensor (NCCL over NVLink) of the packed export "
-                                      "[256 x 512 f32 features | 256 ids] per rank per frame, on a side stream",
+                          "exchange": ("peer memory: the match kernel pulls the other streams' packed exports "
+                                       "[256 x 512 f32 features | 256 ids] over NVLink itself (symmetric memory + "
+                                       "device-side barrier, no collective)" if galg.exchange == "peer" else
+                                       "one all_gather_into_tensor (NCCL over NVLink) of the packed export "
+                                       "[256 x 512 f32 features | 256 ids] per rank per frame") + ", on a side stream",
                           "nvlink_bytes_per_frame_per_rank": int((world - 1) * galg.t_max * (512 + 1) * 4),
                           "cross_stream_matches_last_frame_rank0": len(galg.report())}
         del trkg, galg

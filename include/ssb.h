@@ -227,6 +227,13 @@ int ssb_gallery_cross_match_packed(const void *all_packed_dev, int n_ranks, int 
                                    float max_dist, int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
                                    float *match_dist_out_dev, ssb_stream_t stream);
 
+/* the same match WITHOUT a collective: peer_ptrs_dev is a device array of n_ranks pointers, entry r = rank r's
+ * packed export in peer-accessible memory (torch symmetric-memory buffers: the kernel pulls the other streams'
+ * rows over NVLink itself, each foreign row crossing once); best_scratch_dev t_max uint64; dim == 512 */
+int ssb_gallery_peer_match(const void *peer_ptrs_dev, int n_ranks, int self_rank, int t_max, int dim, float max_dist,
+                           void *best_scratch_dev, int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
+                           float *match_dist_out_dev, ssb_stream_t stream);
+
 /* ---- introspection for tests: copy the live track table (list order) ----- */
 /* any pointer may be NULL.  ids/state/hits/age/tsu/gallery_len int32 [T];
  * mean float64 [T,8]; cov [T,8,8]; feat float32 [T,dim]                     */

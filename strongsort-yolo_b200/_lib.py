@@ -19,7 +19,7 @@ SYMBOLS = [
     "ssb_appearance_cost", "ssb_iou_cost", "ssb_lsap", "ssb_nms_scratch_bytes",
     "ssb_yolo_nms", "ssb_export_tracks",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
-    "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_gallery_cross_match_packed", "ssb_increment_ages",
+    "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_gallery_cross_match_packed", "ssb_gallery_peer_match", "ssb_increment_ages",
     "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes", "ssb_class_counts",
     "ssb_appearance_tc_scratch_bytes", "ssb_appearance_cost_tc", "ssb_appearance_use_tc",
 ]
@@ -105,6 +105,7 @@ def load(debug=False):
     lib.ssb_gallery_export.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.ssb_gallery_cross_match.argtypes = [vp, vp, vp, vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp]
     lib.ssb_gallery_cross_match_packed.argtypes = [vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp]
+    lib.ssb_gallery_peer_match.argtypes = [vp, i32, i32, i32, i32, C.c_float, vp, vp, vp, vp, vp]
     lib.ssb_export_tracks.argtypes = [vp] * 11
     names = list(SYMBOLS)
     if debug:

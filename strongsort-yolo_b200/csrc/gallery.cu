@@ -98,7 +98,130 @@ __global__ void gallery_cross_match_kernel(const float *__restrict__ local, cons
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Peer-memory exchange: the match reads every OTHER stream's packed export straight out of that GPU's memory
+// over NVLink (symmetric-memory peer pointers) -- no all-gather, no staging copy, no NCCL kernel.  A block owns
+// a tile of RT foreign rows: it pulls them across NVLink ONCE (coalesced 16-byte peer loads into shared
+// memory; the whole exchange moves (G - 1) * t_max * (D + 1) * 4 bytes per rank per frame = 3.6 MB at G = 8),
+// then sweeps all local tracks against the tile (local rows come from the local L2) and folds every distance
+// into a per-local-track 64-bit key (order-preserving distance bits << 32 | flat foreign index) with
+// atomicMin -- the same "lowest distance, then lowest rank / row" rule as gallery_cross_match_kernel, with the
+// same per-pair summation order, so both paths give identical results.
+// ---------------------------------------------------------------------------------------------------------
+#define GAL_RT 8
+__device__ __forceinline__ unsigned long long gal_key(float d, int j) {
+    unsigned u = __float_as_uint(d);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned)j;
+}
+__device__ __forceinline__ float gal_key_dist(unsigned long long k) {
+    unsigned u = (unsigned)(k >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+    return __uint_as_float(u);
+}
+
+__global__ void gallery_peer_init_kernel(unsigned long long *best, int t_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < t_max) best[i] = ~0ull;
+}
+
+__global__ void __launch_bounds__(256)
+gallery_peer_match_kernel(const unsigned long long *__restrict__ peer_ptrs, int n_ranks, int self_rank, int t_max, int D,
+                          unsigned long long *__restrict__ best) {
+    extern __shared__ float s_tile[];                  // [GAL_RT][D]
+    __shared__ int s_ids[GAL_RT];
+    const int tiles = (t_max + GAL_RT - 1) / GAL_RT;
+    int r = blockIdx.x / tiles;
+    const int j0 = (blockIdx.x - r * tiles) * GAL_RT;
+    if (r >= self_rank) r++;                           // the G - 1 foreign ranks
+    const float *peer = reinterpret_cast<const float *>(peer_ptrs[r]);
+    const int *peer_ids = reinterpret_cast<const int *>(peer) + (size_t)t_max * D;
+    const float *local = reinterpret_cast<const float *>(peer_ptrs[self_rank]);
+    const int *local_ids = reinterpret_cast<const int *>(local) + (size_t)t_max * D;
+    if (threadIdx.x < GAL_RT) s_ids[threadIdx.x] = j0 + threadIdx.x < t_max ? peer_ids[j0 + threadIdx.x] : -1;
+    __syncthreads();
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < GAL_RT; q++) any |= s_ids[q] >= 0;
+    if (!any) return;                                  // block-uniform: nothing exported in this tile
+    for (int e = threadIdx.x * 4; e < GAL_RT * D; e += blockDim.x * 4) {
+        const int q = e / D;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (s_ids[q] >= 0) v = *reinterpret_cast<const float4 *>(peer + (size_t)(j0 + q) * D + (e - q * D));     // NVLink
+        *reinterpret_cast<float4 *>(s_tile + e) = v;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < t_max; i += nw) {
+        if (local_ids[i] < 0) continue;                // warp-uniform
+        const float *f = local + (size_t)i * D;
+        float4 a[4];                                   // D = 512: lane l owns elements 4l + 128m .. + 3
+#pragma unroll
+        for (int m = 0; m < 4; m++) a[m] = *reinterpret_cast<const float4 *>(f + lane * 4 + 128 * m);
+#pragma unroll
+        for (int q = 0; q < GAL_RT; q++) {
+            if (s_ids[q] < 0) continue;
+            const float *g = s_tile + q * D;
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < 4; m++) {
+                const float4 b = *reinterpret_cast<const float4 *>(g + lane * 4 + 128 * m);
+                acc = fmaf(a[m].x, b.x, acc); acc = fmaf(a[m].y, b.y, acc);
+                acc = fmaf(a[m].z, b.z, acc); acc = fmaf(a[m].w, b.w, acc);
+            }
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+            if (lane == 0) atomicMin(best + i, gal_key(1.f - acc, r * t_max + j0 + q));
+        }
+    }
+}
+
+__global__ void gallery_peer_finalize_kernel(const unsigned long long *__restrict__ peer_ptrs, int self_rank, int t_max, int D,
+                                             float max_dist, const unsigned long long *__restrict__ best,
+                                             int *__restrict__ m_rank, int *__restrict__ m_id, float *__restrict__ m_dist) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t_max) return;
+    const unsigned long long k = best[i];
+    const bool found = k != ~0ull;
+    const int j = (int)(unsigned)k;
+    const float d = found ? gal_key_dist(k) : INFINITY;
+    const bool hit = found && d <= max_dist;
+    int id = -1;
+    if (hit) id = (reinterpret_cast<const int *>(peer_ptrs[j / t_max]) + (size_t)t_max * D)[j % t_max];
+    m_rank[i] = hit ? j / t_max : -1;
+    m_id[i] = id;
+    m_dist[i] = d;
+    (void)self_rank;
+}
+
 }  // namespace
+
+// peer_ptrs_dev: device array of n_ranks pointers, entry r = rank r's packed export [t_max * dim f32 | t_max int32 ids]
+// (peer-accessible memory: symmetric-memory buffers over NVLink, or plain device pointers in a single-GPU test);
+// best_scratch_dev: t_max uint64.  dim must be 512.
+extern "C" int ssb_gallery_peer_match(const void *peer_ptrs_dev, int n_ranks, int self_rank, int t_max, int dim, float max_dist,
+                                      void *best_scratch_dev, int32_t *match_rank_out_dev, int32_t *match_id_out_dev,
+                                      float *match_dist_out_dev, ssb_stream_t stream) {
+    if (!peer_ptrs_dev || !best_scratch_dev || !match_rank_out_dev || !match_id_out_dev || !match_dist_out_dev) { ssb_set_error("null argument"); return -1; }
+    if (n_ranks < 1 || self_rank < 0 || self_rank >= n_ranks || t_max < 1 || dim != 512) {
+        ssb_set_error("bad gallery geometry (dim must be 512)");
+        return -1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned long long *pp = (const unsigned long long *)peer_ptrs_dev;
+    unsigned long long *best = (unsigned long long *)best_scratch_dev;
+    gallery_peer_init_kernel<<<(t_max + 127) / 128, 128, 0, st>>>(best, t_max);
+    SSB_CHECK_LAUNCH();
+    if (n_ranks > 1) {
+        const int tiles = (t_max + GAL_RT - 1) / GAL_RT;
+        gallery_peer_match_kernel<<<(n_ranks - 1) * tiles, 256, GAL_RT * dim * sizeof(float), st>>>(pp, n_ranks, self_rank, t_max, dim, best);
+        SSB_CHECK_LAUNCH();
+    }
+    gallery_peer_finalize_kernel<<<(t_max + 127) / 128, 128, 0, st>>>(pp, self_rank, t_max, dim, max_dist, best, match_rank_out_dev,
+                                                                     match_id_out_dev, match_dist_out_dev);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
 
 extern "C" int ssb_gallery_export(ssb_tracker *t, int t_max, float *feat_out_dev, int32_t *ids_out_dev,
                                   int32_t *count_out_dev, ssb_stream_t stream) {

@@ -83,7 +83,11 @@ class SharedGallery:
     all-gather and the match run on a side stream with double-buffered exports, so the lock-step the
     collective imposes on the ranks never stalls the per-stream association."""
 
-    def __init__(self, tracker, t_max=256, max_dist=0.2):
+    def __init__(self, tracker, t_max=256, max_dist=0.2, exchange="auto"):
+        """exchange: "peer" -- the match kernel reads the other streams' exports straight out of their GPUs'
+        memory over NVLink (torch symmetric memory: peer pointers + a device-side signal-pad barrier; no
+        collective, no staging copy); "nccl" -- one all_gather_into_tensor of the packed export, then a local
+        match; "auto" -- peer when symmetric memory can be set up for the group, else nccl."""
         import ctypes as C
         import torch
         from . import _lib
@@ -92,8 +96,21 @@ class SharedGallery:
         dev, D = tracker.device, tracker.cfg.feat_dim
         z = lambda *shape, dt=torch.float32, fill=0: torch.full(shape, fill, dtype=dt, device=dev)
         # packed export: [t_max * D features | t_max ids | t_max slot scratch] as 4-byte words; the first
-        # t_max * (D + 1) words are what travels (ONE all-gather per frame, 513 KiB per rank)
-        self._packed = [z(self.t_max * (D + 2), dt=torch.int32) for _ in range(2)]
+        # t_max * (D + 1) words are what the other streams read (513 KiB per rank per frame)
+        self._symm = None
+        self.exchange = "nccl"
+        if exchange in ("auto", "peer"):
+            try:
+                self._symm = self._setup_peer(dev, D)
+                self.exchange = "peer"
+            except Exception as e:              # no symmetric memory here (single process, gloo, no P2P): NCCL path
+                if exchange == "peer":
+                    raise
+                self._symm_error = repr(e)
+        if self._symm is not None:
+            self._packed = self._symm["bufs"]
+        else:
+            self._packed = [z(self.t_max * (D + 2), dt=torch.int32) for _ in range(2)]
         self._feat = [p[:self.t_max * D].view(torch.float32).view(self.t_max, D) for p in self._packed]
         self._ids2 = [p[self.t_max * D:] for p in self._packed]
         for i2 in self._ids2:
@@ -108,6 +125,26 @@ class SharedGallery:
         self._k = 0
         self._last = 0
         self.rank = env_rank_world()[0]
+
+    def _setup_peer(self, dev, D):
+        """Two symmetric-memory export buffers (double-buffered) + their rendezvous handles."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        if not (dist.is_initialized() and dist.get_world_size() > 1 and dist.get_backend() == "nccl"):
+            raise RuntimeError("peer exchange needs an initialised NCCL group of more than one rank")
+        words = self.t_max * (D + 2)
+        bufs, hdls = [], []
+        with torch.cuda.device(dev):
+            for _ in range(2):
+                b = symm_mem.empty(words, dtype=torch.int32, device=dev)
+                b.zero_()
+                hdls.append(symm_mem.rendezvous(b, dist.group.WORLD))
+                bufs.append(b)
+            best = torch.zeros(self.t_max, dtype=torch.int64, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        return {"bufs": bufs, "hdls": hdls, "best": best}
 
     # views of the most recent step
     feat = property(lambda self: self._feat[self._last])
@@ -127,19 +164,32 @@ class SharedGallery:
         with torch.cuda.device(trk.device):
             with torch.cuda.stream(trk.stream):
                 trk.stream.wait_event(self._done[b])          # the side stream is done with this buffer
+                # peer exchange: the other ranks read buffer b during THEIR match of two frames ago; they were past it
+                # when last frame's barrier completed, which precedes last frame's match on our side stream
+                trk.stream.wait_event(self._done[b ^ 1])
                 _lib.check(lib.ssb_gallery_export(trk._h, self.t_max, _lib.ptr(feat), _lib.ptr(ids2),
                                                   _lib.ptr(self._count[b]), C.c_void_p(trk.stream.cuda_stream)),
                            "ssb_gallery_export")
             self.stream.wait_stream(trk.stream)
             with torch.cuda.stream(self.stream):
                 D = int(feat.shape[1])
-                allp = gather_packed(self._packed[b][:self.t_max * (D + 1)])
-                G = int(allp.shape[0])
-                _lib.check(lib.ssb_gallery_cross_match_packed(
-                    _lib.ptr(allp), G, self.rank if G > 1 else 0, self.t_max, D, self.max_dist,
-                    _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]), _lib.ptr(self._m_dist[b]),
-                    C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_cross_match_packed")
-                self._all = allp
+                if self._symm is not None:
+                    # every rank's export of this frame is complete once all ranks passed the barrier (device-side,
+                    # signal pads over NVLink); the kernel then pulls the foreign rows itself
+                    hdl = self._symm["hdls"][b]
+                    hdl.barrier(channel=0)
+                    _lib.check(lib.ssb_gallery_peer_match(
+                        C.c_void_p(int(hdl.buffer_ptrs_dev)), int(hdl.world_size), int(hdl.rank), self.t_max, D,
+                        self.max_dist, _lib.ptr(self._symm["best"]), _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]),
+                        _lib.ptr(self._m_dist[b]), C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_peer_match")
+                else:
+                    allp = gather_packed(self._packed[b][:self.t_max * (D + 1)])
+                    G = int(allp.shape[0])
+                    _lib.check(lib.ssb_gallery_cross_match_packed(
+                        _lib.ptr(allp), G, self.rank if G > 1 else 0, self.t_max, D, self.max_dist,
+                        _lib.ptr(self._m_rank[b]), _lib.ptr(self._m_id[b]), _lib.ptr(self._m_dist[b]),
+                        C.c_void_p(self.stream.cuda_stream)), "ssb_gallery_cross_match_packed")
+                    self._all = allp
                 self._done[b].record(self.stream)
         self._last = b
         self._k += 1

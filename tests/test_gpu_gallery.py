@@ -67,6 +67,7 @@ def test_cross_match_matches_restatement(self_rank):
     np.testing.assert_array_equal(m_rank.cpu().numpy(), w_rank)
     np.testing.assert_array_equal(m_id.cpu().numpy(), w_id)
     live = all_ids[self_rank] >= 0
+    live_t = torch.as_tensor(live).cuda()
     np.testing.assert_allclose(m_dist.cpu().numpy()[live], w_dist[live], atol=2e-6)
     assert (w_rank[live] >= 0).sum() > 5            # the scenario does produce cross-stream matches
     # the packed exchange layout ([T * D float32 | T int32 ids] per rank) gives the same answer
@@ -76,6 +77,15 @@ def test_cross_match_matches_restatement(self_rank):
                                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
     torch.cuda.synchronize()
     assert torch.equal(p_rank, m_rank) and torch.equal(p_id, m_id) and torch.equal(p_dist, m_dist)
+    # the collective-free kernel (foreign rows pulled through peer pointers; here all "peers" live on this GPU)
+    ptrs = torch.tensor([packed[g].data_ptr() for g in range(G)], dtype=torch.int64, device="cuda")
+    best = torch.zeros(T, dtype=torch.int64, device="cuda")
+    q_rank, q_id, q_dist = torch.zeros_like(m_rank), torch.zeros_like(m_id), torch.zeros_like(m_dist)
+    _lib.check(lib.ssb_gallery_peer_match(P(ptrs), G, self_rank, T, D, 0.2, P(best), P(q_rank), P(q_id), P(q_dist),
+                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    torch.cuda.synchronize()
+    assert torch.equal(q_rank, m_rank) and torch.equal(q_id, m_id)
+    assert torch.equal(q_dist[live_t], m_dist[live_t])
 
 
 def test_cross_match_against_committed_golden(golden_dir):
