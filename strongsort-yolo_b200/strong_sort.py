@@ -172,6 +172,16 @@ class StrongSORT:
         self._img_dev.copy_(src, non_blocking=True)      # on self.stream (set by caller)
         return self._img_dev
 
+    def prefetch(self, ori_img):
+        """Start the host->device copy of a frame NOW (asynchronously, on the tracker's stream) so that it overlaps
+        whatever the caller does before ``update(dets, ori_img)`` -- typically the detector post-process that
+        produces ``dets``.  ``update`` recognises the same frame object and skips its own copy."""
+        torch = self._torch
+        if torch.is_tensor(ori_img) and ori_img.is_cuda:
+            return
+        with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+            self._staged = (ori_img, self._stage_image(ori_img))
+
     def _after_producer(self, t, stream, caller):
         """A CUDA tensor handed in by the caller may still be pending on the caller's stream (e.g.
         YoloNMS output): order our stream after it and keep the allocator from recycling it.
@@ -242,7 +252,12 @@ class StrongSORT:
                 self._feats_dev[:n].copy_(f, non_blocking=False)
                 feats_ptr = _lib.ptr(self._feats_dev)
             elif n:
-                img_dev = self._stage_image(ori_img, caller)
+                staged = getattr(self, "_staged", None)
+                if staged is not None and staged[0] is ori_img:
+                    img_dev = staged[1]                      # prefetch() already enqueued the copy on this stream
+                else:
+                    img_dev = self._stage_image(ori_img, caller)
+            self._staged = None
             pitch = 3 * W
             _lib.check(lib.ssb_update(
                 self._h, _lib.ptr(self._dets_dev), n,

@@ -291,3 +291,17 @@ def test_class_counts_match_the_reference_count_logic():
     want = Counter(Counter(sorted(v)).most_common(1)[0][0] for v in per_id.values())
     assert len(per_id) > 30
     assert gpu.class_counts() == dict(want)
+
+
+def test_prefetch_overlaps_the_copy_and_changes_nothing():
+    import torch
+    from strongsort_yolo_b200.strong_sort import StrongSORT
+    st = synth.make_stream("C1")
+    frames = [st.next_frame() for _ in range(6)]
+    a = StrongSORT(max_tracks=64, max_dets=32)
+    want = [a.update(f.dets, f.img) for f in frames]
+    b = StrongSORT(max_tracks=64, max_dets=32)
+    for f, w in zip(frames, want):
+        pinned = torch.from_numpy(f.img).pin_memory()
+        b.prefetch(pinned)
+        np.testing.assert_array_equal(b.update(f.dets, pinned), w)
