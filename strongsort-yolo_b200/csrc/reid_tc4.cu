@@ -219,6 +219,12 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
     const uint32_t tmem = *s_tmem;
     int dbg_n = 0;
     auto stamp = [&]() { if (dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 63) dbg[1 + dbg_n++] = clock64(); };
+    // finer stamps of two layers (lc 1: a layer followed by another LightConv, lc 2: the last layer of a stream)
+    // into dbg[64..]: [64] = count
+    int dbg_f = 0;
+    auto fstamp = [&](int layer) {
+        if (dbg && blockIdx.x == 0 && tid == 0 && (layer == 1 || layer == 2) && dbg_f < 40) { dbg[65 + dbg_f++] = clock64(); dbg[64] = dbg_f; }
+    };
     stamp();
     bool ok = true;
 
@@ -388,6 +394,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                 for (int tap = 0; tap < 9; tap++) wd[tap] = ldp4(reinterpret_cast<const float4 *>(wl + tap * C::MIDP));
                 bs = ldp4(reinterpret_cast<const float4 *>(wl + 9 * C::MIDP));
             }
+            fstamp(lc);                        // f0: layer start (taps loaded)
             // ---- pointwise result: TMEM -> fp32 T own rows (+ edge rows into the neighbours' rings)
             {
                 constexpr int NU = C::NT * C::CG, UPT = (NU + C::GROUPS - 1) / C::GROUPS;
@@ -404,7 +411,9 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     tmem_ld4_nw(ta + C::MIDP, rb_[i]);
                 }
                 tmem_wait_ld();
+                fstamp(lc);                    // f1: MMAs complete, TMEM loaded
                 if (a_pending) { cluster_wait(); a_pending = false; }       // [wait A] rings are free
+                fstamp(lc);                    // f2: wait A done
 #pragma unroll
                 for (int i = 0; i < UPT; i++) {
                     const int u = grp + i * C::GROUPS;
@@ -426,10 +435,12 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                 }
             }
             tile_par ^= 1;
+            fstamp(lc);                        // f3: T written, edges pushed
             tc::fence_before_sync();
             if (C::EXCH) { cluster_arrive(); cluster_wait(); }             // [B] pushes visible; CTA-wide barrier too
             else __syncthreads();
             tc::fence_after_sync();
+            fstamp(lc);                        // f4: barrier B done
             stamp();                           // T ready
             // the next stream starts from X1: its pointwise conv runs under this depthwise pass
             if (last && s < 3 && issuer) issue_pw(sX1, lc + 1, 0, C::NT);
@@ -515,14 +526,18 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     if (issuer) issue_pw(sP, lc + 1, TH_, C::NT);
                 } else {
                     dw_rows(0, C::R);
+                    fstamp(lc);                // f5: depthwise rows done (this warp)
                     if (C::EXCH) { cluster_arrive(); a_pending = true; }    // [arrive A]
                     publish();
+                    fstamp(lc);                // f6: published
                     if (issuer) issue_pw(sP, lc + 1, 0, C::NT);
+                    fstamp(lc);                // f7: next pointwise issued
                 }
                 stamp();                       // depthwise done, next pointwise issued
                 continue;
             }
             dw_rows(0, C::R);
+            fstamp(lc);                        // f5: depthwise rows done (this warp)
             {                                  // the column lanes of a (segment, column block, channel group) are adjacent
 #pragma unroll
                 for (int off = C::XL; off >= 2; off >>= 1) {
@@ -535,6 +550,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     *reinterpret_cast<float4 *>(s_scr + ((dw_seg * C::NCB + dw_cb) * C::CG + dw_cg) * 4) = gacc;
             }
             publish();
+            fstamp(lc);                        // f6: published
             stamp();                           // depthwise done
             // ---- ChannelGate: band-partial sums -> every band's shared memory (pushed), cluster barrier,
             //      mean -> MLP -> sigmoid -> gate-scaled conv3 weights (computed redundantly, identically, per band)
@@ -550,7 +566,9 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     *slot = tot;
                 }
             }
+            fstamp(lc);                        // f7: gate sums pushed (warp 0)
             if (C::NB > 1) cluster.sync(); else __syncthreads();      // also phase "A" of the ring protocol
+            fstamp(lc);                        // f8: gate barrier
             if (warp * 32 < C::COUT * C::MCH) {      // warps that own conv3 weight rows; lane c = channel c
                 float tot = 0.f;                   // fixed band order: every CTA of the crop gets the same bits
                 if (lane < C::MIDP)
@@ -586,6 +604,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     *reinterpret_cast<uint4 *>(sC3 + C::C3W_HALF_B + (size_t)u * 16) = *reinterpret_cast<uint4 *>(l);
                 }
             }
+            fstamp(lc);                        // f9: gate MLP + scaled conv3 weights written
             tc::fence_async_smem();
             tc::fence_before_sync();
             __syncthreads();

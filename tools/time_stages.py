@@ -55,7 +55,7 @@ def main():
             trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST())))
     trk.set_reid_backend("tc")
     # phase stamps of CTA 0 inside every tensor-core OSBlock (cycles since kernel start)
-    dbg = torch.zeros(64, dtype=torch.int64, device="cuda")
+    dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
     shapes = [(64, 32, 16), (64, 32, 64), (32, 16, 64), (32, 16, 96), (16, 8, 96), (16, 8, 128)]
     for b, (hh, ww, cin) in enumerate(shapes):
         x = np.maximum(np.random.default_rng(b).normal(0.5, 1, (n, hh, ww, cin)), 0).astype(np.float32)
@@ -68,6 +68,10 @@ def main():
             d = dbg.cpu().numpy()
             k = int(d[0])
             out[f"osblock{b}{tag}_phase_cycles"] = [int(v - d[1]) for v in d[2:1 + k]]
+            if mode == 3 and int(d[64]) > 0:     # fine stamps of layers 1 and 2 (reid_tc4.cu fstamp), deltas
+                f = [int(v) for v in d[65:65 + int(d[64])]]
+                out[f"osblock{b}_fine_deltas"] = [f[i + 1] - f[i] for i in range(len(f) - 1)]
+            dbg.zero_()
     # stem phases (CTA 0): S built, MMAs done, conv drained, pooled
     lib.ssb_reid_tc_debug(P(dbg))
     _lib.check(lib.ssb_reid(trk._h, P(img), 1080, 1920, 1920 * 3, P(boxes), n, P(feats), ST()))

@@ -115,7 +115,7 @@ def process_video(args):
                     emit(labels, rows, tracker.last_det_index, pending.pop(0))
                 tracker.increment_ages()
             else:
-                if pin is None or tuple(pin.shape) != tuple(img.shape):
+                if pin is None or tuple(pin[0].shape) != tuple(img.shape):
                     pin = [torch.empty(img.shape, dtype=torch.uint8).pin_memory() for _ in range(2)]
                 slot = pin[n_frames & 1]                              # the copy of frame k-1 may still be in flight
                 slot.copy_(torch.from_numpy(img))
