@@ -42,6 +42,12 @@ bool ssb_first_on_device(int key) {
     g_dev_done[dev][key] = 1;
     return true;
 }
+static int env_flag(const char *name, int dflt) {
+    const char *v = getenv(name);
+    return v && *v ? atoi(v) != 0 : dflt;
+}
+bool ssb_pdl_enabled() { static const int on = env_flag("SSB_PDL", 1); return on != 0; }
+bool ssb_split_enabled() { static const int on = env_flag("SSB_SPLIT", 1); return on != 0; }
 int ssb_num_sms() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -268,7 +274,7 @@ extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const ui
                           int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
     if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
     if (!feats_dev && n > 0 && !img_dev) { ssb_set_error("null image"); return -1; }
-    if (!feats_dev && img_dev && n >= 48 && t->use_tc && t->w_tc && pitch >= 3 * w) {
+    if (!feats_dev && img_dev && n >= 48 && t->use_tc && t->w_tc && pitch >= 3 * w && ssb_split_enabled()) {
         int rc = ssb_embed(t, 0, dets_dev, n, nullptr, h, w, pitch, stream);          // detection prep only
         if (rc) return rc;
         rc = reid_forward_split(t, img_dev, h, w, pitch, t->fs.det_box, n, t->fs.feats, (cudaStream_t)stream);
@@ -285,7 +291,7 @@ extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, in
     if (!t || !img_dev || !feats_out_dev) { ssb_set_error("null argument"); return -1; }
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
     if (n == 0) return 0;
-    if (n >= 48 && t->use_tc && pitch >= 3 * w)
+    if (n >= 48 && t->use_tc && pitch >= 3 * w && ssb_split_enabled())
         return reid_forward_split(t, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
     return ssb_reid_forward(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
 }

@@ -733,10 +733,12 @@ pw_tc_kernel(const float *__restrict__ x, float *__restrict__ y,
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         tc::mbar_arrive_expect_tx(bar + 2, C::W_B);
         tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 2);
     }
+    tc::pdl_wait();                    // the producer of x has completed (programmatic dependent launch)
     bool ok = true;
     uint32_t ph[2] = {0, 0};
     constexpr uint32_t IDESC = tc::make_idesc_f16(128, C::COUT);
@@ -916,17 +918,20 @@ tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         // PLANES: a crop's operand planes [hl][16 chunks][128 px][8] ARE the staging layout: two 32 KB bulk copies
         tc::mbar_arrive_expect_tx(bar + 1, C::W_B + (PLANES ? C::STG_B : 0));
         tc::bulk_g2s(sW, wblob + C::G_W, C::W_B / 2, bar + 1);
         tc::bulk_g2s(sW + C::W_B / 2, wblob + C::G_W + C::W_B / 2, C::W_B / 2, bar + 1);
+        tc::pdl_wait();
         if (PLANES) {
             const unsigned char *xb = reinterpret_cast<const unsigned char *>(x) + (size_t)crop * C::STG_B;
             tc::bulk_g2s(stg, xb, C::STG_HALF_B, bar + 1);
             tc::bulk_g2s(stg + C::STG_HALF_B, xb + C::STG_HALF_B, C::STG_HALF_B, bar + 1);
         }
     }
+    tc::pdl_wait();
     const float *xin = x + (size_t)crop * C::PX * C::CIN;
     constexpr int F4 = C::CIN / 4;
 #pragma unroll 4
@@ -1057,10 +1062,12 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = *s_tmem;
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         tc::mbar_arrive_expect_tx(bar + 1, C::W_B);
         tc::bulk_g2s(sW, wblob + C::G_W, C::W_B, bar + 1);
     }
+    tc::pdl_wait();                    // the crop boxes come from the previous kernel of the stream
     // ---- build S: every resized+normalised pixel of the band lands in exactly one slot
     const int bx1 = boxes[crop * 4 + 0], by1 = boxes[crop * 4 + 1];
     const int cw = boxes[crop * 4 + 2] - bx1, ch = boxes[crop * 4 + 3] - by1;
@@ -1254,6 +1261,22 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     if (warp == 0) tc::tmem_dealloc(tmem, 512);
 }
 
+// 512-thread launch with the programmatic-dependent-launch attribute (tc_common.cuh: pdl_wait / pdl_launch_dependents)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(OSB_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ssb_pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 using PwT1 = PwCfg<64, 64, 64, 32, true>;     // after conv2: 64x32x64 -> 32x16x64
 using PwT2 = PwCfg<96, 96, 32, 16, true>;     // after conv3: 32x16x96 -> 16x8x96
 
@@ -1267,8 +1290,8 @@ int launch_pw_tc(const float *x, float *y, const unsigned char *w, int n, int *s
     const int per = C::POOL ? 32 : 128;
     int tiles = (int)((total + per - 1) / per);
     int grid = tiles < sms ? tiles : sms;
-    pw_tc_kernel<C, PLANES><<<grid, OSB_THREADS, C::SMEM_B, st>>>(x, y, w, n, status);
-    SSB_CHECK_LAUNCH();
+    SSB_CHECK_CUDA(launch_pdl(pw_tc_kernel<C, PLANES>, grid, C::SMEM_B, st, x, y, w, n, status));
+    g_ssb_launches++;
     return 0;
 }
 
@@ -1325,11 +1348,12 @@ int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *box
         SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
         SSB_CHECK_CUDA(cudaFuncSetAttribute(stem_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, StemCfg::SMEM_B));
     }
+    long long *dbg = g_ssb_tc_dbg;
     if (planes)
-        stem_tc_kernel<true><<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
+        SSB_CHECK_CUDA(launch_pdl(stem_tc_kernel<true>, n * StemCfg::NB, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
     else
-        stem_tc_kernel<false><<<n * StemCfg::NB, OSB_THREADS, StemCfg::SMEM_B, st>>>(img, h, w, pitch, boxes, wsec, out, status, g_ssb_tc_dbg);
-    SSB_CHECK_LAUNCH();
+        SSB_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, n * StemCfg::NB, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
+    g_ssb_launches++;
     return 0;
 }
 
@@ -1346,9 +1370,9 @@ int ssb_reid_tc_aux(int which, const float *x, float *y, const unsigned char *w,
                 SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
                 SSB_CHECK_CUDA(cudaFuncSetAttribute(tail_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TailCfg::SMEM_B));
             }
-            if (planes) tail_tc_kernel<true><<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
-            else tail_tc_kernel<false><<<n, OSB_THREADS, TailCfg::SMEM_B, st>>>(x, y, w, status);
-            SSB_CHECK_LAUNCH();
+            if (planes) SSB_CHECK_CUDA(launch_pdl(tail_tc_kernel<true>, n, TailCfg::SMEM_B, st, x, y, w, status));
+            else SSB_CHECK_CUDA(launch_pdl(tail_tc_kernel<false>, n, TailCfg::SMEM_B, st, x, y, w, status));
+            g_ssb_launches++;
             return 0;
         }
     }

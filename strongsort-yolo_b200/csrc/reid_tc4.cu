@@ -109,6 +109,15 @@ __device__ __forceinline__ void split2(float a, float b, __half2 &h, __half2 &l)
     const float2 hf = __half22float2(h);
     l = __floats2half2_rn(a - hf.x, b - hf.y);
 }
+// same split, the residual as ONE packed fp32x2 subtraction
+__device__ __forceinline__ void split2p(float a, float b, __half2 &h, __half2 &l) {
+    h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    unsigned long long v = ((unsigned long long)__float_as_uint(b) << 32) | __float_as_uint(a);
+    const unsigned long long hv = ((unsigned long long)__float_as_uint(hf.y) << 32) | __float_as_uint(hf.x);
+    asm("sub.rn.f32x2 %0, %0, %1;" : "+l"(v) : "l"(hv));
+    l = __floats2half2_rn(__uint_as_float((uint32_t)v), __uint_as_float((uint32_t)(v >> 32)));
+}
 __device__ __forceinline__ void split1(float v, __half &h, __half &l) {
     h = __float2half_rn(v);
     l = __float2half_rn(v - __half2float(h));
@@ -221,10 +230,15 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
     auto stamp = [&]() { if (dbg && blockIdx.x == 0 && tid == 0 && dbg_n < 63) dbg[1 + dbg_n++] = clock64(); };
     // finer stamps of two layers (lc 1: a layer followed by another LightConv, lc 2: the last layer of a stream)
     // into dbg[64..]: [64] = count
+    // (compiled in with -DSSB_FINE_STAMPS only: the extra branches cost the forward ~9 %)
+#ifdef SSB_FINE_STAMPS
     int dbg_f = 0;
     auto fstamp = [&](int layer) {
         if (dbg && blockIdx.x == 0 && tid == 0 && (layer == 1 || layer == 2) && dbg_f < 40) { dbg[65 + dbg_f++] = clock64(); dbg[64] = dbg_f; }
     };
+#else
+    auto fstamp = [](int) {};
+#endif
     stamp();
     bool ok = true;
 
@@ -235,12 +249,16 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
     // ------------------------------------------------------------------
     const unsigned char *xin = x + (size_t)crop * (4 * C::CIN * C::HW);          // [hl][CIN/8][HW][8] halves
     constexpr int X_LO = 2 * C::CIN * C::HW;                                       // byte offset of the lo planes
+    // programmatic dependent launch: everything above (TMEM, barriers, parameters) and the weight copies below
+    // run while the previous kernel of the stream is still draining; its output is only touched after the wait
+    tc::pdl_launch_dependents();
     if (tid == 0) {
         tc::mbar_arrive_expect_tx(bar_w, C::WALL_B + C::XS_B);
         for (int o = 0; o < C::WALL_B; o += 32768) {
             const int nb = C::WALL_B - o < 32768 ? C::WALL_B - o : 32768;
             tc::bulk_g2s(sW + o, wblob + o, nb, bar_w);
         }
+        tc::pdl_wait();
         for (int hl = 0; hl < 2; hl++)
             for (int ch = 0; ch < C::XCH; ch++)
                 tc::bulk_g2s(sP + hl * C::XS_HALF_B + ch * C::PLANE_B,
@@ -363,6 +381,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
             __syncwarp();
         }
     };
+    tc::pdl_wait();                           // every thread: before its own global reads / writes of activations
     float w3r[8];                             // conv3 weights of this thread's operand row (kc, co)
     {
         const float *w3 = reinterpret_cast<const float *>(wblob + C::G_W3);  // [MIDP][COUT]
@@ -466,25 +485,22 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     for (int j = 0; j < 3; j++) w[j] = ldp4(Tp + trow * C::TW + j);
                 };
                 auto dwrow = [&](int lr, const P4 *wa, const P4 *wb, const P4 *wc) {
-                    // three independent 3-term chains (one per window row) instead of one 9-deep chain
-                    P4 o = bs, o1, o2;
-                    fma4(o, wd[0], wa[0]);
-                    mul4(o1, wd[3], wb[0]);
-                    mul4(o2, wd[6], wc[0]);
-                    fma4(o, wd[1], wa[1]);
-                    fma4(o1, wd[4], wb[1]);
-                    fma4(o2, wd[7], wc[1]);
-                    fma4(o, wd[2], wa[2]);
-                    fma4(o1, wd[5], wb[2]);
-                    fma4(o2, wd[8], wc[2]);
-                    add4(o1, o2);
-                    add4(o, o1);
+                    // The pass is ISSUE-bound with two CTAs per SM (fine stamps, profiles/r02_phases.md: every fp32
+                    // instruction holds its SMSP's pipe for 2 cycles), so instructions are what is saved here: one
+                    // 9-term chain per packed pair (the two pairs interleave; no extra adds), packed residual for lo
+                    P4 o = bs;
+#pragma unroll
+                    for (int dx = 0; dx < 3; dx++) {
+                        fma4(o, wd[dx], wa[dx]);
+                        fma4(o, wd[3 + dx], wb[dx]);
+                        fma4(o, wd[6 + dx], wc[dx]);
+                    }
                     const float ox = fmaxf(p4x(o), 0.f), oy = fmaxf(p4y(o), 0.f);
                     const float oz = fmaxf(p4z(o), 0.f), ow = fmaxf(p4w(o), 0.f);
                     if (last) { gacc.x += ox; gacc.y += oy; gacc.z += oz; gacc.w += ow; }
                     __half2 h[2], l[2];
-                    split2(ox, oy, h[0], l[0]);
-                    split2(oz, ow, h[1], l[1]);
+                    split2p(ox, oy, h[0], l[0]);
+                    split2p(oz, ow, h[1], l[1]);
                     unsigned char *d = dbase + lr * (C::W * 16);
                     *reinterpret_cast<uint2 *>(d) = make_uint2(*reinterpret_cast<uint32_t *>(&h[0]), *reinterpret_cast<uint32_t *>(&h[1]));
                     *reinterpret_cast<uint2 *>(d + C::MAP_HALF_B) =
@@ -721,7 +737,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
 #define SSB_S3_R 16
 #endif
 #ifndef SSB_S3_SPLIT
-#define SSB_S3_SPLIT (SSB_S3_R == 16)
+#define SSB_S3_SPLIT false
 #endif
 constexpr int S2_THREADS = SSB_S2_R == 8 ? 256 : 512, S2_MINB = SSB_S2_R == 8 ? 2 : 1, S2_SEG = SSB_S2_R == 8 ? 2 : 3;
 //            CIN MID MIDP COUT  H   W   R  NB  DOWN SEG THREADS MINB SPLIT
@@ -743,13 +759,15 @@ int launch4(const unsigned char *x, unsigned char *y, const unsigned char *w, in
     cfg.blockDim = dim3(C::THREADS);
     cfg.dynamicSmemBytes = C::SMEM_B;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C::NB;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = ssb_pdl_enabled() ? 2 : 1;
     SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock4_kernel<C>, x, y, w, n, status, dbg));
     g_ssb_launches++;
     return 0;

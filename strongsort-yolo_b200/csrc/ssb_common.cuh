@@ -127,6 +127,8 @@ void ssb_set_error(const char *fmt, ...);
 int ssb_new_key();
 bool ssb_first_on_device(int key);
 int ssb_num_sms();      // SM count of the current device (cached per device)
+bool ssb_pdl_enabled(); // programmatic dependent launch between the ReID kernels (SSB_PDL=0 switches it off: A/B)
+bool ssb_split_enabled();   // ssb_update / ssb_reid embed a frame's crops as two halves on two streams (SSB_SPLIT=0: A/B)
 #define SSB_CHECK_CUDA(expr)                                                        \
     do {                                                                            \
         cudaError_t _e = (expr);                                                    \

@@ -215,6 +215,13 @@ __device__ __forceinline__ bool mbar_wait_cluster(uint64_t *bar, uint32_t parity
     }
 }
 
+// programmatic dependent launch (launch attribute programmaticStreamSerializationAllowed): a kernel may start
+// while its predecessor on the stream is still running; griddepcontrol.wait blocks until the predecessor has
+// completed and its memory is visible, launch_dependents lets the NEXT kernel begin its own prologue.  Both are
+// no-ops when the kernel was launched without the attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map needed),
 // completion counted in bytes on an mbarrier.  size % 16 == 0, 16-byte aligned.
 __device__ __forceinline__ void bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes,

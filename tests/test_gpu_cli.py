@@ -26,9 +26,9 @@ def test_two_sources_two_workers(tmp_path):
         for ln in lines[:50]:                            # reference :167 wire format
             assert re.fullmatch(r"0 \d+ \d+ \d(\.\d+)? \d+ \d+ \d+ \d+ -1 -1 -1 -1", ln), ln
         assert f"[{name}] {frames} frames" in p.stdout
-        m = re.search(r"\[%s\] count: (\{.*\})" % name, p.stdout)
+        m = re.findall(r"\[%s\] count: (\{.*\})" % name, p.stdout)
         assert m, p.stdout[-2000:]
         ids = {int(ln.split()[2]) for ln in lines}
-        assert sum(eval(m.group(1)).values()) == len(ids)      # every reported id counted once
+        assert sum(eval(m[-1]).values()) == len(ids)           # final overlay: every reported id counted once
     # two distinct worker processes (the Pool), each printing its own job dict (reference :245)
     assert p.stdout.count("'source': 'synthetic:") == 2

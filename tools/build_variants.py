@@ -10,12 +10,13 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+# name: (extra nvcc flags, environment of the timing run)
 VARIANTS = {
-    "s2r8": [],                                             # the default geometry
-    "s2r8split": ["-DSSB_S2_SPLIT=true"],
-    "s2r16": ["-DSSB_S2_R=16", "-DSSB_S2_SPLIT=true"],
-    "s3r8": ["-DSSB_S3_R=8"],
-    "s3r16nosplit": ["-DSSB_S3_SPLIT=false"],
+    "base": ([], {}),                                       # the default build
+    "base_nopdl": ([], {"SSB_PDL": "0"}),                   # programmatic dependent launch off
+    "base_nosplit": ([], {"SSB_SPLIT": "0"}),               # whole frame on one stream instead of two halves
+    "s3split": (["-DSSB_S3_SPLIT=true"], {}),
+    "s2r16": (["-DSSB_S2_R=16", "-DSSB_S2_SPLIT=true"], {}),
 }
 
 
@@ -24,8 +25,12 @@ def build():
     spec = importlib.util.spec_from_file_location("_b", os.path.join(ROOT, "strongsort-yolo_b200", "build.py"))
     b = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(b)
-    for name, flags in VARIANTS.items():
-        print(b.build_variant(name, flags))
+    built = set()
+    for name, (flags, _env) in VARIANTS.items():
+        key = name.split("_")[0]
+        if key not in built:
+            print(b.build_variant(key, flags))
+            built.add(key)
 
 
 def time_one():
@@ -65,11 +70,11 @@ def time_one():
 
 def time_all():
     out = {}
-    for name in VARIANTS:
-        lib = os.path.join(ROOT, "strongsort-yolo_b200", "variants", f"libssb_{name}.so")
+    for name, (_flags, extra) in VARIANTS.items():
+        lib = os.path.join(ROOT, "strongsort-yolo_b200", "variants", f"libssb_{name.split('_')[0]}.so")
         if not os.path.exists(lib):
             continue
-        env = dict(os.environ, SSB_LIB=lib)
+        env = dict(os.environ, SSB_LIB=lib, **extra)
         try:
             p = subprocess.run([sys.executable, __file__, "time_one"], env=env, capture_output=True, text=True, timeout=240)
             out[name] = json.loads(p.stdout.strip().splitlines()[-1]) if p.returncode == 0 else {"error": p.stderr[-400:]}
