@@ -35,6 +35,10 @@
 
 namespace cg = cooperative_groups;
 
+#ifndef SSB_DW_CHAINS
+#define SSB_DW_CHAINS 3          // depthwise FMA chains per output (3: one per window row; 1: a single 9-term chain)
+#endif
+
 namespace {
 
 __host__ __device__ constexpr int cmax4(int a, int b) { return a > b ? a : b; }
@@ -485,9 +489,23 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     for (int j = 0; j < 3; j++) w[j] = ldp4(Tp + trow * C::TW + j);
                 };
                 auto dwrow = [&](int lr, const P4 *wa, const P4 *wb, const P4 *wc) {
-                    // The pass is ISSUE-bound with two CTAs per SM (fine stamps, profiles/r02_phases.md: every fp32
-                    // instruction holds its SMSP's pipe for 2 cycles), so instructions are what is saved here: one
-                    // 9-term chain per packed pair (the two pairs interleave; no extra adds), packed residual for lo
+                    // three independent 3-term chains (one per window row): measured on B200 the pass is bound by
+                    // dependent-issue latency, not by instruction count -- one 9-term chain per packed pair (4 fewer
+                    // instructions per row) ran the whole forward 4.5 % SLOWER (profiles/r02_reid_variants.md)
+#if SSB_DW_CHAINS == 3
+                    P4 o = bs, o1, o2;
+                    fma4(o, wd[0], wa[0]);
+                    mul4(o1, wd[3], wb[0]);
+                    mul4(o2, wd[6], wc[0]);
+                    fma4(o, wd[1], wa[1]);
+                    fma4(o1, wd[4], wb[1]);
+                    fma4(o2, wd[7], wc[1]);
+                    fma4(o, wd[2], wa[2]);
+                    fma4(o1, wd[5], wb[2]);
+                    fma4(o2, wd[8], wc[2]);
+                    add4(o1, o2);
+                    add4(o, o1);
+#else
                     P4 o = bs;
 #pragma unroll
                     for (int dx = 0; dx < 3; dx++) {
@@ -495,6 +513,7 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                         fma4(o, wd[3 + dx], wb[dx]);
                         fma4(o, wd[6 + dx], wc[dx]);
                     }
+#endif
                     const float ox = fmaxf(p4x(o), 0.f), oy = fmaxf(p4y(o), 0.f);
                     const float oz = fmaxf(p4z(o), 0.f), ow = fmaxf(p4w(o), 0.f);
                     if (last) { gacc.x += ox; gacc.y += oy; gacc.z += oz; gacc.w += ow; }
@@ -729,6 +748,9 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
 //   stage 3: SSB_S3_R = 16 -> 2 bands x 256 px (default);  8 -> 4 bands x 128 px
 #ifndef SSB_S2_R
 #define SSB_S2_R 8
+#endif
+#ifndef SSB_DW_CHAINS
+#define SSB_DW_CHAINS 3
 #endif
 #ifndef SSB_S2_SPLIT
 #define SSB_S2_SPLIT false
