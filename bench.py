@@ -342,28 +342,29 @@ def impl_reference(args, rank):
 
 
 class DetectorPost:
-    """decode + NMS + scale_boxes of one frame's raw head on `stream`; returns the device rows and the
-    detection count (one 4-byte read-back: the tracker's C-ABI takes n as a host integer)."""
+    """The frame's detector post-process (yolo.YoloV8Post: one C call, 5 launches) with LOOK-AHEAD: ``get(i)``
+    returns frame i's detections and has already submitted frame i+1's head, so in a stream loop the host never
+    waits for a post-process it has just enqueued (the tracker's C-ABI takes the detection count as a host
+    integer: one 16-byte read-back per frame, of work that finished a frame ago).  The slots of YoloV8Post rotate
+    three deep: a frame's rows stay valid until two more frames have been submitted."""
 
-    def __init__(self, device, frame_hw):
+    def __init__(self, device, frame_hw, raws_dev):
+        import torch
         from strongsort_yolo_b200 import yolo
-        self.dec = yolo.YoloV8Decode(NUM_CLASSES, 0, NET_HW[0], NET_HW[1], device=str(device))
-        self.nms = yolo.YoloNMS(num_classes=NUM_CLASSES, max_anchors=self.dec.A, device=str(device))
-        self.frame_hw = frame_hw
-        import torch
-        self._cnt_pin = torch.zeros(4, dtype=torch.int32).pin_memory()
+        self.post = yolo.YoloV8Post(NUM_CLASSES, 0, NET_HW[0], NET_HW[1], frame_hw, device=str(device), depth=4)
+        self.raws = raws_dev
+        self.stream = torch.cuda.Stream(device=device, priority=-1)
+        self.pending = {}
 
-    def __call__(self, raw_dev, stream):
-        import torch
-        with torch.cuda.stream(stream):
-            pred = self.dec(raw_dev, stream)
-            self.nms(pred, stream)
-            out, cnt = self.nms.scale_boxes(NET_HW, self.frame_hw, stream)
-            rows = out[:256, :6].clone()        # the NMS buffer is reused by the next frame while this one is in flight
-            self._cnt_pin.copy_(cnt, non_blocking=True)
-        stream.synchronize()
-        m = int(self._cnt_pin[0])
-        return rows[:m] if m <= 256 else out[:m, :6].clone()
+    def submit(self, i):
+        if 0 <= i < len(self.raws) and i not in self.pending:
+            self.pending[i] = self.post.submit(self.raws[i], self.stream)
+
+    def get(self, i, lookahead=True):
+        self.submit(i)
+        if lookahead:
+            self.submit(i + 1)
+        return self.post.result(self.pending.pop(i))[:, :6]
 
 
 def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W, want_cpu):
@@ -384,13 +385,41 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)
     res = {}
 
+    post = DetectorPost(device, (H, Wd), raws_dev) if use_post else None
+
+    def frame_dets(i, stream=None, lookahead=True):
+        """frame i's detections on the device; a serial caller (lookahead False) orders the post-process after its
+        own stream (the L2 flush of the serial timing loop)"""
+        if not use_post:
+            return dets_dev[i]
+        if not lookahead and stream is not None and i not in post.pending:
+            post.stream.wait_stream(stream)
+        return post.get(i, lookahead)
+
+    if args.only_device:
+        trk = StrongSORT(device=str(device), **trk_kw)
+        pstream = torch.cuda.Stream(device=device)
+        for i in range(W):
+            trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+        trk.flush_pipelined()
+        barrier()
+        torch.cuda.profiler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.ssb_launch_count()
+        e0.record(trk.stream)
+        for k in range(K):
+            trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+        trk.flush_pipelined()
+        e1.record(trk.stream)
+        barrier()
+        torch.cuda.profiler.stop()
+        print(json.dumps({"only_device": True, "ms_per_step": e0.elapsed_time(e1) / K, "steps": K, "warmup": W,
+                          "gpu_launches": int(lib.ssb_launch_count() - l0)}), flush=True)
+        sys.exit(0)
+
     # ---------------- (a) serial: one frame at a time, L2 flushed between steps; stage split -------------
     trk = StrongSORT(device=str(device), **trk_kw)
-    post = DetectorPost(device, (H, Wd)) if use_post else None
     st = trk.stream
-
-    def frame_dets(i, stream):
-        return post(raws_dev[i], stream) if use_post else dets_dev[i]
 
     for i in range(W):
         trk.update(frame_dets(i, st), imgs_dev[i])
@@ -404,7 +433,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
         with torch.cuda.stream(st):
             flush.fill_(k & 0xFF)                      # L2 flush, outside the timed events
             ev[k][0].record(st)
-        d = frame_dets(W + k, st)
+        d = frame_dets(W + k, st, lookahead=False)
         ev[k][1].record(st)
         trk.update(d, imgs_dev[W + k])
         ev[k][2].record(st)
@@ -521,7 +550,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     n_seen = 0
     for k in range(K):
         trk2.prefetch(imgs[W + k])                 # the frame's H2D runs under the detector post-process
-        d = frame_dets(W + k, pstream)
+        d = frame_dets(W + k, pstream, lookahead=False)       # synchronous caller: this frame's head only
         n_seen += int(d.shape[0])
         trk2.update(d, imgs[W + k])
     e1.record(trk2.stream)
@@ -580,6 +609,8 @@ def main():
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
                     help="C2 (default, the BASELINE.json metric) or C4 (4K, 500 dets/frame)")
     ap.add_argument("--no-c4", action="store_true", help="skip the appended C4 block of the N=1 line")
+    ap.add_argument("--only-device", action="store_true",
+                    help="profiling aid: only the device-resident pipelined loop (for ncu launch lists)")
     ap.add_argument("--shared-gallery", action="store_true",
                     help="config C5's optional exchange: every stream's confirmed-track features exchanged after each "
                          "frame and matched across streams (read-only), inside the timed region")

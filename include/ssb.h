@@ -180,6 +180,15 @@ int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_
 int ssb_yolo_scale_boxes(float *rows_dev, int cols, const int32_t *count_dev, int max_det, float gain,
                          float pad_x, float pad_y, int w0, int h0, ssb_stream_t stream);
 
+/* The whole YOLOv8 detector post-process in one call (5 launches): decode with the best class per anchor fused,
+ * confidence filter + class-aware NMS, and -- when gain > 0 -- scale_boxes fused into the gather.  Same results as
+ * ssb_yolo_decode_v8 -> ssb_yolo_nms -> ssb_yolo_scale_boxes.  pred_scratch_dev: float32 [4 + nc + 3*kpts, A]. */
+int ssb_yolo_postprocess_v8(const float *raw_dev, int num_classes, int num_kpts, int in_h, int in_w,
+                            float conf_thres, float iou_thres, int max_det, int agnostic,
+                            float gain, float pad_x, float pad_y, int w0, int h0,
+                            float *pred_scratch_dev, float *out_dev, int32_t *count_dev, void *scratch_dev,
+                            ssb_stream_t stream);
+
 /* YOLOv8 detect / pose head decode: raw float32 [4*16 + nc + 3*kpts, A] (DFL bins,
  * class logits, keypoint x,y,vis) for a network input of in_h x in_w (multiples of 32; A =
  * ssb_yolo_num_anchors, stride-8/16/32 levels concatenated) -> pred float32 [4 + nc + 3*kpts, A],

@@ -20,7 +20,7 @@ SYMBOLS = [
     "ssb_yolo_nms", "ssb_export_tracks",
     "ssb_yolo_num_anchors", "ssb_yolo_decode_v8", "ssb_yolo_decode_v5", "ssb_camera_update",
     "ssb_gallery_export", "ssb_gallery_cross_match", "ssb_gallery_cross_match_packed", "ssb_gallery_peer_match", "ssb_increment_ages",
-    "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes", "ssb_class_counts",
+    "ssb_profile_enable", "ssb_profile_read", "ssb_yolo_scale_boxes", "ssb_class_counts", "ssb_yolo_postprocess_v8",
     "ssb_appearance_tc_scratch_bytes", "ssb_appearance_cost_tc", "ssb_appearance_use_tc",
 ]
 
@@ -97,6 +97,8 @@ def load(debug=False):
     lib.ssb_nms_scratch_bytes.restype = i64
     lib.ssb_yolo_nms.argtypes = [vp, i32, i32, i32, C.c_float, C.c_float, i32, i32, vp, vp, vp, vp]
     lib.ssb_yolo_scale_boxes.argtypes = [vp, i32, vp, i32, C.c_float, C.c_float, C.c_float, i32, i32, vp]
+    lib.ssb_yolo_postprocess_v8.argtypes = [vp, i32, i32, i32, i32, C.c_float, C.c_float, i32, i32, C.c_float, C.c_float,
+                                            C.c_float, i32, i32, vp, vp, vp, vp, vp]
     lib.ssb_yolo_num_anchors.argtypes = [i32, i32]
     lib.ssb_yolo_num_anchors.restype = i32
     lib.ssb_yolo_decode_v8.argtypes = [vp, i32, i32, i32, i32, vp, vp]

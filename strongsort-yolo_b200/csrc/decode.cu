@@ -13,8 +13,11 @@
 
 namespace {
 
+// conf_out / cls_out (nullable): the anchor's best class probability and index, the first maximum winning like
+// torch.max -- what ssb_yolo_nms's score pass would recompute from `out` (fused here: one pass less over the head)
 __global__ void yolo_decode_v8_kernel(const float *__restrict__ raw, int nc, int nk, int in_h, int in_w,
-                                      int A, float *__restrict__ out) {
+                                      int A, float *__restrict__ out, float *__restrict__ conf_out,
+                                      int *__restrict__ cls_out) {
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= A) return;
     // level / grid position of anchor a
@@ -44,8 +47,14 @@ __global__ void yolo_decode_v8_kernel(const float *__restrict__ raw, int nc, int
     out[(size_t)1 * A + a] = ((y1 + y2) / 2.f) * fs;
     out[(size_t)2 * A + a] = (x2 - x1) * fs;
     out[(size_t)3 * A + a] = (y2 - y1) * fs;
-    for (int c = 0; c < nc; c++)
-        out[(size_t)(4 + c) * A + a] = 1.f / (1.f + expf(-raw[(size_t)(64 + c) * A + a]));
+    float best = -INFINITY;
+    int bi = 0;
+    for (int c = 0; c < nc; c++) {
+        const float p = 1.f / (1.f + expf(-raw[(size_t)(64 + c) * A + a]));
+        out[(size_t)(4 + c) * A + a] = p;
+        if (c == 0 || p > best) { best = p; bi = c; }
+    }
+    if (conf_out) { conf_out[a] = best; cls_out[a] = bi; }
     for (int k = 0; k < nk; k++) {
         const size_t ri = (size_t)(64 + nc + 3 * k) * A + a, oi = (size_t)(4 + nc + 3 * k) * A + a;
         out[oi] = (raw[ri] * 2.f + (ax - 0.5f)) * fs;
@@ -108,7 +117,17 @@ extern "C" int ssb_yolo_decode_v8(const float *raw_dev, int num_classes, int num
     const int A = ssb_yolo_num_anchors(in_h, in_w);
     if (A <= 0 || num_classes < 1 || num_kpts < 0) { ssb_set_error("bad head geometry %dx%d nc=%d kpts=%d", in_h, in_w, num_classes, num_kpts); return -1; }
     yolo_decode_v8_kernel<<<(A + 127) / 128, 128, 0, (cudaStream_t)stream>>>(raw_dev, num_classes, num_kpts, in_h, in_w, A,
-                                                                             pred_out_dev);
+                                                                              pred_out_dev, nullptr, nullptr);
+    SSB_CHECK_LAUNCH();
+    return 0;
+}
+
+// decode + best class per anchor in one pass (ssb_yolo_postprocess_v8, nms.cu)
+int ssb_launch_decode_v8_scored(const float *raw, int nc, int nk, int in_h, int in_w, float *pred, float *conf, int *cls,
+                                cudaStream_t st) {
+    const int A = ssb_yolo_num_anchors(in_h, in_w);
+    if (A <= 0 || nc < 1 || nk < 0) { ssb_set_error("bad head geometry %dx%d nc=%d kpts=%d", in_h, in_w, nc, nk); return -1; }
+    yolo_decode_v8_kernel<<<(A + 127) / 128, 128, 0, st>>>(raw, nc, nk, in_h, in_w, A, pred, conf, cls);
     SSB_CHECK_LAUNCH();
     return 0;
 }

@@ -150,43 +150,96 @@ __global__ void nms_mask_kernel(float iou_thres, NmsScratch s) {
     s.mask[(size_t)i * words + wj] = bits;
 }
 
-// greedy scan + gather (single CTA)
+// greedy scan + gather (single CTA).  The suppression matrix of the M candidates is first copied into shared
+// memory when it fits (M <= ~700: 48 KB); ONE warp then walks the sorted candidates with the "removed" bit set
+// spread over its lanes (lane l owns words l, l + 32: M <= 4096) -- no block barrier per kept box (the round-1
+// kernel paid two __syncthreads and a dependent global read per box: 37 us at M = 100) -- and the whole CTA
+// gathers the kept rows.  gain > 0 folds ultralytics' scale_boxes (letterbox -> frame) into the gather.
+#define NMS_SMEM_MASK_BYTES 49152
 __global__ void __launch_bounds__(256)
 nms_scan_kernel(const float *__restrict__ pred, int nc, int n_extra, int A, int max_det,
-                NmsScratch s, float *__restrict__ out, int *__restrict__ count_out) {
-    extern __shared__ unsigned long long s_removed[];
+                NmsScratch s, float *__restrict__ out, int *__restrict__ count_out,
+                float gain, float pad_x, float pad_y, float w0, float h0) {
+    extern __shared__ unsigned long long s_mask[];
     __shared__ int s_keep_n;
-    __shared__ int s_cur_keep;
     const int M = min(s.count[0], NMS_MAX_CAND);
     const int words = (M + 63) / 64;
-    for (int w = threadIdx.x; w < words; w += blockDim.x) s_removed[w] = 0ull;
-    if (threadIdx.x == 0) s_keep_n = 0;
+    const bool cached = (size_t)M * words * 8 <= NMS_SMEM_MASK_BYTES;
+    if (cached)
+        for (int e = threadIdx.x; e < M * words; e += blockDim.x) s_mask[e] = s.mask[e];
+    int *keep = reinterpret_cast<int *>(s.sarea);  // sarea[] (float[A]) is dead after the mask kernel: the kept ranks
     __syncthreads();
-    const int cols = 6 + n_extra;
-    for (int i = 0; i < M; i++) {
-        if (s_keep_n >= max_det) break;
-        const bool removed = (s_removed[i >> 6] >> (i & 63)) & 1ull;
-        __syncthreads();
-        if (removed) continue;
-        if (threadIdx.x == 0) { s_cur_keep = s_keep_n; s_keep_n = s_keep_n + 1; }
-        for (int w = threadIdx.x; w < words; w += blockDim.x)
-            s_removed[w] |= s.mask[(size_t)i * words + w];
-        __syncthreads();
-        // gather row (original, un-offset box)
-        const int row = s_cur_keep;
-        const int a = s.cand[s.order[i]];
-        if (threadIdx.x == 0) {
-            const float x = pred[a], y = pred[(size_t)A + a];
-            const float dw = pred[(size_t)2 * A + a] / 2.f, dh = pred[(size_t)3 * A + a] / 2.f;
-            float *o = out + (size_t)row * cols;
-            o[0] = x - dw; o[1] = y - dh; o[2] = x + dw; o[3] = y + dh;
-            o[4] = s.conf[a]; o[5] = (float)s.cls[a];
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        int nkeep = 0;
+        if (words <= 64) {
+            unsigned long long rem0 = 0ull, rem1 = 0ull;
+            for (int i = 0; i < M && nkeep < max_det; i++) {
+                const int w = i >> 6;
+                const unsigned long long rw = __shfl_sync(0xffffffffu, (w >> 5) ? rem1 : rem0, w & 31);
+                if ((rw >> (i & 63)) & 1ull) continue;                 // warp-uniform
+                if (lane == 0) keep[nkeep] = i;
+                nkeep++;
+                const unsigned long long *row = cached ? s_mask + (size_t)i * words : s.mask + (size_t)i * words;
+                if (lane < words) rem0 |= row[lane];
+                if (lane + 32 < words) rem1 |= row[lane + 32];
+            }
+        } else {                              // > 4096 candidates (rare): test each box against the kept ones' mask rows
+            for (int i = 0; i < M && nkeep < max_det; i++) {
+                bool removed = false;
+                for (int k0 = 0; k0 < nkeep && !removed; k0 += 32) {
+                    const int k = k0 + lane;
+                    const bool hit = k < nkeep && ((s.mask[(size_t)keep[k] * words + (i >> 6)] >> (i & 63)) & 1ull);
+                    removed = __any_sync(0xffffffffu, hit);
+                }
+                if (removed) continue;
+                if (lane == 0) keep[nkeep] = i;
+                __syncwarp();
+                nkeep++;
+            }
         }
-        for (int e = threadIdx.x; e < n_extra; e += blockDim.x)
-            out[(size_t)row * cols + 6 + e] = pred[(size_t)(4 + nc + e) * A + a];
+        if (lane == 0) s_keep_n = nkeep;
     }
     __syncthreads();
-    if (threadIdx.x == 0) count_out[0] = s_keep_n;
+    const int nkeep = s_keep_n;
+    const int cols = 6 + n_extra;
+    for (int r = threadIdx.x; r < nkeep; r += blockDim.x) {            // gather (original, un-offset boxes)
+        const int a = s.cand[s.order[keep[r]]];
+        const float x = pred[a], y = pred[(size_t)A + a];
+        const float dw = pred[(size_t)2 * A + a] / 2.f, dh = pred[(size_t)3 * A + a] / 2.f;
+        float x1 = x - dw, y1 = y - dh, x2 = x + dw, y2 = y + dh;
+        if (gain > 0.f) {
+            x1 = fminf(fmaxf((x1 - pad_x) / gain, 0.f), w0); y1 = fminf(fmaxf((y1 - pad_y) / gain, 0.f), h0);
+            x2 = fminf(fmaxf((x2 - pad_x) / gain, 0.f), w0); y2 = fminf(fmaxf((y2 - pad_y) / gain, 0.f), h0);
+        }
+        float *o = out + (size_t)r * cols;
+        o[0] = x1; o[1] = y1; o[2] = x2; o[3] = y2;
+        o[4] = s.conf[a]; o[5] = (float)s.cls[a];
+        for (int e = 0; e < n_extra; e++) o[6 + e] = pred[(size_t)(4 + nc + e) * A + a];
+    }
+    if (threadIdx.x == 0) count_out[0] = nkeep;
+}
+
+static int nms_after_scores(const float *pred_dev, int num_classes, int num_extra, int A, float conf_thres, float iou_thres,
+                            int max_det, int agnostic, float *out_dev, int32_t *count_dev, const NmsScratch &s,
+                            float gain, float pad_x, float pad_y, float w0, float h0, cudaStream_t st) {
+    nms_compact_kernel<<<1, 1024, 0, st>>>(A, conf_thres, s);
+    SSB_CHECK_LAUNCH();
+    // the candidate count lives on the device: grids are sized for the worst case
+    nms_rank_kernel<<<(A + 127) / 128, 128, 0, st>>>(pred_dev, A, agnostic, s);
+    SSB_CHECK_LAUNCH();
+    const int Mc = A < NMS_MAX_CAND ? A : NMS_MAX_CAND;
+    const int words = (Mc + 63) / 64;
+    dim3 mb(32, 8), mg((words + 31) / 32, (Mc + 7) / 8);
+    nms_mask_kernel<<<mg, mb, 0, st>>>(iou_thres, s);
+    SSB_CHECK_LAUNCH();
+    static const int key = ssb_new_key();
+    if (ssb_first_on_device(key))
+        SSB_CHECK_CUDA(cudaFuncSetAttribute(nms_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NMS_SMEM_MASK_BYTES));
+    nms_scan_kernel<<<1, 256, NMS_SMEM_MASK_BYTES, st>>>(pred_dev, num_classes, num_extra, A, max_det, s, out_dev, count_dev,
+                                                        gain, pad_x, pad_y, w0, h0);
+    SSB_CHECK_LAUNCH();
+    return 0;
 }
 
 extern "C" int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extra, int num_anchors,
@@ -201,19 +254,32 @@ extern "C" int ssb_yolo_nms(const float *pred_dev, int num_classes, int num_extr
     const int A = num_anchors;
     nms_score_kernel<<<(A + 255) / 256, 256, 0, st>>>(pred_dev, num_classes, A, s);
     SSB_CHECK_LAUNCH();
-    nms_compact_kernel<<<1, 1024, 0, st>>>(A, conf_thres, s);
-    SSB_CHECK_LAUNCH();
-    // the candidate count lives on the device: grids are sized for the worst case
-    nms_rank_kernel<<<(A + 127) / 128, 128, 0, st>>>(pred_dev, A, agnostic, s);
-    SSB_CHECK_LAUNCH();
-    const int Mc = A < NMS_MAX_CAND ? A : NMS_MAX_CAND;
-    const int words = (Mc + 63) / 64;
-    dim3 mb(32, 8), mg((words + 31) / 32, (Mc + 7) / 8);
-    nms_mask_kernel<<<mg, mb, 0, st>>>(iou_thres, s);
-    SSB_CHECK_LAUNCH();
-    nms_scan_kernel<<<1, 256, (size_t)words * 8, st>>>(pred_dev, num_classes, num_extra, A, max_det, s, out_dev, count_dev);
-    SSB_CHECK_LAUNCH();
-    return 0;
+    return nms_after_scores(pred_dev, num_classes, num_extra, A, conf_thres, iou_thres, max_det, agnostic, out_dev, count_dev,
+                            s, 0.f, 0.f, 0.f, 0.f, 0.f, st);
+}
+
+int ssb_launch_decode_v8_scored(const float *raw, int nc, int nk, int in_h, int in_w, float *pred, float *conf, int *cls,
+                                cudaStream_t st);
+
+// The whole detector post-process of a YOLOv8 head in ONE call, 5 launches: decode (+ best class per anchor fused),
+// ordered compaction, stable rank, suppression matrix, scan + gather (+ scale_boxes fused when gain > 0).
+// Same results as ssb_yolo_decode_v8 -> ssb_yolo_nms -> ssb_yolo_scale_boxes.
+extern "C" int ssb_yolo_postprocess_v8(const float *raw_dev, int num_classes, int num_kpts, int in_h, int in_w,
+                                       float conf_thres, float iou_thres, int max_det, int agnostic,
+                                       float gain, float pad_x, float pad_y, int w0, int h0,
+                                       float *pred_scratch_dev, float *out_dev, int32_t *count_dev, void *scratch_dev,
+                                       ssb_stream_t stream) {
+    if (!raw_dev || !pred_scratch_dev || !out_dev || !count_dev || !scratch_dev) { ssb_set_error("null argument"); return -1; }
+    if (max_det < 1) { ssb_set_error("bad NMS dims"); return -1; }
+    const int A = ssb_yolo_num_anchors(in_h, in_w);
+    if (A <= 0) { ssb_set_error("bad head geometry"); return -1; }
+    cudaStream_t st = (cudaStream_t)stream;
+    NmsScratch s;
+    nms_carve((char *)scratch_dev, A, &s);
+    int rc = ssb_launch_decode_v8_scored(raw_dev, num_classes, num_kpts, in_h, in_w, pred_scratch_dev, s.conf, s.cls, st);
+    if (rc) return rc;
+    return nms_after_scores(pred_scratch_dev, num_classes, 3 * num_kpts, A, conf_thres, iou_thres, max_det, agnostic, out_dev,
+                            count_dev, s, gain, pad_x, pad_y, (float)w0, (float)h0, st);
 }
 
 // ultralytics scale_boxes (ops.py; SURVEY.md C.2 "boxes are scaled back from letterbox to the original

@@ -463,6 +463,7 @@ __global__ void iou_cost_arrays_kernel(const double *tlwh, int n_tracks, const f
 // rectangular LSAP, one warp, scipy tie-breaks (oracle/lsap.c is the C twin)
 // ---------------------------------------------------------------------------
 struct LsapSmem {
+    long long lsap_t_stage, lsap_t_solve;   // clock64 deltas of the last lsap_block (thread 0; debug builds read them)
     double *u, *v, *spc, *cost;   // cost == nullptr -> read global
     int *path, *row4col, *col4row, *remaining;
     unsigned char *SR, *SC;
@@ -636,9 +637,11 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
 // Solve with the whole block staging, warp 0 iterating.  C is [nr0][nc0]
 // row-major (ld = nc0).  Results in ORIGINAL orientation: col4row_out[nr0],
 // row4col_out[nc0] (-1 = unassigned).  Must be called by all threads.
-__device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapSmem m,
+__device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapSmem &m,
                            size_t cost_smem_bytes, int *col4row_out, int *row4col_out) {
     const int tid = threadIdx.x, lane = tid & 31;
+    const long long t_l0 = clock64();
+    m.lsap_t_stage = m.lsap_t_solve = 0;
     if (nr0 == 0 || nc0 == 0) {
         for (int i = tid; i < nr0; i += blockDim.x) col4row_out[i] = -1;
         for (int j = tid; j < nc0; j += blockDim.x) row4col_out[j] = -1;
@@ -658,6 +661,7 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     for (int i = tid; i < nr; i += blockDim.x) { m.u[i] = 0.0; m.col4row[i] = -1; }
     for (int j = tid; j < nc; j += blockDim.x) { m.v[j] = 0.0; m.row4col[j] = -1; m.path[j] = -1; }
     __syncthreads();
+    m.lsap_t_stage = clock64() - t_l0;
 
     // Too big for shared memory (C4: 344 x 498): every search step would wait for an L2 round trip.
     // The clamped matrices are one background value (their maximum) plus a few real entries per row,
@@ -666,7 +670,7 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     // global-memory path when the real entries do not fit.
     LsapSparse sp;
     bool sparse = false;
-    if (!staged && nc <= 512) {
+    if (!staged && nc <= 1024) {
         __shared__ double s_bg[8];
         __shared__ int s_total;
         const int wid = tid >> 5, nwarp = blockDim.x >> 5;
@@ -717,16 +721,20 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
         __syncthreads();
     }
 
-    if (tid < 32 && nc <= 512) {
+    if (tid < 32 && nc <= 1024) {
+        // 513 .. 1024 working columns (C4 once more than 512 tracks are alive): 32 columns per lane; part of the
+        // per-column state then lives in (L1-resident) local memory, still far from the global-memory walk below
         const double *Cw = staged ? m.cost : C;
         bool okr;
         if (sparse) {
             if (nc <= 128) okr = lsap_warp_reg<4, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
             else if (nc <= 256) okr = lsap_warp_reg<8, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-            else okr = lsap_warp_reg<16, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+            else if (nc <= 512) okr = lsap_warp_reg<16, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+            else okr = lsap_warp_reg<32, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
         } else if (nc <= 128) okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         else if (nc <= 256) okr = lsap_warp_reg<8, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else okr = lsap_warp_reg<16, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else if (nc <= 512) okr = lsap_warp_reg<16, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        else okr = lsap_warp_reg<32, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         if (!okr) {
             for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
             for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
@@ -817,6 +825,7 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
         }
     }
     __syncthreads();
+    m.lsap_t_solve = clock64() - t_l0;
     if (!tr) {
         for (int i = tid; i < nr0; i += blockDim.x) col4row_out[i] = m.col4row[i];
         for (int j = tid; j < nc0; j += blockDim.x) row4col_out[j] = m.row4col[j];
@@ -871,7 +880,13 @@ __global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d,
     LsapSmem m;
     lsap_carve(smem, L, m);
     const int rows = fs.cnt[FC_N_CONF], cols = n;
+#ifdef SSB_BASELINES            // phase stamps (libssb_dbg.so, tools/time_stages.py): cnt[20..23] = start, staged, solved, lists
+    const long long t_a0 = clock64();
+#endif
     lsap_block(fs.cost_a, rows, cols, m, cost_smem_bytes, fs.col4row, fs.row4col);
+#ifdef SSB_BASELINES
+    const long long t_a1 = clock64();
+#endif
     const int n_unconf = fs.cnt[FC_N_UNCONF];
     // unmatched detections, part 1: unassigned columns ascending
     {
@@ -915,6 +930,12 @@ __global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d,
         fs.cnt[FC_N_MATCH] = tot3[0];
         fs.cnt[FC_N_MATCH_A] = tot3[0];
         fs.cnt[FC_ROWS_A] = rows; fs.cnt[FC_COLS_A] = cols;
+#ifdef SSB_BASELINES
+        fs.cnt[20] = (int)(t_a1 - t_a0);
+        fs.cnt[21] = (int)(clock64() - t_a1);
+        fs.cnt[22] = (int)m.lsap_t_stage;
+        fs.cnt[23] = (int)m.lsap_t_solve;
+#endif
     }
 }
 

@@ -50,7 +50,9 @@ class StrongSORT:
         if nbytes < 0:
             _lib.check(-1, "ssb_workspace_bytes")
         with torch.cuda.device(self.device):
-            self.stream = torch.cuda.Stream(device=self.device)
+            # high priority: when the association of frame k shares the GPU with the OSNet of frame k+1 (two-stage
+            # pipeline), its many small kernels get the SM slots the big ReID CTAs free up first
+            self.stream = torch.cuda.Stream(device=self.device, priority=-1)
             self._ws = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=self.device)
             base = (self._ws.data_ptr() + 255) & ~255
             h = C.c_void_p()

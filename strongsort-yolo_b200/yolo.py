@@ -102,6 +102,71 @@ class YoloV8Decode:
         return self._out
 
 
+class YoloV8Post:
+    """The whole detector post-process of a raw YOLOv8 head in ONE C call / 5 launches (``ssb_yolo_postprocess_v8``):
+    DFL decode with the best class per anchor fused, confidence filter + class-aware NMS, scale_boxes back to the
+    frame fused into the gather.  ``submit`` enqueues the work of one frame on a stream and returns a ticket;
+    ``result`` waits for THAT ticket only and returns the detections [M, 6 (+extras)] (a private device copy), so a
+    stream loop can keep the post-process of frame k+1 in flight while frame k is being tracked."""
+
+    def __init__(self, num_classes=80, num_kpts=0, in_h=384, in_w=640, frame_hw=(1080, 1920), device="cuda:0",
+                 conf=DEFAULT_CONF, iou=DEFAULT_IOU, max_det=DEFAULT_MAX_DET, agnostic=False, depth=3):
+        torch = _lib.require_cuda()
+        self._torch, self._lib = torch, _lib.load()
+        self.device = torch.device(device)
+        self.nc, self.nk, self.in_h, self.in_w = int(num_classes), int(num_kpts), int(in_h), int(in_w)
+        self.frame_hw = (int(frame_hw[0]), int(frame_hw[1]))
+        self.conf, self.iou, self.max_det, self.agnostic = float(conf), float(iou), int(max_det), bool(agnostic)
+        self.A = int(self._lib.ssb_yolo_num_anchors(self.in_h, self.in_w))
+        if self.A <= 0:
+            raise ValueError("network input size must be a positive multiple of 32")
+        self.cols = 6 + 3 * self.nk
+        self.gain, self.pad_x, self.pad_y = letterbox_params((self.in_h, self.in_w), self.frame_hw)
+        nbytes = int(self._lib.ssb_nms_scratch_bytes(self.A))
+        dev = self.device
+        self._slots = []
+        for _ in range(int(depth)):
+            self._slots.append({
+                "scratch": torch.empty(nbytes + 256, dtype=torch.uint8, device=dev),
+                "pred": torch.empty((4 + self.nc + 3 * self.nk, self.A), dtype=torch.float32, device=dev),
+                "out": torch.zeros((self.max_det, self.cols), dtype=torch.float32, device=dev),
+                "count": torch.zeros(4, dtype=torch.int32, device=dev),
+                "count_pin": torch.zeros(4, dtype=torch.int32).pin_memory(),
+                "done": torch.cuda.Event(),
+            })
+        self._k = 0
+
+    def submit(self, raw, stream=None):
+        torch = self._torch
+        if raw.dim() == 3:
+            raw = raw[0]
+        if tuple(raw.shape) != (64 + self.nc + 3 * self.nk, self.A):
+            raise ValueError(f"raw head shape {tuple(raw.shape)} != {(64 + self.nc + 3 * self.nk, self.A)}")
+        raw = raw.contiguous()
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        sl = self._slots[self._k % len(self._slots)]
+        self._k += 1
+        base = (sl["scratch"].data_ptr() + 255) & ~255
+        with torch.cuda.stream(st):
+            _lib.check(self._lib.ssb_yolo_postprocess_v8(
+                _lib.ptr(raw), self.nc, self.nk, self.in_h, self.in_w, self.conf, self.iou, self.max_det,
+                int(self.agnostic), self.gain, self.pad_x, self.pad_y, self.frame_hw[1], self.frame_hw[0],
+                _lib.ptr(sl["pred"]), _lib.ptr(sl["out"]), _lib.ptr(sl["count"]), C.c_void_p(base),
+                C.c_void_p(st.cuda_stream)), "ssb_yolo_postprocess_v8")
+            sl["count_pin"].copy_(sl["count"], non_blocking=True)
+            sl["done"].record(st)
+        return sl
+
+    def result(self, ticket):
+        """Detections of a submitted frame: waits for its event (not for the stream)."""
+        ticket["done"].synchronize()
+        m = int(ticket["count_pin"][0])
+        return ticket["out"][:m]
+
+    def __call__(self, raw, stream=None):
+        return self.result(self.submit(raw, stream))
+
+
 # yolov5n/s/m/l/x anchors (models/yolov5*.yaml), pixels, P3/8, P4/16, P5/32
 V5_ANCHORS = np.asarray([[10, 13, 16, 30, 33, 23], [30, 61, 62, 45, 59, 119], [116, 90, 156, 198, 373, 326]],
                         dtype=np.float32).reshape(3, 3, 2)

@@ -76,6 +76,34 @@ def test_c2_head_decode_nms_scale_recovers_frame_detections():
     np.testing.assert_array_equal(got[:, 5], fr.dets[order, 5])
 
 
+def test_fused_postprocess_equals_the_three_calls():
+    """ssb_yolo_postprocess_v8 (one call, 5 launches, look-ahead tickets) == decode -> NMS -> scale_boxes, bit for bit."""
+    import torch
+    rng = np.random.default_rng(5)
+    net, frame = (384, 640), (1080, 1920)
+    st = synth.make_stream("C2", render=False)
+    dec = yolo.YoloV8Decode(80, 0, net[0], net[1])
+    nms = yolo.YoloNMS(num_classes=80, max_anchors=dec.A)
+    post = yolo.YoloV8Post(80, 0, net[0], net[1], frame, depth=3)
+    g, px, py = yolo.letterbox_params(net, frame)
+    raws, want = [], []
+    for k in range(4):
+        fr = st.next_frame()
+        d = fr.dets.copy()
+        d[:, 5] = np.where(fr.gt_ids >= 0, fr.gt_ids % 80, 79)
+        d[:, [0, 2]] = d[:, [0, 2]] * g + px
+        d[:, [1, 3]] = d[:, [1, 3]] * g + py
+        raw = torch.as_tensor(yolo.synth_raw_head_v8(d, 80, net[0], net[1], rng=rng)).cuda()
+        raws.append(raw)
+        nms(dec(raw))
+        out, cnt = nms.scale_boxes(net, frame)
+        want.append(out[:int(cnt[0].item())].clone())
+    tickets = [post.submit(r) for r in raws[:3]]            # three frames in flight
+    got = [post.result(t).clone() for t in tickets] + [post(raws[3]).clone()]
+    for a, b in zip(got, want):
+        assert a.shape == b.shape and torch.equal(a, b)
+
+
 def test_camera_update_matches_oracle_and_tracking_continues():
     from strongsort_yolo_b200.strong_sort import StrongSORT
     st = synth.make_stream("C1", render=False)

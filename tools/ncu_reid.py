@@ -18,9 +18,11 @@ from strongsort_yolo_b200.strong_sort import StrongSORT  # noqa: E402
 
 
 def main():
-    lib = _lib.load(debug=True)
+    backend = sys.argv[1] if len(sys.argv) > 1 else "tc"
+    dbg = backend != "tc"                       # the product library for the product path, libssb_dbg.so for the baselines
+    lib = _lib.load(debug=dbg)
     P = lambda t: C.c_void_p(t.data_ptr())
-    trk = StrongSORT(debug=True)
+    trk = StrongSORT(debug=dbg)
     st = synth.make_stream("C2")
     fr = [st.next_frame() for _ in range(3)][-1]
     n = len(fr.dets)
@@ -30,7 +32,6 @@ def main():
     feats = torch.zeros((n, 512), dtype=torch.float32, device="cuda")
     sp = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(lib.ssb_crop_boxes(P(dets), n, 1080, 1920, P(boxes), sp))
-    backend = sys.argv[1] if len(sys.argv) > 1 else "tc"
     trk.set_reid_backend(backend)
     for r in range(3):
         if r == 2:

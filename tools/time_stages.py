@@ -81,6 +81,13 @@ def main():
     out["stem_phase_cycles"] = [int(v - d[41]) for v in d[42:41 + int(d[40])]]
     # stage-A-like clamped cost matrices from the live tracker
     a, b = trk.debug_costs()
+    # phase stamps of the last assign_stage_a_kernel (debug build): cycles
+    pa, pb, pd = C.c_void_p(), C.c_void_p(), C.c_void_p()
+    _lib.check(lib.ssb_debug_cost_ptrs(trk._h, C.byref(pa), C.byref(pb), C.byref(pd)))
+    from strongsort_yolo_b200.strong_sort import _wrap_device
+    cnt = _wrap_device(torch, pd.value, (16,), "<i4", trk.device).cpu().numpy()     # cnt[FC_ROWS_A ...]
+    out["assign_stage_a_cycles"] = {"lsap_block": int(cnt[10]), "lists": int(cnt[11]), "staged_at": int(cnt[12]),
+                                    "solved_at": int(cnt[13])}
     for name, m in (("lsap_stageA", a), ("lsap_stageB", b)):
         if m.size:
             md = torch.as_tensor(m).cuda()
