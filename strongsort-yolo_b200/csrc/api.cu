@@ -47,6 +47,7 @@ static int env_flag(const char *name, int dflt) {
     return v && *v ? atoi(v) != 0 : dflt;
 }
 bool ssb_pdl_enabled() { static const int on = env_flag("SSB_PDL", 1); return on != 0; }
+bool ssb_pw_fused() { static const int on = env_flag("SSB_PW_FUSED", 1); return on != 0; }
 bool ssb_split_enabled() { static const int on = env_flag("SSB_SPLIT", 1); return on != 0; }
 int ssb_num_sms() {
     int dev = 0;
@@ -253,7 +254,11 @@ extern "C" int ssb_associate(ssb_tracker *t, int slot, int n, int h, int w, cons
 static int reid_forward_split(ssb_tracker *t, const uint8_t *img_dev, int h, int w, int pitch, const int *boxes,
                               int n, float *feats, cudaStream_t st) {
     if (!t->side_stream) {
-        SSB_CHECK_CUDA(cudaStreamCreateWithFlags(&t->side_stream, cudaStreamNonBlocking));
+        // same priority as the caller's stream: the two halves must interleave CTA by CTA (a high-priority half simply
+        // runs first and the tail-filling effect is gone: 638 instead of 515 us per 99 crops, measured)
+        int prio = 0;
+        SSB_CHECK_CUDA(cudaStreamGetPriority(st, &prio));
+        SSB_CHECK_CUDA(cudaStreamCreateWithPriority(&t->side_stream, cudaStreamNonBlocking, prio));
         SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
         SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
     }

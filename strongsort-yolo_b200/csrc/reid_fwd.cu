@@ -34,7 +34,15 @@ static int reid_forward_planes(ssb_tracker *t, int slot, const uint8_t *img, int
     int rc = ssb_reid_tc_stem(img, h, w, pitch, boxes, W + t->w_tc_off[9], A, n, t->tc_status, st, 1);
     if (rc) return rc;
     float *cur = A, *nxt = Bf;
+    const bool fused = ssb_pw_fused();
     for (int b = 0; b < 6; b++) {
+        if (fused && (b == 1 || b == 3)) {          // OSBlock + its stage's transition layer in one launch (9 launches in all)
+            rc = ssb_reid_tc4_block_pw(b, cur, nxt, W + t->w_tc_off[10 + b], W + t->w_tc_off[6 + (b == 1 ? 0 : 1)], n,
+                                       t->tc_status, st);
+            if (rc) return rc;
+            { float *tmp = cur; cur = nxt; nxt = tmp; }
+            continue;
+        }
         rc = ssb_reid_tc4_block(b, cur, nxt, W + t->w_tc_off[10 + b], n, t->tc_status, st);
         if (rc) return rc;
         { float *tmp = cur; cur = nxt; nxt = tmp; }

@@ -46,8 +46,13 @@ __host__ __device__ constexpr int rup128_4(int a) { return (a + 127) / 128 * 128
 __host__ __device__ constexpr int pow2cols(int c) { return c <= 32 ? 32 : c <= 64 ? 64 : c <= 128 ? 128 : c <= 256 ? 256 : 512; }
 
 template <int CIN_, int MID_, int MIDP_, int COUT_, int H_, int W_, int R_, int NB_, bool DOWN_, int SEG_,
-          int THREADS_, int MINB_, bool SPLIT_>
+          int THREADS_, int MINB_, bool SPLIT_, bool PW_ = false>
 struct B4 {
+    // PW: the stage's transition layer (conv1x1 COUT -> COUT + ReLU + avgpool 2x2, the former pw_tc_kernel launch) is
+    // fused behind the block: the block's output never goes to HBM -- the final epilogue writes it as an operand map
+    // in shared memory with the tile rows in pooling-window order, one more tcgen05 GEMM runs on it, and the 2x2
+    // average is a 2-step shuffle over adjacent TMEM lanes; what is stored is the pooled map's operand planes.
+    static constexpr bool PW = PW_;
     static constexpr int CIN = CIN_, MID = MID_, MIDP = MIDP_, COUT = COUT_, H = H_, W = W_, R = R_, NB = NB_;
     static constexpr int SEG = SEG_, THREADS = THREADS_, MINB = MINB_;
     static constexpr bool DOWN = DOWN_, SPLIT = SPLIT_, EXCH = NB_ > 1;
@@ -75,6 +80,7 @@ struct B4 {
     static constexpr int DNW_HALF_B = DOWN ? CIN * COUT * 2 : 0, DNW_B = 2 * DNW_HALF_B;
     static constexpr int LCW_B = MIDP * MIDP * 4;
     static constexpr int WALL_B = C1W_B + DNW_B + 10 * LCW_B;
+    static constexpr int PWW_HALF_B = COUT * COUT * 2, PWW_B = 2 * PWW_HALF_B;   // transition weights [COUT/8][COUT][8] hi | lo
     static constexpr int C3W_HALF_B = MIDP * COUT * 2, C3W_B = 2 * C3W_HALF_B;
     // PAR (floats): B1[MIDP] | 10 x { DW[9][MIDP], B[MIDP] } | B3[COUT] | GW1[MIDP][2] | GB1[2] |
     //               GW2[2][MIDP] | GB2[MIDP]          (identical to reid_tc3's B3: same weight blob)
@@ -102,6 +108,7 @@ struct B4 {
     static_assert(CG % 2 == 0 && (CG / 2) % CPW == 0 && W % XL == 0, "depthwise warp tasks");
     static_assert(SEG * TPS <= NWARPS, "depthwise warp tasks fit the CTA");
     static_assert(WALL_B + XS_B < (1 << 20), "mbarrier tx count");
+    static_assert(!PW || (!DOWN && CIN == COUT && R % 2 == 0 && (PWW_B <= MAP_B || PWW_B <= WALL_B)), "fused transition");
     // global weight blob sections (bytes): C1W | DNW | LCW[10] | PAR (fp32) | W3 (fp32 [MIDP][COUT])
     static constexpr int G_PAR = rup128_4(WALL_B);
     static constexpr int G_W3 = G_PAR + rup128_4(NPAR * 4);
@@ -196,7 +203,7 @@ template <class C>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__ y,
                 const unsigned char *__restrict__ wblob, int n_crops, int *__restrict__ status,
-                long long *__restrict__ dbg) {
+                long long *__restrict__ dbg, const unsigned char *__restrict__ pwblob) {
     extern __shared__ __align__(1024) unsigned char smem[];
     cg::cluster_group cluster = cg::this_cluster();
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -465,6 +472,16 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
             tc::fence_after_sync();
             fstamp(lc);                        // f4: barrier B done
             stamp();                           // T ready
+            if (C::PW && lc == 9 && tid == 0) {
+                // every pointwise MMA has completed: X1 and the LightConv weights are dead -- the transition weights
+                // land in whichever of the two regions holds them, long before the final epilogue needs them
+                unsigned char *dstw = C::PWW_B <= C::MAP_B ? sX1 : sW;
+                tc::mbar_arrive_expect_tx(bar_w, C::PWW_B);
+                for (int o = 0; o < C::PWW_B; o += 32768) {
+                    const int nb = C::PWW_B - o < 32768 ? C::PWW_B - o : 32768;
+                    tc::bulk_g2s(dstw + o, pwblob + o, nb, bar_w);
+                }
+            }
             // the next stream starts from X1: its pointwise conv runs under this depthwise pass
             if (last && s < 3 && issuer) issue_pw(sX1, lc + 1, 0, C::NT);
             // the previous stream's conv3 MMAs read P: done before this stream overwrites it
@@ -725,9 +742,82 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                 if (!C::DOWN) { f0 += r[q]; f1 += r[q + 1]; }
                 split2(fmaxf(f0, 0.f), fmaxf(f1, 0.f), h[q >> 1], l[q >> 1]);
             }
-            unsigned char *dst = yout + (size_t)(c0 / 8 + j) * C::HW * 16 + gp * 16;
-            *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
-            *reinterpret_cast<uint4 *>(dst + Y_LO) = *reinterpret_cast<uint4 *>(l);
+            if (!C::PW) {
+                unsigned char *dst = yout + (size_t)(c0 / 8 + j) * C::HW * 16 + gp * 16;
+                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+                *reinterpret_cast<uint4 *>(dst + Y_LO) = *reinterpret_cast<uint4 *>(l);
+            } else {
+                // operand map of the transition GEMM (the dead input-operand buffer): pixel (lr, col) goes to tile row
+                // (pooled pixel) * 4 + (window position), so the four members of a 2x2 window are adjacent TMEM lanes
+                const int p = i * 128 + quad * 32 + lane, lr = p / C::W, col = p % C::W;
+                const int mrow = (((lr >> 1) * (C::W / 2) + (col >> 1)) << 2) + ((lr & 1) << 1) + (col & 1);
+                unsigned char *dst = sP + (c0 / 8 + j) * C::PLANE_B + mrow * 16;
+                *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+                *reinterpret_cast<uint4 *>(dst + C::XS_HALF_B) = *reinterpret_cast<uint4 *>(l);
+            }
+        }
+    }
+    if (C::PW) {
+        // ---- fused transition: relu(conv1x1(y) + b), 2x2 average, stored as the pooled map's operand planes
+        tc::fence_async_smem();
+        if (!tc::mbar_wait(bar_w, 1)) ok = false;              // transition weights landed (issued after layer 9's drain)
+        tc::fence_before_sync();
+        __syncthreads();                                       // y map complete; conv3 accumulators fully drained
+        tc::fence_after_sync();
+        if (issuer) {
+            if (tc::elect_one()) {
+                const unsigned char *wsm = C::PWW_B <= C::MAP_B ? sX1 : sW;
+                const uint64_t ah0 = tc::make_smem_desc(tc::smem_u32(sP), C::PLANE_B, 128);
+                const uint64_t al0 = dadv(ah0, C::XS_HALF_B / 16);
+                const uint64_t bh0 = tc::make_smem_desc(tc::smem_u32(wsm), C::COUT * 16, 128);
+                const uint64_t bl0 = dadv(bh0, C::PWW_HALF_B / 16);
+#pragma unroll
+                for (int t = 0; t < C::NT; t++) {
+                    const uint32_t d = tmem + C::TM_C3 + t * C::COUT;          // the drained conv3 accumulator columns
+#pragma unroll
+                    for (int ks = 0; ks < C::COUT / 16; ks++) {
+                        const int ka = t * 128 + ks * 2 * C::NPX, kb = ks * 2 * C::COUT;
+                        mma3(d, dadv(ah0, ka), dadv(al0, ka), dadv(bh0, kb), dadv(bl0, kb), IDESC_OUT, ks > 0);
+                    }
+                }
+                tc::mma_commit(bar_c1);
+            }
+            __syncwarp();
+        }
+        if (!tc::mbar_wait(bar_c1, 1)) ok = false;
+        tc::fence_after_sync();
+        constexpr int HWO = C::HW / 4;                          // pooled map
+        unsigned char *pout = y + (size_t)crop * (4 * C::COUT * HWO);
+        const float *pwb = reinterpret_cast<const float *>(pwblob + C::PWW_B);
+        constexpr int NU2 = C::NT * (C::COUT / 16), U2 = (NU2 + C::GROUPS - 1) / C::GROUPS;
+#pragma unroll 1
+        for (int e = 0; e < U2; e++) {
+            const int u = grp + e * C::GROUPS;
+            if (u >= NU2) continue;                             // warp-uniform
+            const int t = u / (C::COUT / 16), c0 = (u - t * (C::COUT / 16)) * 16;
+            float v[16];
+            tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + C::TM_C3 + t * C::COUT + c0, v);
+            const int m = quad * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                float f = fmaxf(v[j] + pwb[c0 + j], 0.f);
+                f += __shfl_xor_sync(0xffffffffu, f, 1);
+                f += __shfl_xor_sync(0xffffffffu, f, 2);
+                v[j] = f * 0.25f;
+            }
+            if ((m & 3) == 0) {
+                const size_t gpo = (size_t)band * (C::NPX / 4) + t * 32 + (m >> 2);
+#pragma unroll
+                for (int j = 0; j < 2; j++) {
+                    __align__(16) __half2 h[4];
+                    __align__(16) __half2 l[4];
+#pragma unroll
+                    for (int q = 0; q < 8; q += 2) split2(v[j * 8 + q], v[j * 8 + q + 1], h[q >> 1], l[q >> 1]);
+                    unsigned char *dst = pout + (size_t)(c0 / 8 + j) * HWO * 16 + gpo * 16;
+                    *reinterpret_cast<uint4 *>(dst) = *reinterpret_cast<uint4 *>(h);
+                    *reinterpret_cast<uint4 *>(dst + 2 * C::COUT * HWO) = *reinterpret_cast<uint4 *>(l);
+                }
+            }
         }
     }
     stamp();                                   // final epilogue done
@@ -767,12 +857,15 @@ using K0 = B4<16, 16, 16, 64, 64, 32, SSB_S2_R, 64 / SSB_S2_R, true, S2_SEG, S2_
 using K1 = B4<64, 16, 16, 64, 64, 32, SSB_S2_R, 64 / SSB_S2_R, false, S2_SEG, S2_THREADS, S2_MINB, SSB_S2_SPLIT>;
 using K2 = B4<64, 24, 32, 96, 32, 16, SSB_S3_R, 32 / SSB_S3_R, true, 4, 512, 1, SSB_S3_SPLIT>;
 using K3 = B4<96, 24, 32, 96, 32, 16, SSB_S3_R, 32 / SSB_S3_R, false, 4, 512, 1, SSB_S3_SPLIT>;
+// blocks 1 and 3 with their stage's transition layer fused behind them (the forward's default)
+using K1F = B4<64, 16, 16, 64, 64, 32, SSB_S2_R, 64 / SSB_S2_R, false, S2_SEG, S2_THREADS, S2_MINB, SSB_S2_SPLIT, true>;
+using K3F = B4<96, 24, 32, 96, 32, 16, SSB_S3_R, 32 / SSB_S3_R, false, 4, 512, 1, SSB_S3_SPLIT, true>;
 using K4 = B4<96, 32, 32, 128, 16, 8, 16, 1, true, 7, 512, 1, false>;
 using K5 = B4<128, 32, 32, 128, 16, 8, 16, 1, false, 7, 512, 1, false>;
 
 template <class C>
 int launch4(const unsigned char *x, unsigned char *y, const unsigned char *w, int n, int *status, long long *dbg,
-            cudaStream_t st) {
+            cudaStream_t st, const unsigned char *pw = nullptr) {
     static const int key = ssb_new_key();
     if (ssb_first_on_device(key))
         SSB_CHECK_CUDA(cudaFuncSetAttribute(osblock4_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_B));
@@ -790,7 +883,7 @@ int launch4(const unsigned char *x, unsigned char *y, const unsigned char *w, in
     at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
     cfg.numAttrs = ssb_pdl_enabled() ? 2 : 1;
-    SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock4_kernel<C>, x, y, w, n, status, dbg));
+    SSB_CHECK_CUDA(cudaLaunchKernelEx(&cfg, osblock4_kernel<C>, x, y, w, n, status, dbg, pw));
     g_ssb_launches++;
     return 0;
 }
@@ -861,6 +954,19 @@ int ssb_reid_tc4_block(int b, const void *x, void *y, const unsigned char *w, in
         case 5: return launch4<K5>(xi, yo, w, n, status, dbg, st);
     }
     ssb_set_error("bad OSBlock index %d", b);
+    return -1;
+}
+
+// block b (1 or 3) + the transition layer behind it in one launch: y = the POOLED map's operand planes;
+// pw = the transition's weight section (reid_tc.cu PwCfg blob: hi | lo weights, then the bias)
+int ssb_reid_tc4_block_pw(int b, const void *x, void *y, const unsigned char *w, const unsigned char *pw, int n, int *status,
+                          cudaStream_t st) {
+    long long *dbg = g_ssb_tc_dbg;
+    const unsigned char *xi = (const unsigned char *)x;
+    unsigned char *yo = (unsigned char *)y;
+    if (b == 1) return launch4<K1F>(xi, yo, w, n, status, dbg, st, pw);
+    if (b == 3) return launch4<K3F>(xi, yo, w, n, status, dbg, st, pw);
+    ssb_set_error("only OSBlocks 1 and 3 are followed by a transition layer (got %d)", b);
     return -1;
 }
 

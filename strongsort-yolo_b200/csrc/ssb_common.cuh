@@ -185,5 +185,8 @@ int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *box
                      float *out, int n, int *status, cudaStream_t st, int planes = 0);
 int64_t ssb_reid_tc4_block_bytes(int b);
 int ssb_reid_tc4_block(int b, const void *x, void *y, const unsigned char *w, int n, int *status, cudaStream_t st);
+int ssb_reid_tc4_block_pw(int b, const void *x, void *y, const unsigned char *w, const unsigned char *pw, int n, int *status,
+                          cudaStream_t st);
+bool ssb_pw_fused();    // transitions fused behind OSBlocks 1 and 3 (SSB_PW_FUSED=0: separate pw_tc launches, A/B)
 int ssb_reid_nhwc_to_planes(const float *x, void *y, int n, int hw, int c, cudaStream_t st);
 int ssb_reid_planes_to_nhwc(const void *x, float *y, int n, int hw, int c, cudaStream_t st);

@@ -464,6 +464,7 @@ __global__ void iou_cost_arrays_kernel(const double *tlwh, int n_tracks, const f
 // ---------------------------------------------------------------------------
 struct LsapSmem {
     long long lsap_t_stage, lsap_t_solve;   // clock64 deltas of the last lsap_block (thread 0; debug builds read them)
+    long long stats[3];                     // register solver: search steps, cycles in the searches, cycles elsewhere
     double *u, *v, *spc, *cost;   // cost == nullptr -> read global
     int *path, *row4col, *col4row, *remaining;
     unsigned char *SR, *SC;
@@ -514,7 +515,8 @@ struct LsapSparse {
 template <int CPL, bool SPARSE>
 __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr, int nc0, int nr,
                               int nc, double *u, int *col4row, int *row4col_out, int lane,
-                              LsapSparse sp = LsapSparse()) {
+                              LsapSparse sp = LsapSparse(), long long *stats = nullptr) {
+    long long st_steps = 0, st_search = 0, st_rest = 0, st_t = stats ? clock64() : 0;
     double v[CPL], spc[CPL];
     int pos[CPL], r4c[CPL], path[CPL];
     unsigned sc = 0;
@@ -530,7 +532,9 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
         }
         double minVal = 0.0;
         int i = curRow, num_remaining = nc, sink = -1;
+        if (stats) { const long long t = clock64(); st_rest += t - st_t; st_t = t; }
         while (sink == -1) {
+            st_steps++;
             const double ui = u[i];
             double bv = INFINITY;
             unsigned bkey = 0;
@@ -592,6 +596,7 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
             num_remaining--;
             if (rj == -1) sink = jwin; else i = rj;
         }
+        if (stats) { const long long t = clock64(); st_search += t - st_t; st_t = t; }
         // dual updates (column-wise: visited column j with row r = row4col[j] gives u[r])
         if (lane == 0) u[curRow] += minVal;
 #pragma unroll
@@ -631,6 +636,7 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
         if (j < nc) row4col_out[j] = r4c[k];
     }
     __syncwarp();
+    if (stats && lane == 0) { stats[0] = st_steps; stats[1] = st_search; stats[2] = st_rest + (clock64() - st_t); }
     return true;
 }
 
@@ -731,8 +737,13 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
             else if (nc <= 256) okr = lsap_warp_reg<8, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
             else if (nc <= 512) okr = lsap_warp_reg<16, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
             else okr = lsap_warp_reg<32, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-        } else if (nc <= 128) okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else if (nc <= 256) okr = lsap_warp_reg<8, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+        } else if (nc <= 128) {
+#ifdef SSB_BASELINES
+            okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, LsapSparse(), m.stats);
+#else
+            okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+#endif
+        } else if (nc <= 256) okr = lsap_warp_reg<8, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         else if (nc <= 512) okr = lsap_warp_reg<16, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         else okr = lsap_warp_reg<32, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
         if (!okr) {
@@ -935,6 +946,7 @@ __global__ void assign_stage_a_kernel(TrackTable tt, FrameScratch fs, SsbDims d,
         fs.cnt[21] = (int)(clock64() - t_a1);
         fs.cnt[22] = (int)m.lsap_t_stage;
         fs.cnt[23] = (int)m.lsap_t_solve;
+        fs.cnt[24] = (int)m.stats[0]; fs.cnt[25] = (int)m.stats[1]; fs.cnt[26] = (int)m.stats[2];
 #endif
     }
 }

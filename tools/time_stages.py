@@ -85,9 +85,10 @@ def main():
     pa, pb, pd = C.c_void_p(), C.c_void_p(), C.c_void_p()
     _lib.check(lib.ssb_debug_cost_ptrs(trk._h, C.byref(pa), C.byref(pb), C.byref(pd)))
     from strongsort_yolo_b200.strong_sort import _wrap_device
-    cnt = _wrap_device(torch, pd.value, (16,), "<i4", trk.device).cpu().numpy()     # cnt[FC_ROWS_A ...]
+    cnt = _wrap_device(torch, pd.value, (20,), "<i4", trk.device).cpu().numpy()     # cnt[FC_ROWS_A ...]
     out["assign_stage_a_cycles"] = {"lsap_block": int(cnt[10]), "lists": int(cnt[11]), "staged_at": int(cnt[12]),
-                                    "solved_at": int(cnt[13])}
+                                    "solved_at": int(cnt[13]), "search_steps": int(cnt[14]),
+                                    "search_cycles": int(cnt[15]), "other_cycles": int(cnt[16])}
     for name, m in (("lsap_stageA", a), ("lsap_stageB", b)):
         if m.size:
             md = torch.as_tensor(m).cuda()
