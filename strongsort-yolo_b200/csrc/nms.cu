@@ -128,9 +128,11 @@ __global__ void nms_rank_kernel(const float *__restrict__ pred, int A, int agnos
 __global__ void nms_mask_kernel(float iou_thres, NmsScratch s) {
     const int M = min(s.count[0], NMS_MAX_CAND);
     const int words = (M + 63) / 64;
-    const int i = blockIdx.y * blockDim.y + threadIdx.y;
     const int wj = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M || wj >= words) return;
+    if (wj >= words) return;
+    // the candidate count lives on the device: a bounded grid strides over the rows (the worst-case grid of
+    // A / 8 row blocks cost 22 us of empty CTAs per frame)
+    for (int i = blockIdx.y * blockDim.y + threadIdx.y; i < M; i += gridDim.y * blockDim.y) {
     const float ix1 = s.sbox[i * 4], iy1 = s.sbox[i * 4 + 1];
     const float ix2 = s.sbox[i * 4 + 2], iy2 = s.sbox[i * 4 + 3];
     const float iarea = s.sarea[i];
@@ -148,6 +150,7 @@ __global__ void nms_mask_kernel(float iou_thres, NmsScratch s) {
         if (ovr > iou_thres) bits |= 1ull << b;
     }
     s.mask[(size_t)i * words + wj] = bits;
+    }
 }
 
 // greedy scan + gather (single CTA).  The suppression matrix of the M candidates is first copied into shared
@@ -230,7 +233,7 @@ static int nms_after_scores(const float *pred_dev, int num_classes, int num_extr
     SSB_CHECK_LAUNCH();
     const int Mc = A < NMS_MAX_CAND ? A : NMS_MAX_CAND;
     const int words = (Mc + 63) / 64;
-    dim3 mb(32, 8), mg((words + 31) / 32, (Mc + 7) / 8);
+    dim3 mb(32, 8), mg((words + 31) / 32, ((Mc + 7) / 8) < 64 ? ((Mc + 7) / 8) : 64);
     nms_mask_kernel<<<mg, mb, 0, st>>>(iou_thres, s);
     SSB_CHECK_LAUNCH();
     static const int key = ssb_new_key();

@@ -640,6 +640,159 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
     return true;
 }
 
+// The same solver spread over NW warps for wide problems (config C4 once more than 512 tracks are alive): 4 columns
+// per lane, 128 per warp, up to 8 warps = 1024 columns.  A search step is the single-warp step on each warp's own
+// 128 columns, one shared-memory exchange of the NW warp winners (double-buffered, one named barrier of the NW
+// warps) and the same "lowest value, then largest tie key" rule applied to them -- the key is a function of the
+// column's global position in scipy's remaining[], so the combined choice is the serial algorithm's choice.
+// Control flow is replicated in every warp (they all see the same winner); u[] and col4row[] live in shared memory.
+struct LsapXch {                 // one warp's winner of a search step
+    double bv;
+    unsigned bkey;
+    int j, pos, r4c;
+};
+__device__ __forceinline__ void lsap_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
+template <int NW, bool SPARSE>
+__device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, int nr, int nc, double *u, int *col4row,
+                               int *row4col_out, LsapXch *xch /* [2][NW] shared */, int *s_aug /* [2] shared */,
+                               LsapSparse sp = LsapSparse()) {
+    constexpr int CPL = 4;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, base = wid * 128;
+    double v[CPL], spc[CPL];
+    int pos[CPL], r4c[CPL], path[CPL];
+    unsigned sc = 0;
+    int xb = 0;                                   // exchange buffer parity
+#pragma unroll
+    for (int k = 0; k < CPL; k++) { v[k] = 0.0; r4c[k] = -1; path[k] = -1; }
+    for (int curRow = 0; curRow < nr; curRow++) {
+        sc = 0;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            const int j = base + lane + 32 * k;
+            spc[k] = INFINITY;
+            pos[k] = j < nc ? nc - 1 - j : -1;
+        }
+        double minVal = 0.0;
+        int i = curRow, num_remaining = nc, sink = -1;
+        while (sink == -1) {
+            const double ui = u[i];
+            double bv = INFINITY;
+            unsigned bkey = 0;
+            int bk = -1;
+            double cs[SPARSE ? CPL : 1];
+            if (SPARSE) {
+#pragma unroll
+                for (int k = 0; k < CPL; k++) cs[k] = sp.bg;
+                const int e0 = sp.rowptr[i], e1 = e0 + sp.rowlen[i];
+                for (int e = e0; e < e1; e++) {                  // block-uniform trip count
+                    const int cj = sp.ecol[e] - base;
+                    const double cv = sp.eval[e];
+#pragma unroll
+                    for (int k = 0; k < CPL; k++)
+                        if (cj >= 0 && k == (cj >> 5) && lane == (cj & 31) && cj < 128) cs[k] = cv;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < CPL; k++) {
+                const int j = base + lane + 32 * k;
+                if (j < nc && !((sc >> k) & 1u)) {
+                    const double cij = SPARSE ? cs[SPARSE ? k : 0]
+                                              : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]);
+                    const double r = minVal + cij - ui - v[k];
+                    if (r < spc[k]) { path[k] = i; spc[k] = r; }
+                    const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k])
+                                                      : (unsigned)(nc - pos[k]);
+                    if (spc[k] < bv || (spc[k] == bv && key > bkey)) { bv = spc[k]; bkey = key; bk = k; }
+                }
+            }
+            // this warp's winner (value, then tie key), as in lsap_warp_reg
+            const unsigned long long ok = f64_order_key(bv);
+            const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
+            const unsigned hmin = __reduce_min_sync(0xffffffffu, bk >= 0 ? hi : 0xffffffffu);
+            const unsigned lmin = __reduce_min_sync(0xffffffffu, (bk >= 0 && hi == hmin) ? lo : 0xffffffffu);
+            const bool vwin = bk >= 0 && hi == hmin && lo == lmin;
+            unsigned wmask = __ballot_sync(0xffffffffu, vwin);
+            if (wmask & (wmask - 1)) {
+                const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
+                wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            }
+            const int wl = wmask ? __ffs(wmask) - 1 : -1;
+            int my_pos = -1, my_r = -1;
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (k == bk) { my_pos = pos[k]; my_r = r4c[k]; }
+            if (lane == (wl >= 0 ? wl : 0)) {
+                LsapXch x;
+                x.bv = wl >= 0 ? bv : INFINITY;
+                x.bkey = wl >= 0 ? bkey : 0u;
+                x.j = wl >= 0 ? base + lane + 32 * bk : -1;
+                x.pos = my_pos; x.r4c = my_r;
+                xch[xb * NW + wid] = x;
+            }
+            lsap_bar(32 * NW);
+            // every warp combines the NW winners identically
+            LsapXch g = xch[xb * NW];
+#pragma unroll
+            for (int w = 1; w < NW; w++) {
+                const LsapXch o = xch[xb * NW + w];
+                const bool take = o.j >= 0 && (g.j < 0 || o.bv < g.bv || (o.bv == g.bv && o.bkey > g.bkey));
+                if (take) g = o;
+            }
+            xb ^= 1;
+            if (g.j < 0) return false;
+            minVal = g.bv;
+            if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible
+            const int jwin = g.j, index = g.pos, rj = g.r4c;
+            if (jwin - base == lane + 32 * ((jwin - base) >> 5) && jwin >= base && jwin < base + 128)
+                sc |= 1u << ((jwin - base) >> 5);
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (!((sc >> k) & 1u) && pos[k] == num_remaining - 1) pos[k] = index;
+            num_remaining--;
+            if (rj == -1) sink = jwin; else i = rj;
+        }
+        // dual updates: every lane for its own visited columns (distinct rows of u)
+        if (threadIdx.x == 0) u[curRow] += minVal;
+#pragma unroll
+        for (int k = 0; k < CPL; k++) {
+            if ((sc >> k) & 1u) {
+                const double dlt = minVal - spc[k];
+                if (r4c[k] >= 0) u[r4c[k]] += dlt;
+                v[k] -= dlt;
+            }
+        }
+        lsap_bar(32 * NW);
+        // augment along the path: the owner of column j publishes path[j]; col4row is read by all, then written by one
+        int j = sink;
+        while (true) {
+            const int lj = j - base;
+            const bool mine = lj >= 0 && lj < 128 && (lj & 31) == lane;
+            if (mine) {
+                int r = -1;
+#pragma unroll
+                for (int k = 0; k < CPL; k++)
+                    if (k == (lj >> 5)) { r = path[k]; r4c[k] = r; }
+                s_aug[0] = r;
+            }
+            lsap_bar(32 * NW);
+            const int r = s_aug[0];
+            const int t = col4row[r];
+            lsap_bar(32 * NW);
+            if (threadIdx.x == 0) col4row[r] = j;
+            j = t;
+            if (r == curRow) break;
+        }
+        lsap_bar(32 * NW);
+    }
+#pragma unroll
+    for (int k = 0; k < CPL; k++) {
+        const int j = base + lane + 32 * k;
+        if (j < nc) row4col_out[j] = r4c[k];
+    }
+    return true;
+}
+
 // Solve with the whole block staging, warp 0 iterating.  C is [nr0][nc0]
 // row-major (ld = nc0).  Results in ORIGINAL orientation: col4row_out[nr0],
 // row4col_out[nc0] (-1 = unassigned).  Must be called by all threads.
@@ -727,28 +880,46 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
         __syncthreads();
     }
 
-    if (tid < 32 && nc <= 1024) {
-        // 513 .. 1024 working columns (C4 once more than 512 tracks are alive): 32 columns per lane; part of the
-        // per-column state then lives in (L1-resident) local memory, still far from the global-memory walk below
-        const double *Cw = staged ? m.cost : C;
-        bool okr;
-        if (sparse) {
-            if (nc <= 128) okr = lsap_warp_reg<4, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-            else if (nc <= 256) okr = lsap_warp_reg<8, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-            else if (nc <= 512) okr = lsap_warp_reg<16, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-            else okr = lsap_warp_reg<32, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
-        } else if (nc <= 128) {
+    __shared__ LsapXch s_xch[2 * 8];
+    __shared__ int s_aug[2];
+    if (nc <= 128) {
+        if (tid < 32) {                       // one warp, everything in registers (config C2)
+            const double *Cw = staged ? m.cost : C;
+            bool okr;
+            if (sparse) okr = lsap_warp_reg<4, true>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, sp);
+            else {
 #ifdef SSB_BASELINES
-            okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, LsapSparse(), m.stats);
+                okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane, LsapSparse(), m.stats);
 #else
-            okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
+                okr = lsap_warp_reg<4, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
 #endif
-        } else if (nc <= 256) okr = lsap_warp_reg<8, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else if (nc <= 512) okr = lsap_warp_reg<16, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        else okr = lsap_warp_reg<32, false>(Cw, staged, tr, nc0, nr, nc, m.u, m.col4row, m.row4col, lane);
-        if (!okr) {
-            for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
-            for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
+            }
+            if (!okr) {
+                for (int i = lane; i < nr; i += 32) m.col4row[i] = -1;
+                for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
+            }
+        }
+    } else if (nc <= 1024) {
+        // 129 .. 1024 working columns: 4 columns per lane on 2 / 4 / 8 warps (lsap_block_reg)
+        const int nwarp_s = nc <= 256 ? 2 : (nc <= 512 ? 4 : 8);
+        if (tid < 32 * nwarp_s) {
+            const double *Cw = staged ? m.cost : C;
+            const bool trw = staged ? false : tr;
+            const int ldw = staged ? nc : nc0;
+            bool okr;
+            if (nwarp_s == 2)
+                okr = sparse ? lsap_block_reg<2, true>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
+                             : lsap_block_reg<2, false>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
+            else if (nwarp_s == 4)
+                okr = sparse ? lsap_block_reg<4, true>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
+                             : lsap_block_reg<4, false>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
+            else
+                okr = sparse ? lsap_block_reg<8, true>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
+                             : lsap_block_reg<8, false>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
+            if (!okr) {
+                for (int i = tid; i < nr; i += 32 * nwarp_s) m.col4row[i] = -1;
+                for (int j = tid; j < nc; j += 32 * nwarp_s) m.row4col[j] = -1;
+            }
         }
     } else if (tid < 32) {
         bool failed = false;

@@ -36,6 +36,12 @@ def short(name):
     if m:
         a = [s.strip() for s in m.group(1).split(",")]
         return "osblock_tc<cin %s, mid %s, cout %s, %sx%s>" % (a[0], a[1], a[3], a[4], a[5])
+    m = re.match(r"osblock4_kernel<B4<([^>]*)>", name)
+    if m:
+        a = [s.strip() for s in m.group(1).split(",")]
+        pw = len(a) > 13 and a[13] in ("1", "true", "(bool)1")
+        return "osblock4<cin %s, mid %s, cout %s, %sx%s, R %s x %s bands, %s thr%s>" % (
+            a[0], a[1], a[3], a[4], a[5], a[6], a[7], a[10], ", +transition" if pw else "")
     m = re.match(r"pw_tc_kernel<PwCfg<([^>]*)>", name)
     if m:
         a = [s.strip() for s in m.group(1).split(",")]
