@@ -660,13 +660,15 @@ def main():
     achieved_tf = reid_flops / (r["reid_ms"] * 1e-3) / 1e12
     peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops")))
     hbm = float(peaks.get("hbm_gbs", 6570.6))
-    traffic = None
+    traffic = traffic_warm = None
     tpath = os.path.join(ROOT, "profiles", "reid_traffic_bytes.json")
     if os.path.exists(tpath):
         try:
-            traffic = json.load(open(tpath)).get("dram_bytes_per_reid_forward")
+            tj = json.load(open(tpath))
+            traffic = tj.get("dram_bytes_per_reid_forward")             # ncu --set full: caches flushed before every pass
+            traffic_warm = tj.get("dram_bytes_per_reid_forward_warm")   # ncu application replay, caches left alone
         except Exception:
-            traffic = None
+            traffic = traffic_warm = None
     n_conf = 256 if CFG == "C4" else 100
     app_bytes = (n_conf * 128 + 128 * ((r["reid_n"] + 127) // 128)) * 512 * 4      # operand planes the kernel streams
     app_gbs = app_bytes / max(r["stages_us"]["appearance"], 1e-3) / 1e3
@@ -718,7 +720,8 @@ def main():
                        "reid_forward": 1000.0 * r["reid_ms"], **r["stages_us"], "association_total": r["assoc_us"]},
             "roofline": {"bound": "tensor", "kernel": "OSNet ReID forward (all kernels of ssb_reid)",
                          "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved_tf / peak_tf, "traffic": traffic, "traffic_not_flushed": traffic_warm,
+                         "peak_source": peak_src,
                          "reid_ms": r["reid_ms"], "flops_per_launch": reid_flops},
             "roofline_cost": {"bound": "hbm", "kernel": "appearance_tc_kernel (cosine-NN cost over the gallery)",
                               "achieved": app_gbs, "peak": hbm, "unit": "GB/s", "frac": app_gbs / hbm,

@@ -160,6 +160,10 @@ __device__ __forceinline__ void tmem_wait_ld() {
 // hardware cluster barrier, split phase (release / acquire at cluster scope)
 __device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
 __device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+// phase "A" of the ring protocol publishes nothing (it only says "I have finished READING my ring", and those loads
+// have been consumed by the arithmetic before it): no release fence -- the MEMBAR / ERRBAR pair behind a releasing
+// arrive was ~14 % of the kernel's stall samples
+__device__ __forceinline__ void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
 __device__ __forceinline__ void st_cluster_f4(uint32_t cluster_addr, float a, float b, float c, float d) {
     asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d)
                  : "memory");
@@ -231,8 +235,6 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
         tc::mbar_init(bar_c3, 1);
         tc::fence_mbar_init();
     }
-    for (int i = tid; i < C::NPAR; i += C::THREADS)
-        sPar[i] = reinterpret_cast<const float *>(wblob + C::G_PAR)[i];
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
@@ -264,11 +266,15 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
     // run while the previous kernel of the stream is still draining; its output is only touched after the wait
     tc::pdl_launch_dependents();
     if (tid == 0) {
-        tc::mbar_arrive_expect_tx(bar_w, C::WALL_B + C::XS_B);
+        // the fp32 parameters (biases, depthwise taps, gate MLP) ride the same mbarrier: a per-thread ld.global ->
+        // st.shared copy of these 7-14 KB was 4.5 % of the kernel's stall samples (ncu source page, round 2)
+        constexpr int PAR_B = (C::NPAR * 4 + 15) / 16 * 16;
+        tc::mbar_arrive_expect_tx(bar_w, C::WALL_B + C::XS_B + PAR_B);
         for (int o = 0; o < C::WALL_B; o += 32768) {
             const int nb = C::WALL_B - o < 32768 ? C::WALL_B - o : 32768;
             tc::bulk_g2s(sW + o, wblob + o, nb, bar_w);
         }
+        tc::bulk_g2s(sPar, wblob + C::G_PAR, PAR_B, bar_w);
         tc::pdl_wait();
         for (int hl = 0; hl < 2; hl++)
             for (int ch = 0; ch < C::XCH; ch++)
@@ -573,13 +579,13 @@ osblock4_kernel(const unsigned char *__restrict__ x, unsigned char *__restrict__
                     publish();
                     if (issuer) issue_pw(sP, lc + 1, 0, TH_);
                     dw_rows(HR, C::R);
-                    if (C::EXCH) { cluster_arrive(); a_pending = true; }    // [arrive A] done reading my ring
+                    if (C::EXCH) { cluster_arrive_relaxed(); a_pending = true; }    // [arrive A] done reading my ring
                     publish();
                     if (issuer) issue_pw(sP, lc + 1, TH_, C::NT);
                 } else {
                     dw_rows(0, C::R);
                     fstamp(lc);                // f5: depthwise rows done (this warp)
-                    if (C::EXCH) { cluster_arrive(); a_pending = true; }    // [arrive A]
+                    if (C::EXCH) { cluster_arrive_relaxed(); a_pending = true; }    // [arrive A]
                     publish();
                     fstamp(lc);                // f6: published
                     if (issuer) issue_pw(sP, lc + 1, 0, C::NT);
