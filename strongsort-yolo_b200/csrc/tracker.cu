@@ -1476,7 +1476,11 @@ __global__ void export_tracks_kernel(TrackTable tt, SsbDims d, int *ids, int *st
 // ---------------------------------------------------------------------------
 static int g_lsap_smem_limit_dev[64];   // bytes of dynamic smem opted in, per device
 
-static int lsap_prepare(int L, size_t *dyn_bytes, size_t *cost_bytes) {
+// L: upper bound of max(rows, cols) of the problem(s) the launch will solve; want_cost_bytes: bytes of the largest
+// dense cost matrix it may have to stage.  The launch asks for what THIS frame needs, not for the whole SM: a
+// 225 KB request (round 1) can only be placed on an EMPTY SM, so in the two-stage pipeline every assignment kernel
+// waited for a gap between the ReID kernels of the next frame; ~90 KB at C2 co-resides with a ReID CTA.
+static int lsap_prepare(int L, size_t want_cost_bytes, size_t *dyn_bytes, size_t *cost_bytes) {
     int dev = 0;
     SSB_CHECK_CUDA(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64) { ssb_set_error("device index %d out of range", dev); return -3; }
@@ -1496,8 +1500,12 @@ static int lsap_prepare(int L, size_t *dyn_bytes, size_t *cost_bytes) {
         ssb_set_error("LSAP dimension %d exceeds shared memory", L);
         return -3;
     }
-    *dyn_bytes = g_lsap_smem_limit;
-    *cost_bytes = (size_t)g_lsap_smem_limit - fixed - 16;
+    const size_t avail = (size_t)g_lsap_smem_limit - fixed - 16;
+    size_t cost = want_cost_bytes < avail ? want_cost_bytes : avail;       // too big to stage: the rest is the sparse store
+    if (cost < 16384) cost = 16384 < avail ? 16384 : avail;
+    *cost_bytes = cost;
+    *dyn_bytes = (fixed + cost + 16 + 1023) & ~(size_t)1023;
+    if (*dyn_bytes > (size_t)g_lsap_smem_limit) *dyn_bytes = g_lsap_smem_limit;
     return 0;
 }
 
@@ -1517,9 +1525,10 @@ int ssb_launch_track_frame(ssb_tracker *t, int slot, int n, int h, int w, const 
     FrameScratch fs = ssb_slot_view(t, slot);
     if (feats) fs.feats = const_cast<float *>(feats);
     const int Tmax = (track_hint >= 0 && track_hint <= d.S) ? track_hint : d.S;
-    const int L = d.S > d.N ? d.S : d.N;
+    // rows <= live tracks entering the frame (Tmax), columns <= n, for both assignment stages
+    const int L = (Tmax > n ? Tmax : n) > 1 ? (Tmax > n ? Tmax : n) : 1;
     size_t dyn = 0, cost_b = 0;
-    int rc = lsap_prepare(L, &dyn, &cost_b);
+    int rc = lsap_prepare(L, (size_t)Tmax * (size_t)n * 8, &dyn, &cost_b);
     if (rc) return rc;
 #define SSB_PROF(i) do { if (t->prof_on) SSB_CHECK_CUDA(cudaEventRecord(t->prof_ev[i], st)); } while (0)
     SSB_PROF(0);
@@ -1655,7 +1664,7 @@ extern "C" int ssb_lsap(const double *cost_dev, int nr, int nc, int32_t *col4row
     if (nr < 0 || nc < 0) { ssb_set_error("negative LSAP dims"); return -1; }
     const int L = (nr > nc ? nr : nc) > 1 ? (nr > nc ? nr : nc) : 1;
     size_t dyn = 0, cost_b = 0;
-    int rc = lsap_prepare(L, &dyn, &cost_b);
+    int rc = lsap_prepare(L, (size_t)nr * (size_t)nc * 8, &dyn, &cost_b);
     if (rc) return rc;
     lsap_kernel<<<1, 256, dyn, (cudaStream_t)stream>>>(cost_dev, nr, nc, L, cost_b, col4row_out_dev, row4col_out_dev);
     SSB_CHECK_LAUNCH();
