@@ -390,16 +390,22 @@ class StrongSORT:
                                            _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
                                            C.c_void_p(pst.cuda_stream)), "ssb_embed")
             self._p_embed_done[slot].record(pst)
-        # the previous frame finishes while this frame's embeddings are computed
-        prev = self._pipe_collect(slot ^ 1) if k > 0 else None
+        # The association of THIS frame is enqueued before the previous frame's result is read back: the host never
+        # holds the next ReID launch hostage to a device->host round trip.  track_hint only sizes grids and shared
+        # memory, so a bound suffices: the live tracks last read back + the detections of the frames read back since
+        # (every detection can start at most one track).
+        hint = min(self.cfg.max_tracks, self._track_hint + (self._p_n_prev if k > 0 else 0))
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.stream.wait_event(self._p_embed_done[slot])
             _lib.check(self._lib.ssb_associate(
                 self._h, slot, n, H, W, None, C.c_void_p(self._p_out[slot].data_ptr() + _HDR_BYTES),
-                _lib.ptr(self._p_out[slot]), self._track_hint, C.c_void_p(self.stream.cuda_stream)),
+                _lib.ptr(self._p_out[slot]), hint, C.c_void_p(self.stream.cuda_stream)),
                 "ssb_associate")
             self._p_pin[slot].copy_(self._p_out[slot], non_blocking=True)
             self._p_assoc_done[slot].record(self.stream)
+        # the previous frame finishes while this frame's embeddings are computed
+        prev = self._pipe_collect(slot ^ 1) if k > 0 else None
+        self._p_n_prev = n
         self._p_k = k + 1
         return prev
 
