@@ -11,6 +11,7 @@ timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -12 gpurun_out/${tag}_pytest.log
 timeout 420 python tools/time_stages.py > gpurun_out/${tag}_stages.json 2> gpurun_out/${tag}_stages.err
+SSB_LSAP_DENSE_MAX=100000000 timeout 420 python tools/time_stages.py > gpurun_out/${tag}_stages_dense.json 2>> gpurun_out/${tag}_stages.err
 timeout 900 python tools/build_variants.py time > gpurun_out/${tag}_variants.json 2> gpurun_out/${tag}_variants.err
 cat gpurun_out/${tag}_variants.json
 python - <<PY
@@ -18,7 +19,9 @@ import json
 try:
     d = json.load(open("gpurun_out/${tag}_stages.json"))
     for k, v in d.items():
-        if isinstance(v, dict): print(k, round(v["median_us"], 1))
+        if isinstance(v, dict) and "median_us" in v: print(k, round(v["median_us"], 1))
+    dd = json.load(open("gpurun_out/${tag}_stages_dense.json"))
+    print("lsap dense-staged:", {k: round(v["median_us"], 1) for k, v in dd.items() if k.startswith("lsap")})
 except Exception as e:
     print("stages:", e)
 PY
