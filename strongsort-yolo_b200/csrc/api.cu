@@ -197,11 +197,12 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
 
 extern "C" int ssb_destroy(ssb_tracker *t) {
     if (!t) return 0;
-    if (t->side_stream) {
-        cudaStreamDestroy(t->side_stream);
-        cudaEventDestroy(t->ev_fork);
-        cudaEventDestroy(t->ev_join);
-    }
+    for (int i = 0; i < 2; i++)
+        if (t->side_stream[i]) {
+            cudaStreamDestroy(t->side_stream[i]);
+            cudaEventDestroy(t->ev_fork[i]);
+            cudaEventDestroy(t->ev_join[i]);
+        }
     if (t->prof_ev[0])
         for (int i = 0; i < 12; i++) cudaEventDestroy(t->prof_ev[i]);
     free(t->w_off);
@@ -220,6 +221,9 @@ extern "C" int ssb_reset(ssb_tracker *t, ssb_stream_t stream) {
     return ssb_launch_reset(t, (cudaStream_t)stream);
 }
 
+static int reid_forward_split(ssb_tracker *t, int slot, const uint8_t *img_dev, int h, int w, int pitch, const int *boxes,
+                              int n, float *feats, cudaStream_t st);
+
 // stage 1 of a frame: detection prep + OSNet embeddings into slot (0/1).  Independent of
 // the track table, so frame t+1 may be embedded while frame t is still being associated.
 extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n, const uint8_t *img_dev,
@@ -234,6 +238,8 @@ extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n,
     if (rc || n == 0) return rc;
     if (!img_dev) return 0;                         // caller supplies embeddings to ssb_associate
     if (pitch < 3 * w) { ssb_set_error("bad pitch"); return -1; }
+    if (n >= 48 && ssb_split_enabled())
+        return reid_forward_split(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
     return ssb_reid_forward(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
 }
 
@@ -246,31 +252,38 @@ extern "C" int ssb_associate(ssb_tracker *t, int slot, int n, int h, int w, cons
                                   (cudaStream_t)stream);
 }
 
-// Synchronous single-frame embedding (ssb_update, ssb_reid): nothing else uses the second embedding
-// workspace, so the crops are embedded as two halves on two streams (fork / join by events, still
-// graph-capturable).  Every ReID kernel is 1 CTA per SM and most grids end in a partial wave (404 CTAs =
-// 2.73 waves of 148); with two independent halves in flight the block scheduler fills one half's tail with
-// the other half's CTAs (measured: serial frame 1.078 -> 1.012 ms, e2e 810 -> 851 frames/s).
-static int reid_forward_split(ssb_tracker *t, const uint8_t *img_dev, int h, int w, int pitch, const int *boxes,
+// Embedding of a frame's crops as two halves on two streams (fork / join by events, still graph-capturable), inside
+// ONE detection slot's workspace, so it serves the synchronous calls (ssb_update, ssb_reid) and the two-stage pipeline
+// (ssb_embed of frame k+1 while frame k is associated) alike.  Every ReID kernel ends in a partial wave; with two
+// independent halves in flight the block scheduler fills one half's tail with the other half's CTAs.
+static int reid_forward_split(ssb_tracker *t, int slot, const uint8_t *img_dev, int h, int w, int pitch, const int *boxes,
                               int n, float *feats, cudaStream_t st) {
-    if (!t->side_stream) {
-        // same priority as the caller's stream: the two halves must interleave CTA by CTA (a high-priority half simply
-        // runs first and the tail-filling effect is gone: 638 instead of 515 us per 99 crops, measured)
-        int prio = 0;
-        SSB_CHECK_CUDA(cudaStreamGetPriority(st, &prio));
-        SSB_CHECK_CUDA(cudaStreamCreateWithPriority(&t->side_stream, cudaStreamNonBlocking, prio));
-        SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_fork, cudaEventDisableTiming));
-        SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_join, cudaEventDisableTiming));
+    slot &= 1;
+    // same priority as the caller's stream: the two halves must interleave CTA by CTA (a high-priority half simply
+    // runs first and the tail-filling effect is gone: 591 instead of 468 us per 99 crops, measured) -- so the side
+    // stream is re-made when a caller arrives on a stream of another priority
+    int prio = 0;
+    SSB_CHECK_CUDA(cudaStreamGetPriority(st, &prio));
+    if (t->side_stream[slot] && t->side_prio[slot] != prio) {
+        SSB_CHECK_CUDA(cudaStreamSynchronize(t->side_stream[slot]));
+        SSB_CHECK_CUDA(cudaStreamDestroy(t->side_stream[slot]));
+        t->side_stream[slot] = nullptr;
     }
-    const int n0 = (n + 1) / 2, n1 = n - n0;
-    SSB_CHECK_CUDA(cudaEventRecord(t->ev_fork, st));
-    SSB_CHECK_CUDA(cudaStreamWaitEvent(t->side_stream, t->ev_fork, 0));
-    int rc = ssb_reid_forward(t, 0, img_dev, h, w, pitch, boxes, n0, feats, st);
+    if (!t->side_stream[slot]) {
+        SSB_CHECK_CUDA(cudaStreamCreateWithPriority(&t->side_stream[slot], cudaStreamNonBlocking, prio));
+        t->side_prio[slot] = prio;
+        if (!t->ev_fork[slot]) {
+            SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_fork[slot], cudaEventDisableTiming));
+            SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_join[slot], cudaEventDisableTiming));
+        }
+    }
+    SSB_CHECK_CUDA(cudaEventRecord(t->ev_fork[slot], st));
+    SSB_CHECK_CUDA(cudaStreamWaitEvent(t->side_stream[slot], t->ev_fork[slot], 0));
+    int rc = ssb_reid_forward_halves(t, slot, img_dev, h, w, pitch, boxes, n, feats, st, t->side_stream[slot]);
+    if (rc == 1) rc = ssb_reid_forward(t, slot, img_dev, h, w, pitch, boxes, n, feats, st);   // baseline modes: unsplit
     if (rc) return rc;
-    rc = ssb_reid_forward(t, 1, img_dev, h, w, pitch, boxes + 4 * n0, n1, feats + (size_t)n0 * t->dims.D, t->side_stream);
-    if (rc) return rc;
-    SSB_CHECK_CUDA(cudaEventRecord(t->ev_join, t->side_stream));
-    SSB_CHECK_CUDA(cudaStreamWaitEvent(st, t->ev_join, 0));
+    SSB_CHECK_CUDA(cudaEventRecord(t->ev_join[slot], t->side_stream[slot]));
+    SSB_CHECK_CUDA(cudaStreamWaitEvent(st, t->ev_join[slot], 0));
     return 0;
 }
 
@@ -279,13 +292,6 @@ extern "C" int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const ui
                           int32_t *counts_dev, int track_hint, ssb_stream_t stream) {
     if (!t || !out_dev || !counts_dev) { ssb_set_error("null argument"); return -1; }
     if (!feats_dev && n > 0 && !img_dev) { ssb_set_error("null image"); return -1; }
-    if (!feats_dev && img_dev && n >= 48 && t->use_tc && t->w_tc && pitch >= 3 * w && ssb_split_enabled()) {
-        int rc = ssb_embed(t, 0, dets_dev, n, nullptr, h, w, pitch, stream);          // detection prep only
-        if (rc) return rc;
-        rc = reid_forward_split(t, img_dev, h, w, pitch, t->fs.det_box, n, t->fs.feats, (cudaStream_t)stream);
-        if (rc) return rc;
-        return ssb_associate(t, 0, n, h, w, nullptr, out_dev, counts_dev, track_hint, stream);
-    }
     int rc = ssb_embed(t, 0, dets_dev, n, feats_dev ? nullptr : img_dev, h, w, pitch, stream);
     if (rc) return rc;
     return ssb_associate(t, 0, n, h, w, feats_dev, out_dev, counts_dev, track_hint, stream);
@@ -296,8 +302,8 @@ extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, in
     if (!t || !img_dev || !feats_out_dev) { ssb_set_error("null argument"); return -1; }
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
     if (n == 0) return 0;
-    if (n >= 48 && t->use_tc && pitch >= 3 * w && ssb_split_enabled())
-        return reid_forward_split(t, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
+    if (n >= 48 && pitch >= 3 * w && ssb_split_enabled())
+        return reid_forward_split(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
     return ssb_reid_forward(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
 }
 

@@ -115,8 +115,9 @@ struct ssb_tracker {
     DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
     // ssb_update embeds the two halves of a frame's crops on two streams (fork / join by events):
     // the partial last waves of one half's kernels are filled by the other half's
-    cudaStream_t side_stream;
-    cudaEvent_t ev_fork, ev_join;
+    cudaStream_t side_stream[2];      // per detection slot: two frames' embeddings may be in flight
+    cudaEvent_t ev_fork[2], ev_join[2];
+    int side_prio[2];
 };
 
 void ssb_set_error(const char *fmt, ...);
@@ -170,6 +171,8 @@ int ssb_launch_appearance_tc(const unsigned char *gal_planes, const int *gal_cou
 inline int ssb_det_npad(int n) { return n <= 128 ? 128 : (n <= 256 ? 256 : 512); }
 int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch,
                      const int *boxes, int n, float *feats_out, cudaStream_t st);
+int ssb_reid_forward_halves(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+                            int n, float *feats_out, cudaStream_t st, cudaStream_t side);
 int64_t ssb_reid_ws_floats(int max_dets);
 int64_t ssb_reid_tc_block_bytes(int b);
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,

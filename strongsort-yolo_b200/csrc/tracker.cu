@@ -1502,13 +1502,14 @@ static int lsap_prepare(int L, size_t want_cost_bytes, size_t *dyn_bytes, size_t
         return -3;
     }
     const size_t avail = (size_t)g_lsap_smem_limit - fixed - 16;
-    // a matrix too big to stage is kept as its non-background entries (12 bytes each): 64 KB hold 5 461 of them --
-    // config C4 has ~2 500 -- and let the kernel share an SM with a ReID CTA; beyond that the dense global path runs
-    // ... and a matrix above SSB_LSAP_DENSE_MAX bytes (default 48 KB) is not staged densely either: the tracker's
-    // matrices are > 99 % background, their sparse form needs a few KB, and an assignment kernel that asks for
-    // <= ~90 KB is placed next to a running ReID CTA instead of waiting for an empty SM (two-stage pipeline)
-    static const size_t dense_max = [] { const char *v = getenv("SSB_LSAP_DENSE_MAX"); return v && *v ? (size_t)atoll(v) : (size_t)49152; }();
-    size_t cost = (want_cost_bytes <= avail && want_cost_bytes <= dense_max) ? want_cost_bytes : (avail < 65536 ? avail : 65536);
+    // The request is capped so that the kernel can sit next to a running ReID CTA (108 KB) in the two-stage pipeline
+    // instead of waiting for an empty SM: 96 KB of matrix (64 KB when the per-column state is large) hold config C2's
+    // dense 100 x 100 matrix (staging it densely is 18 % faster than its sparse form: 113 vs 134 us); a bigger matrix
+    // is kept as its non-background entries (12 bytes each; C4 has ~2 500) -- beyond that the dense global path runs.
+    static const size_t dense_max = [] { const char *v = getenv("SSB_LSAP_DENSE_MAX"); return v && *v ? (size_t)atoll(v) : (size_t)98304; }();
+    const size_t cap = fixed > 16384 ? 65536 : dense_max;
+    size_t cost = want_cost_bytes < cap ? want_cost_bytes : cap;
+    if (cost > avail) cost = avail;
     if (cost < 16384) cost = 16384 < avail ? 16384 : avail;
     *cost_bytes = cost;
     *dyn_bytes = (fixed + cost + 16 + 1023) & ~(size_t)1023;
