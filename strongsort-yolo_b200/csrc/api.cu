@@ -48,7 +48,10 @@ static int env_flag(const char *name, int dflt) {
 }
 bool ssb_pdl_enabled() { static const int on = env_flag("SSB_PDL", 1); return on != 0; }
 bool ssb_pw_fused() { static const int on = env_flag("SSB_PW_FUSED", 1); return on != 0; }
-bool ssb_split_enabled() { static const int on = env_flag("SSB_SPLIT", 1); return on != 0; }
+int ssb_split_parts() {        // SSB_SPLIT = parts a frame's crops are embedded in (0 / 1: unsplit), default 2
+    static const int p = [] { const char *v = getenv("SSB_SPLIT"); return v && *v ? atoi(v) : 2; }();
+    return p < 1 ? 1 : p > 4 ? 4 : p;
+}
 int ssb_num_sms() {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -197,12 +200,11 @@ extern "C" int ssb_create(const ssb_config *cfg, void *workspace_dev, int64_t wo
 
 extern "C" int ssb_destroy(ssb_tracker *t) {
     if (!t) return 0;
-    for (int i = 0; i < 2; i++)
-        if (t->side_stream[i]) {
-            cudaStreamDestroy(t->side_stream[i]);
-            cudaEventDestroy(t->ev_fork[i]);
-            cudaEventDestroy(t->ev_join[i]);
-        }
+    for (int i = 0; i < 2; i++) {
+        for (int p = 0; p < 3; p++)
+            if (t->side_stream[i][p]) { cudaStreamDestroy(t->side_stream[i][p]); cudaEventDestroy(t->ev_join[i][p]); }
+        if (t->ev_fork[i]) cudaEventDestroy(t->ev_fork[i]);
+    }
     if (t->prof_ev[0])
         for (int i = 0; i < 12; i++) cudaEventDestroy(t->prof_ev[i]);
     free(t->w_off);
@@ -238,7 +240,7 @@ extern "C" int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n,
     if (rc || n == 0) return rc;
     if (!img_dev) return 0;                         // caller supplies embeddings to ssb_associate
     if (pitch < 3 * w) { ssb_set_error("bad pitch"); return -1; }
-    if (n >= 48 && ssb_split_enabled())
+    if (n >= 48 && ssb_split_parts() > 1)
         return reid_forward_split(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
     return ssb_reid_forward(t, slot, img_dev, h, w, pitch, fs.det_box, n, fs.feats, st);
 }
@@ -252,38 +254,46 @@ extern "C" int ssb_associate(ssb_tracker *t, int slot, int n, int h, int w, cons
                                   (cudaStream_t)stream);
 }
 
-// Embedding of a frame's crops as two halves on two streams (fork / join by events, still graph-capturable), inside
-// ONE detection slot's workspace, so it serves the synchronous calls (ssb_update, ssb_reid) and the two-stage pipeline
-// (ssb_embed of frame k+1 while frame k is associated) alike.  Every ReID kernel ends in a partial wave; with two
-// independent halves in flight the block scheduler fills one half's tail with the other half's CTAs.
+// Embedding of a frame's crops in `parts` parts on as many streams (fork / join by events, still graph-capturable),
+// inside ONE detection slot's workspace, so it serves the synchronous calls (ssb_update, ssb_reid) and the two-stage
+// pipeline (ssb_embed of frame k+1 while frame k is associated) alike.  Every ReID kernel ends in a partial wave; with
+// independent parts in flight the block scheduler fills one part's tail with another part's CTAs.
 static int reid_forward_split(ssb_tracker *t, int slot, const uint8_t *img_dev, int h, int w, int pitch, const int *boxes,
                               int n, float *feats, cudaStream_t st) {
     slot &= 1;
-    // same priority as the caller's stream: the two halves must interleave CTA by CTA (a high-priority half simply
+    int parts = ssb_split_parts();
+    if (parts > n / 24) parts = n / 24;               // a part below ~24 crops no longer fills the GPU's tail, it is one
+    if (parts < 2) return ssb_reid_forward(t, slot, img_dev, h, w, pitch, boxes, n, feats, st);
+    // same priority as the caller's stream: the parts must interleave CTA by CTA (a high-priority part simply
     // runs first and the tail-filling effect is gone: 591 instead of 468 us per 99 crops, measured) -- so the side
-    // stream is re-made when a caller arrives on a stream of another priority
+    // streams are re-made when a caller arrives on a stream of another priority
     int prio = 0;
     SSB_CHECK_CUDA(cudaStreamGetPriority(st, &prio));
-    if (t->side_stream[slot] && t->side_prio[slot] != prio) {
-        SSB_CHECK_CUDA(cudaStreamSynchronize(t->side_stream[slot]));
-        SSB_CHECK_CUDA(cudaStreamDestroy(t->side_stream[slot]));
-        t->side_stream[slot] = nullptr;
-    }
-    if (!t->side_stream[slot]) {
-        SSB_CHECK_CUDA(cudaStreamCreateWithPriority(&t->side_stream[slot], cudaStreamNonBlocking, prio));
-        t->side_prio[slot] = prio;
-        if (!t->ev_fork[slot]) {
-            SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_fork[slot], cudaEventDisableTiming));
-            SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_join[slot], cudaEventDisableTiming));
+    if (!t->ev_fork[slot]) SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_fork[slot], cudaEventDisableTiming));
+    cudaStream_t streams[4] = {st, nullptr, nullptr, nullptr};
+    for (int p = 0; p < parts - 1; p++) {
+        cudaStream_t &ss = t->side_stream[slot][p];
+        if (ss && t->side_prio[slot] != prio) {
+            SSB_CHECK_CUDA(cudaStreamSynchronize(ss));
+            SSB_CHECK_CUDA(cudaStreamDestroy(ss));
+            ss = nullptr;
         }
+        if (!ss) {
+            SSB_CHECK_CUDA(cudaStreamCreateWithPriority(&ss, cudaStreamNonBlocking, prio));
+            if (!t->ev_join[slot][p]) SSB_CHECK_CUDA(cudaEventCreateWithFlags(&t->ev_join[slot][p], cudaEventDisableTiming));
+        }
+        streams[p + 1] = ss;
     }
+    t->side_prio[slot] = prio;
     SSB_CHECK_CUDA(cudaEventRecord(t->ev_fork[slot], st));
-    SSB_CHECK_CUDA(cudaStreamWaitEvent(t->side_stream[slot], t->ev_fork[slot], 0));
-    int rc = ssb_reid_forward_halves(t, slot, img_dev, h, w, pitch, boxes, n, feats, st, t->side_stream[slot]);
+    for (int p = 1; p < parts; p++) SSB_CHECK_CUDA(cudaStreamWaitEvent(streams[p], t->ev_fork[slot], 0));
+    int rc = ssb_reid_forward_parts(t, slot, img_dev, h, w, pitch, boxes, n, feats, parts, streams);
     if (rc == 1) rc = ssb_reid_forward(t, slot, img_dev, h, w, pitch, boxes, n, feats, st);   // baseline modes: unsplit
     if (rc) return rc;
-    SSB_CHECK_CUDA(cudaEventRecord(t->ev_join[slot], t->side_stream[slot]));
-    SSB_CHECK_CUDA(cudaStreamWaitEvent(st, t->ev_join[slot], 0));
+    for (int p = 1; p < parts; p++) {
+        SSB_CHECK_CUDA(cudaEventRecord(t->ev_join[slot][p - 1], streams[p]));
+        SSB_CHECK_CUDA(cudaStreamWaitEvent(st, t->ev_join[slot][p - 1], 0));
+    }
     return 0;
 }
 
@@ -302,7 +312,7 @@ extern "C" int ssb_reid(ssb_tracker *t, const uint8_t *img_dev, int h, int w, in
     if (!t || !img_dev || !feats_out_dev) { ssb_set_error("null argument"); return -1; }
     if (n < 0 || n > t->dims.N) { ssb_set_error("n=%d outside [0,%d]", n, t->dims.N); return -1; }
     if (n == 0) return 0;
-    if (n >= 48 && pitch >= 3 * w && ssb_split_enabled())
+    if (n >= 48 && pitch >= 3 * w && ssb_split_parts() > 1)
         return reid_forward_split(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
     return ssb_reid_forward(t, 0, img_dev, h, w, pitch, boxes_dev, n, feats_out_dev, (cudaStream_t)stream);
 }

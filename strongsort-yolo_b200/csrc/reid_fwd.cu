@@ -71,16 +71,19 @@ int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w,
 // forks / joins the streams).  Every ReID kernel ends in a partial wave; two independent half-frames in flight fill
 // each other's tails (measured: 489 vs 558 us per 100 crops).  Returns 1 when the split does not apply (baseline
 // modes of the debug library: the caller falls back to ssb_reid_forward).
-int ssb_reid_forward_halves(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
-                            int n, float *feats_out, cudaStream_t st, cudaStream_t side) {
+int ssb_reid_forward_parts(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+                           int n, float *feats_out, int parts, const cudaStream_t *streams) {
     if (!t->w_tc || !t->have_tc3) { ssb_set_error("ReID weights not set (ssb_reid_set_weights_tc)"); return -1; }
     if (t->use_tc != 3) return 1;
     float *ws = (slot & 1) ? t->reid_ws1 : t->reid_ws;
-    const int n0 = (n + 1) / 2, n1 = n - n0;
-    int rc = reid_forward_planes(t, ws, img, h, w, pitch, boxes, n0, feats_out, st);
-    if (rc) return rc;
-    return reid_forward_planes(t, ws + (size_t)2 * n0 * REID_BIG, img, h, w, pitch, boxes + 4 * n0, n1,
-                               feats_out + (size_t)n0 * t->dims.D, side);
+    for (int p = 0, off = 0; p < parts; p++) {
+        const int np = (n - off + (parts - p) - 1) / (parts - p);
+        int rc = reid_forward_planes(t, ws + (size_t)2 * off * REID_BIG, img, h, w, pitch, boxes + 4 * off, np,
+                                     feats_out + (size_t)off * t->dims.D, streams[p]);
+        if (rc) return rc;
+        off += np;
+    }
+    return 0;
 }
 
 // ---- tensor-core weights -----------------------------------------------------

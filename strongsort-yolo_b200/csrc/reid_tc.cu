@@ -1010,31 +1010,40 @@ tail_tc_kernel(const float *__restrict__ x, float *__restrict__ feats,
 // S is built once per band in the [chunk][pixel][8] operand layout, so the 16
 // taps are 16 shifted GEMMs (K = 16, N = 16) exactly like the 3x3 convs above.
 // ---------------------------------------------------------------------------
+#ifndef SSB_STEM_PR
+#define SSB_STEM_PR 4
+#endif
 struct StemCfg {
-    static constexpr int PR = 8;                    // pooled rows per CTA
+    static constexpr int PR = SSB_STEM_PR;          // pooled rows per CTA (4: two CTAs per SM, one builds its S map
+                                                    // while the other's MMAs run; 8: round-1 shape, one CTA per SM)
+    static constexpr int THREADS = PR >= 8 ? 512 : 256, MINB = PR >= 8 ? 1 : 2, GROUPS = THREADS / 128;
     static constexpr int NB = 64 / PR;              // bands per crop
-    static constexpr int CROWS = 2 * PR + 1;        // conv rows needed (17)
-    static constexpr int SROWS = CROWS + 3;         // space-to-depth rows (20)
+    static constexpr int CROWS = 2 * PR + 1;        // conv rows needed
+    static constexpr int SROWS = CROWS + 3;         // space-to-depth rows
     static constexpr int WPS = 67;                  // S row pitch (64 conv cols + 3)
     static constexpr int NPX = CROWS * WPS;         // output pixel index space
-    static constexpr int NT = (NPX + 127) / 128;    // 9 M tiles
-    static constexpr int MAP_PX = 1408;             // >= NT*128 + 3*WPS + 3
+    static constexpr int NT = (NPX + 127) / 128;    // M tiles (5 / 9)
+    static constexpr int MAP_PX = (NT * 128 + 3 * WPS + 3 + 7) / 8 * 8;
     static constexpr int PLANE_B = MAP_PX * 16;
     static constexpr int MAP_HALF_B = 2 * PLANE_B, MAP_B = 2 * MAP_HALF_B;
     static constexpr int W_HALF_B = 16 * 16 * 16 * 2, W_B = 2 * W_HALF_B;     // [tap][2][16][8]
     static constexpr int CP = 20;                   // floats per conv pixel in sConv (16 + 4 pad: the pooling stage's
                                                     // stride-2 column walk then touches distinct banks)
     static constexpr int CONV_B = CROWS * 64 * CP * 4;
-    static constexpr int OFF_MAP = 0, OFF_W = MAP_B, OFF_CONV = OFF_W + W_B;
-    static constexpr int OFF_BIAS = OFF_CONV + CONV_B, OFF_MISC = OFF_BIAS + 64;
+    // sConv (the drained conv rows) reuses the operand map: it is first written after the last MMA has read the map
+    static constexpr int OFF_MAP = 0, OFF_CONV = 0, OFF_W = MAP_B;
+    static constexpr int OFF_BIAS = OFF_W + W_B, OFF_MISC = OFF_BIAS + 64;
     static constexpr int SMEM_B = OFF_MISC + 64;
+    static constexpr int TM_COLS = NT * 32, TM_ALLOC = TM_COLS <= 256 ? 256 : 512;
     static constexpr int G_W = 0, G_BIAS = W_B, G_TOTAL = W_B + 128;
+    static_assert(64 % PR == 0, "bands");
     static_assert(NT * 128 + 3 * WPS + 3 <= MAP_PX, "map guard");
+    static_assert(CONV_B <= MAP_B, "sConv aliases the operand map");
     static_assert(SMEM_B <= 232448, "shared memory");
 };
 
 template <bool PLANES>
-__global__ void __launch_bounds__(OSB_THREADS, 1)
+__global__ void __launch_bounds__(StemCfg::THREADS, StemCfg::MINB)
 stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const int *__restrict__ boxes,
                const unsigned char *__restrict__ wblob, float *__restrict__ out, int *__restrict__ status,
                long long *__restrict__ dbg) {
@@ -1049,12 +1058,12 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     float *sBias = reinterpret_cast<float *>(smem + C::OFF_BIAS);
     uint64_t *bar = reinterpret_cast<uint64_t *>(smem + C::OFF_MISC);     // [0] mma, [1] weights
     uint32_t *s_tmem = reinterpret_cast<uint32_t *>(bar + 2);
-    if (warp == 0) tc::tmem_alloc(s_tmem, 512);
+    if (warp == 0) tc::tmem_alloc(s_tmem, C::TM_ALLOC);
     if (tid == 0) { tc::mbar_init(bar, 1); tc::mbar_init(bar + 1, 1); tc::fence_mbar_init(); }
     if (tid < 16) sBias[tid] = reinterpret_cast<const float *>(wblob + C::G_BIAS)[tid];
     // the operand map is written in full below (every S pixel, all 16 channels); only the guard
     // pixels past the band's S rows (read by the shifted taps of the last tile) are zeroed here
-    for (int i = tid; i < (C::MAP_PX - C::SROWS * C::WPS) * 4; i += OSB_THREADS) {
+    for (int i = tid; i < (C::MAP_PX - C::SROWS * C::WPS) * 4; i += C::THREADS) {
         const int px = C::SROWS * C::WPS + i / 4, pl = i & 3;       // 4 planes: hi c0, hi c1, lo c0, lo c1
         *reinterpret_cast<uint4 *>(sMap + (pl >> 1) * C::MAP_HALF_B + (pl & 1) * C::PLANE_B + px * 16) = make_uint4(0u, 0u, 0u, 0u);
     }
@@ -1087,7 +1096,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     const float nsc[3] = {1.0f / (255.0f * 0.229f), 1.0f / (255.0f * 0.224f), 1.0f / (255.0f * 0.225f)};
     const float nof[3] = {-0.485f / 0.229f, -0.456f / 0.224f, -0.406f / 0.225f};
     auto u8f = [](uint8_t b) { return __uint_as_float(0x4B000000u | (unsigned)b) - 8388608.0f; };
-    for (int q = tid; q < C::SROWS * C::WPS; q += OSB_THREADS) {
+    for (int q = tid; q < C::SROWS * C::WPS; q += C::THREADS) {
         const int Y = q / C::WPS, X = q - Y * C::WPS;
         int xo0[2], xo1[2];
         float lxv[2];
@@ -1182,7 +1191,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     tc::fence_after_sync();
     stamp();                                   // MMAs done
     // ---- epilogue: bias + ReLU -> sConv[lcy][cx][16]; rows outside the conv map = -inf
-    for (int t = grp; t < C::NT; t += OSB_GROUPS) {
+    for (int t = grp; t < C::NT; t += C::GROUPS) {
         const int p = t * 128 + quad * 32 + lane;
         float v[16], w[16];
         tc::tmem_ld16(tmem + ((uint32_t)(quad * 32) << 16) + t * 32, v);
@@ -1211,7 +1220,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     // ---- maxpool 3x3 s2 p1 -> operand planes [crop][hl][2 chunks][64*32 px][8] (PLANES) ...
     if (PLANES) {
         unsigned char *ob = reinterpret_cast<unsigned char *>(out) + (size_t)crop * (4 * 16 * 2048);
-        for (int o = tid; o < C::PR * 32 * 2; o += OSB_THREADS) {
+        for (int o = tid; o < C::PR * 32 * 2; o += C::THREADS) {
             const int px = o & 31, ch = (o >> 5) & 1, pr = o >> 6;
             float4 m0 = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY), m1 = m0;
 #pragma unroll
@@ -1237,7 +1246,7 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
         }
     }
     // ... or float32 out[crop][py][px][16]
-    for (int o = tid; o < (PLANES ? 0 : C::PR * 32 * 4); o += OSB_THREADS) {
+    for (int o = tid; o < (PLANES ? 0 : C::PR * 32 * 4); o += C::THREADS) {
         const int c4 = o & 3, px = (o >> 2) & 31, pr = o >> 7;
         float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
 #pragma unroll
@@ -1258,15 +1267,15 @@ stem_tc_kernel(const uint8_t *__restrict__ img, int H, int W, int pitch, const i
     if (!ok && tid == 0) atomicExch(status, 4);
     tc::fence_before_sync();
     __syncthreads();
-    if (warp == 0) tc::tmem_dealloc(tmem, 512);
+    if (warp == 0) tc::tmem_dealloc(tmem, C::TM_ALLOC);
 }
 
-// 512-thread launch with the programmatic-dependent-launch attribute (tc_common.cuh: pdl_wait / pdl_launch_dependents)
+// launch with the programmatic-dependent-launch attribute (tc_common.cuh: pdl_wait / pdl_launch_dependents)
 template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int smem, cudaStream_t st, Args... args) {
+cudaError_t launch_pdl_t(void (*kern)(KArgs...), int grid, int threads, int smem, cudaStream_t st, Args... args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(OSB_THREADS);
+    cfg.blockDim = dim3(threads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
@@ -1275,6 +1284,10 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int smem, cudaStream_t 
     cfg.attrs = at;
     cfg.numAttrs = ssb_pdl_enabled() ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), int grid, int smem, cudaStream_t st, Args... args) {
+    return launch_pdl_t(kern, grid, OSB_THREADS, smem, st, args...);
 }
 
 using PwT1 = PwCfg<64, 64, 64, 32, true>;     // after conv2: 64x32x64 -> 32x16x64
@@ -1350,9 +1363,9 @@ int ssb_reid_tc_stem(const uint8_t *img, int h, int w, int pitch, const int *box
     }
     long long *dbg = g_ssb_tc_dbg;
     if (planes)
-        SSB_CHECK_CUDA(launch_pdl(stem_tc_kernel<true>, n * StemCfg::NB, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
+        SSB_CHECK_CUDA(launch_pdl_t(stem_tc_kernel<true>, n * StemCfg::NB, StemCfg::THREADS, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
     else
-        SSB_CHECK_CUDA(launch_pdl(stem_tc_kernel<false>, n * StemCfg::NB, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
+        SSB_CHECK_CUDA(launch_pdl_t(stem_tc_kernel<false>, n * StemCfg::NB, StemCfg::THREADS, StemCfg::SMEM_B, st, img, h, w, pitch, boxes, wsec, out, status, dbg));
     g_ssb_launches++;
     return 0;
 }

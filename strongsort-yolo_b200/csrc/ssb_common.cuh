@@ -115,8 +115,8 @@ struct ssb_tracker {
     DetSlot slot[2];          // slot 0 aliases the buffers in `fs`
     // ssb_update embeds the two halves of a frame's crops on two streams (fork / join by events):
     // the partial last waves of one half's kernels are filled by the other half's
-    cudaStream_t side_stream[2];      // per detection slot: two frames' embeddings may be in flight
-    cudaEvent_t ev_fork[2], ev_join[2];
+    cudaStream_t side_stream[2][3];   // per detection slot (two frames' embeddings may be in flight) x extra parts
+    cudaEvent_t ev_fork[2], ev_join[2][3];
     int side_prio[2];
 };
 
@@ -129,7 +129,7 @@ int ssb_new_key();
 bool ssb_first_on_device(int key);
 int ssb_num_sms();      // SM count of the current device (cached per device)
 bool ssb_pdl_enabled(); // programmatic dependent launch between the ReID kernels (SSB_PDL=0 switches it off: A/B)
-bool ssb_split_enabled();   // ssb_update / ssb_reid embed a frame's crops as two halves on two streams (SSB_SPLIT=0: A/B)
+int ssb_split_parts();      // ssb_update / ssb_reid embed a frame's crops as this many parts on as many streams (SSB_SPLIT=1: unsplit, A/B)
 #define SSB_CHECK_CUDA(expr)                                                        \
     do {                                                                            \
         cudaError_t _e = (expr);                                                    \
@@ -171,8 +171,8 @@ int ssb_launch_appearance_tc(const unsigned char *gal_planes, const int *gal_cou
 inline int ssb_det_npad(int n) { return n <= 128 ? 128 : (n <= 256 ? 256 : 512); }
 int ssb_reid_forward(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch,
                      const int *boxes, int n, float *feats_out, cudaStream_t st);
-int ssb_reid_forward_halves(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
-                            int n, float *feats_out, cudaStream_t st, cudaStream_t side);
+int ssb_reid_forward_parts(ssb_tracker *t, int slot, const uint8_t *img, int h, int w, int pitch, const int *boxes,
+                           int n, float *feats_out, int parts, const cudaStream_t *streams);
 int64_t ssb_reid_ws_floats(int max_dets);
 int64_t ssb_reid_tc_block_bytes(int b);
 int ssb_reid_tc_block(int b, const float *x, float *y, const unsigned char *w, int n, int *status,

@@ -8,7 +8,7 @@ python - <<PY
 import json
 try:
     d = json.loads(open("gpurun_out/${tag}_bench.json").read().strip().splitlines()[-1])
-    print("value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "stream", round(d["e2e"]["streaming"]["value"], 1),
+    print("value", round(d["value"], 1), "e2e", round(d["e2e"]["value"], 1), "sync", round(d["e2e"]["synchronous"]["value"], 1),
           "reid_ms", round(d["roofline"]["reid_ms"], 4), "frac", round(d["roofline"]["frac"], 4))
     print("stages", {k: round(v, 1) if isinstance(v, float) else v for k, v in d["stages"].items()})
     print("cost", d["roofline_cost"])
