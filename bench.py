@@ -83,6 +83,9 @@ NET_HW = (384, 640)                    # 1080p letterboxed for the detector (str
 NUM_CLASSES = 80
 
 
+PIPE_LAG = 2      # update_pipelined(..., lag=2): rows come back two calls later, every inter-frame dependency is a device event
+
+
 def gen_frames(stream_id, count, pin, heads=True):
     """Pre-generate `count` frames of the stream: host images (pinned torch tensors when `pin`), the
     detections a detector would report (class = identity mod 80, so that class-aware NMS keeps
@@ -401,7 +404,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
         trk = StrongSORT(device=str(device), **trk_kw)
         pstream = torch.cuda.Stream(device=device)
         for i in range(W):
-            trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+            trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i], lag=PIPE_LAG)
         trk.flush_pipelined()
         barrier()
         torch.cuda.profiler.start()
@@ -409,7 +412,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
         l0 = lib.ssb_launch_count()
         e0.record(trk.stream)
         for k in range(K):
-            trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+            trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k], lag=PIPE_LAG)
         trk.flush_pipelined()
         e1.record(trk.stream)
         barrier()
@@ -458,7 +461,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     gal = ssb_dist.SharedGallery(trk) if args.shared_gallery else None
     pstream = torch.cuda.Stream(device=device)          # detector post-process of the next frame
     for i in range(W):
-        trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+        trk.update_pipelined(frame_dets(i, pstream), imgs_dev[i], lag=PIPE_LAG)
         if gal is not None:
             gal.step()
     trk.flush_pipelined()
@@ -469,7 +472,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     l0 = lib.ssb_launch_count()
     e0.record(st)
     for k in range(K):
-        trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+        trk.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k], lag=PIPE_LAG)
         if gal is not None:
             gal.step()                     # export + exchange + cross-stream match, inside the timed region
     trk.flush_pipelined()
@@ -492,14 +495,14 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
         galg = ssb_dist.SharedGallery(trkg)
         K2 = min(K, 60)
         for i in range(W):
-            trkg.update_pipelined(frame_dets(i, pstream), imgs_dev[i])
+            trkg.update_pipelined(frame_dets(i, pstream), imgs_dev[i], lag=PIPE_LAG)
             galg.step()
         trkg.flush_pipelined()
         barrier()
         g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         g0.record(trkg.stream)
         for k in range(K2):
-            trkg.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k])
+            trkg.update_pipelined(frame_dets(W + k, pstream), imgs_dev[W + k], lag=PIPE_LAG)
             galg.step()
         trkg.flush_pipelined()
         trkg.stream.wait_stream(galg.stream)
@@ -567,16 +570,28 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
     # ---------------- e2e, streaming call: update_pipelined with host frames -----------------------------
     trk3 = StrongSORT(device=str(device), **trk_kw)
     for i in range(W):
-        trk3.update_pipelined(frame_dets(i, pstream), imgs[i])
+        trk3.update_pipelined(frame_dets(i, pstream), imgs[i], lag=PIPE_LAG)
     trk3.flush_pipelined()
     barrier()
     t0 = time.perf_counter()
     for k in range(K):
-        trk3.update_pipelined(frame_dets(W + k, pstream), imgs[W + k])
+        trk3.update_pipelined(frame_dets(W + k, pstream), imgs[W + k], lag=PIPE_LAG)
     trk3.flush_pipelined()
     torch.cuda.synchronize()
     res["e2e_streaming"] = world * K / max_over_ranks(time.perf_counter() - t0)
     res["same_ids_streaming"] = int(trk3.last_counts[3]) == final_next_id
+    del trk3
+    trk3 = StrongSORT(device=str(device), **trk_kw)              # the same at one frame of latency
+    for i in range(W):
+        trk3.update_pipelined(frame_dets(i, pstream), imgs[i], lag=1)
+    trk3.flush_pipelined()
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(K):
+        trk3.update_pipelined(frame_dets(W + k, pstream), imgs[W + k], lag=1)
+    trk3.flush_pipelined()
+    torch.cuda.synchronize()
+    res["e2e_streaming_lag1"] = world * K / max_over_ranks(time.perf_counter() - t0)
     del trk3
 
     res.update(stages_us=stages, assoc_us=assoc_us, post_us=1000.0 * post_ms, frames=total,
@@ -712,10 +727,11 @@ def main():
                            "cross_stream_matches_last_frame_rank0": r["n_cross"]} if args.shared_gallery else {})},
             "e2e": {"value": r["e2e_streaming"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"],
                     "call": "StrongSORT.update_pipelined(dets, img) with the frame in pinned host memory -- the call the "
-                            "CLI's frame loop makes (yolo_multi_model.py); it returns frame k-1's rows while frame k is "
-                            "in flight; every step copies its frame H2D and reads its result rows D2H",
-                    "streaming": {"value": r["e2e_streaming"], "unit": UNIT,
-                                  "call": "StrongSORT.update_pipelined(dets, img) -- one frame of latency, host frame"},
+                            "CLI's frame loop makes (yolo_multi_model.py); called with lag=2 it returns frame k-2's rows while "
+                            "frames k-1 and k are in flight; every step copies its frame H2D and reads its result rows D2H",
+                    "lag_frames": PIPE_LAG,
+                    "lag1": {"value": r["e2e_streaming_lag1"], "unit": UNIT,
+                             "call": "StrongSORT.update_pipelined(dets, img, lag=1) -- rows of the previous frame, host frame"},
                     "synchronous": {"value": r["e2e"], "unit": UNIT,
                                     "call": "StrongSORT.prefetch(img); dets = detector post-process; StrongSORT.update(dets, img) "
                                             "-- the reference's blocking call shape: one host synchronisation per frame, "

@@ -48,8 +48,8 @@ static int env_flag(const char *name, int dflt) {
 }
 bool ssb_pdl_enabled() { static const int on = env_flag("SSB_PDL", 1); return on != 0; }
 bool ssb_pw_fused() { static const int on = env_flag("SSB_PW_FUSED", 1); return on != 0; }
-int ssb_split_parts() {        // SSB_SPLIT = parts a frame's crops are embedded in (0 / 1: unsplit), default 2
-    static const int p = [] { const char *v = getenv("SSB_SPLIT"); return v && *v ? atoi(v) : 2; }();
+int ssb_split_parts() {        // SSB_SPLIT = parts a frame's crops are embedded in (0 / 1: unsplit), default 3
+    static const int p = [] { const char *v = getenv("SSB_SPLIT"); return v && *v ? atoi(v) : 3; }();
     return p < 1 ? 1 : p > 4 ? 4 : p;
 }
 int ssb_num_sms() {

@@ -1513,6 +1513,10 @@ static int lsap_prepare(int L, size_t want_cost_bytes, size_t *dyn_bytes, size_t
     if (cost < 16384) cost = 16384 < avail ? 16384 : avail;
     *cost_bytes = cost;
     *dyn_bytes = (fixed + cost + 16 + 1023) & ~(size_t)1023;
+    // SSB_LSAP_EXCL=1 (A/B knob): claim a whole SM -- the solver is one latency-bound CTA, and a ReID CTA sharing its
+    // SM takes issue slots from the serial augmenting-path chain
+    static const int excl = [] { const char *v = getenv("SSB_LSAP_EXCL"); return v && *v ? atoi(v) : 0; }();
+    if (excl == 1 || (excl > 1 && L >= excl)) *dyn_bytes = g_lsap_smem_limit;
     if (*dyn_bytes > (size_t)g_lsap_smem_limit) *dyn_bytes = g_lsap_smem_limit;
     return 0;
 }

@@ -316,8 +316,11 @@ class StrongSORT:
     # ------------------------------------------------------------------
     # two-stage pipeline: embedding of frame k overlaps the association of frame k-1
     # ------------------------------------------------------------------
-    def _pipe_init(self):
+    def _pipe_init(self, lag=1):
         torch = self._torch
+        if lag not in (1, 2, 3):
+            raise ValueError("lag must be 1, 2 or 3 frames")
+        R = lag + 1                                  # result buffers: frames k-lag .. k are in flight
         with torch.cuda.device(self.device):
             # one embedding stream per slot: the OSNet launches of two consecutive frames may
             # interleave on the GPU and fill each other's partial waves
@@ -327,19 +330,25 @@ class StrongSORT:
             self._p_dets = [torch.empty((N, 6), dtype=torch.float32, device=self.device) for _ in range(2)]
             self._p_dets_pin = [torch.empty((N, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
             self._p_img = [None, None]
-            self._p_out = [torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device) for _ in range(2)]
-            self._p_pin = [torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+            self._p_out = [torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device) for _ in range(R)]
+            self._p_pin = [torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory() for _ in range(R)]
             self._p_embed_done = [torch.cuda.Event() for _ in range(2)]
-            self._p_assoc_done = [torch.cuda.Event() for _ in range(2)]
+            self._p_assoc_done = [torch.cuda.Event() for _ in range(2)]     # per embedding slot (GPU-side slot reuse)
+            self._p_res_done = [torch.cuda.Event() for _ in range(R)]       # per result buffer (host-side collect)
+        self._p_lag, self._p_ring = lag, R
         self._p_k = 0
-        self._p_meta = [None, None]
+        self._p_done = 0                             # frames collected so far
+        self._p_n = {}                               # detections of the frames not yet collected
 
-    def _pipe_collect(self, slot):
-        """Wait for the association of the frame in `slot`; return its rows."""
-        self._p_assoc_done[slot].synchronize()
-        buf = self._p_pin[slot].numpy()
+    def _pipe_collect(self, k):
+        """Wait for the association of frame k of the pipeline; return its rows."""
+        r = k % self._p_ring
+        self._p_res_done[r].synchronize()
+        buf = self._p_pin[r].numpy()
         cnt = buf[:32].view(np.int32)
         self.last_counts = cnt.copy()
+        self._p_done = k + 1
+        self._p_n.pop(k, None)
         self._raise_on_error(cnt)
         self._track_hint = int(cnt[CNT_TRACKS])
         m = int(cnt[CNT_OUT_ROWS])
@@ -347,14 +356,19 @@ class StrongSORT:
         self.last_det_index = rows[:, 7].astype(np.int64)
         return rows[:, :7]
 
-    def update_pipelined(self, dets, ori_img):
-        """Same arguments as ``update``; returns the rows of the PREVIOUS frame (None on the
-        first call) -- one frame of latency buys the overlap of this frame's OSNet with the
-        previous frame's association on a second stream.  ``flush_pipelined()`` returns the
-        rows of the last submitted frame.  Results are identical to ``update``."""
+    def update_pipelined(self, dets, ori_img, lag=1):
+        """Same arguments as ``update``; returns the rows of the frame submitted ``lag`` calls ago (None while
+        fewer have been submitted).  ``lag=1`` (default): one frame of latency buys the overlap of this frame's
+        OSNet with the previous frame's association on a second stream.  ``lag=2`` additionally takes the host out
+        of the loop: with one frame of latency the caller cannot hand over frame k+1 before frame k-1's rows came
+        back, so every second frame's OSNet starts a host round trip late; with two, every dependency between frames
+        is a device-side event.  ``lag`` is fixed by the first call (``flush_pipelined`` / ``drain_pipelined`` reset
+        it).  Results are identical to ``update``."""
         torch = self._torch
-        if not hasattr(self, "_pstream"):
-            self._pipe_init()
+        if not hasattr(self, "_pstream") or (self._p_k == 0 and self._p_lag != lag):
+            self._pipe_init(lag)
+        elif lag != self._p_lag:
+            raise ValueError("lag changes only on an empty pipeline (call drain_pipelined() first)")
         k, slot = self._p_k, self._p_k & 1
         if torch.is_tensor(dets):
             d = dets.detach().reshape(-1, 6).to(torch.float32)
@@ -373,6 +387,8 @@ class StrongSORT:
                     self._after_producer(d, pst, caller)
                     self._p_dets[slot][:n].copy_(d, non_blocking=True)
                 else:
+                    if self._p_lag > 1 and k >= 2:
+                        self._p_embed_done[slot].synchronize()        # frame k-2's copy out of the pinned rows is over
                     self._p_dets_pin[slot][:n].copy_(d)
                     self._p_dets[slot][:n].copy_(self._p_dets_pin[slot][:n], non_blocking=True)
             img_dev = None
@@ -390,33 +406,41 @@ class StrongSORT:
                                            _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
                                            C.c_void_p(pst.cuda_stream)), "ssb_embed")
             self._p_embed_done[slot].record(pst)
-        # The association of THIS frame is enqueued before the previous frame's result is read back: the host never
+        # The association of THIS frame is enqueued before any earlier frame's result is read back: the host never
         # holds the next ReID launch hostage to a device->host round trip.  track_hint only sizes grids and shared
-        # memory, so a bound suffices: the live tracks last read back + the detections of the frames read back since
+        # memory, so a bound suffices: the live tracks last read back + the detections of the frames submitted since
         # (every detection can start at most one track).
-        hint = min(self.cfg.max_tracks, self._track_hint + (self._p_n_prev if k > 0 else 0))
+        hint = min(self.cfg.max_tracks, self._track_hint + sum(self._p_n.values()))
+        r = k % self._p_ring
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.stream.wait_event(self._p_embed_done[slot])
             _lib.check(self._lib.ssb_associate(
-                self._h, slot, n, H, W, None, C.c_void_p(self._p_out[slot].data_ptr() + _HDR_BYTES),
-                _lib.ptr(self._p_out[slot]), hint, C.c_void_p(self.stream.cuda_stream)),
+                self._h, slot, n, H, W, None, C.c_void_p(self._p_out[r].data_ptr() + _HDR_BYTES),
+                _lib.ptr(self._p_out[r]), hint, C.c_void_p(self.stream.cuda_stream)),
                 "ssb_associate")
-            self._p_pin[slot].copy_(self._p_out[slot], non_blocking=True)
+            self._p_pin[r].copy_(self._p_out[r], non_blocking=True)
             self._p_assoc_done[slot].record(self.stream)
-        # the previous frame finishes while this frame's embeddings are computed
-        prev = self._pipe_collect(slot ^ 1) if k > 0 else None
-        self._p_n_prev = n
+            self._p_res_done[r].record(self.stream)
+        self._p_n[k] = n
         self._p_k = k + 1
-        return prev
+        # an earlier frame finishes while this frame's embeddings are computed
+        return self._pipe_collect(k - self._p_lag) if k >= self._p_lag else None
+
+    def drain_pipelined(self):
+        """Rows of every frame still in flight, oldest first (empty list if none); the pipeline is empty afterwards,
+        so the next ``update_pipelined`` calls return None again until ``lag`` frames are in flight."""
+        if not hasattr(self, "_pstream"):
+            return []
+        out = [self._pipe_collect(k) for k in range(self._p_done, self._p_k)]
+        self._p_k = self._p_done = 0
+        self._p_n = {}
+        return out
 
     def flush_pipelined(self):
-        """Rows of the last submitted frame (None if nothing is in flight); drains the pipeline, so the
-        next ``update_pipelined`` call returns None again."""
-        if not hasattr(self, "_pstream") or self._p_k == 0:
-            return None
-        rows = self._pipe_collect((self._p_k - 1) & 1)
-        self._p_k = 0
-        return rows
+        """Rows of the last submitted frame (None if nothing is in flight); drains the pipeline (with ``lag`` > 1 use
+        ``drain_pipelined`` to get every outstanding frame's rows)."""
+        out = self.drain_pipelined()
+        return out[-1] if out else None
 
     def export_tracks(self):
         """Live track table in list order (== Tracker.tracks of the oracle)."""

@@ -257,6 +257,25 @@ def test_pipelined_update_equals_synchronous():
     assert len(got) == len(want)
     for x, y in zip(got, want):
         np.testing.assert_array_equal(x, y)
+    # two frames of latency (no host round trip between frames), then back to one on the drained pipeline
+    for lag in (2, 3, 1):
+        c = StrongSORT(max_tracks=64, max_dets=32)
+        got = []
+        for i, f in enumerate(frames):
+            r = c.update_pipelined(f.dets, f.img, lag=lag)
+            assert (r is None) == (i < lag)
+            if r is not None:
+                got.append(r)
+        rest = c.drain_pipelined()
+        assert len(rest) == lag and c.drain_pipelined() == []
+        got += rest
+        assert len(got) == len(want)
+        for x, y in zip(got, want):
+            np.testing.assert_array_equal(x, y)
+        assert c.update_pipelined(frames[0].dets, frames[0].img, lag=1) is None      # empty pipeline: lag may change
+        with pytest.raises(ValueError):
+            c.update_pipelined(frames[1].dets, frames[1].img, lag=2)
+        c.drain_pipelined()
 
 
 def test_class_counts_match_the_reference_count_logic():

@@ -15,7 +15,7 @@ VARIANTS = {
     "base": ([], {}),                                       # the default build
     "base_nopdl": ([], {"SSB_PDL": "0"}),                   # programmatic dependent launch off
     "base_nosplit": ([], {"SSB_SPLIT": "0"}),               # whole frame on one stream instead of two halves
-    "base_split3": ([], {"SSB_SPLIT": "3"}),                # three / four parts on three / four streams
+    "base_split2": ([], {"SSB_SPLIT": "2"}),                # two / four parts on two / four streams (default: three)
     "base_split4": ([], {"SSB_SPLIT": "4"}),
     "base_nopwf": ([], {"SSB_PW_FUSED": "0"}),              # transitions as separate pw_tc launches (11 instead of 9)
     "dw1chain": (["-DSSB_DW_CHAINS=1"], {}),                # single 9-term depthwise chain (4 fewer instructions per row)
