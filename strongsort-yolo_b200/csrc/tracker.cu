@@ -1502,21 +1502,22 @@ static int lsap_prepare(int L, size_t want_cost_bytes, size_t *dyn_bytes, size_t
         return -3;
     }
     const size_t avail = (size_t)g_lsap_smem_limit - fixed - 16;
-    // The request is capped so that the kernel can sit next to a running ReID CTA (108 KB) in the two-stage pipeline
-    // instead of waiting for an empty SM: 96 KB of matrix (64 KB when the per-column state is large) hold config C2's
-    // dense 100 x 100 matrix (staging it densely is 18 % faster than its sparse form: 113 vs 134 us); a bigger matrix
-    // is kept as its non-background entries (12 bytes each; C4 has ~2 500) -- beyond that the dense global path runs.
-    static const size_t dense_max = [] { const char *v = getenv("SSB_LSAP_DENSE_MAX"); return v && *v ? (size_t)atoll(v) : (size_t)98304; }();
-    const size_t cap = fixed > 16384 ? 65536 : dense_max;
+    // The WHOLE request (per-row/column state + matrix) is capped at 112 KB so that the kernel fits the slot one
+    // stage-2 ReID CTA (108.6 KB with its reserve) leaves when it retires.  It matters in the two-stage pipeline: the
+    // block scheduler backfills freed slots with whatever fits, so a high-priority CTA that needs more than any
+    // single freed slot is starved until the ReID kernels of the next frame run out of CTAs -- at C4 (13 waves per
+    // kernel, three parts on three streams) that was the end of the whole forward: association and embedding ran
+    // back to back (6.98 ms per frame = 2.2 + 3.6 + gaps; SSB_LSAP_EXCL-style whole-SM requests changed nothing).
+    // Inside the cap: config C2's dense 100 x 100 matrix (staging it densely is 18 % faster than its sparse form:
+    // 113 vs 134 us); a bigger matrix is kept as its non-background entries (12 bytes each; C4 has ~2 500) -- beyond
+    // that the dense global path runs.
+    static const size_t total_cap = [] { const char *v = getenv("SSB_LSAP_SMEM_CAP"); return v && *v ? (size_t)atoll(v) : (size_t)114688; }();
+    size_t cap = total_cap > fixed + 16 + 16384 ? total_cap - fixed - 16 : 16384;
     size_t cost = want_cost_bytes < cap ? want_cost_bytes : cap;
     if (cost > avail) cost = avail;
     if (cost < 16384) cost = 16384 < avail ? 16384 : avail;
     *cost_bytes = cost;
     *dyn_bytes = (fixed + cost + 16 + 1023) & ~(size_t)1023;
-    // SSB_LSAP_EXCL=1 (A/B knob): claim a whole SM -- the solver is one latency-bound CTA, and a ReID CTA sharing its
-    // SM takes issue slots from the serial augmenting-path chain
-    static const int excl = [] { const char *v = getenv("SSB_LSAP_EXCL"); return v && *v ? atoi(v) : 0; }();
-    if (excl == 1 || (excl > 1 && L >= excl)) *dyn_bytes = g_lsap_smem_limit;
     if (*dyn_bytes > (size_t)g_lsap_smem_limit) *dyn_bytes = g_lsap_smem_limit;
     return 0;
 }

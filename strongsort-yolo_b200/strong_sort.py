@@ -329,7 +329,13 @@ class StrongSORT:
             N = self.cfg.max_dets
             self._p_dets = [torch.empty((N, 6), dtype=torch.float32, device=self.device) for _ in range(2)]
             self._p_dets_pin = [torch.empty((N, 6), dtype=torch.float32).pin_memory() for _ in range(2)]
-            self._p_img = [None, None]
+            # host frames: their H2D copies run on a stream of their own into a ring of three device buffers, so the
+            # copy of frame k+1 is under way while frame k is embedded (a buffer is free again once the embedding
+            # that read it is done -- not only once that frame has been associated)
+            self._p_copy = torch.cuda.Stream(device=self.device)
+            self._p_img = [None, None, None]
+            self._p_img_ready = [torch.cuda.Event() for _ in range(3)]
+            self._p_img_free = [torch.cuda.Event() for _ in range(3)]
             self._p_out = [torch.zeros(self._out_bytes, dtype=torch.uint8, device=self.device) for _ in range(R)]
             self._p_pin = [torch.zeros(self._out_bytes, dtype=torch.uint8).pin_memory() for _ in range(R)]
             self._p_embed_done = [torch.cuda.Event() for _ in range(2)]
@@ -380,6 +386,16 @@ class StrongSORT:
         H, W = int(ori_img.shape[0]), int(ori_img.shape[1])
         pst = self._pstreams[slot]
         caller = torch.cuda.current_stream(self.device)
+        host_img = n > 0 and not (torch.is_tensor(ori_img) and ori_img.is_cuda)
+        ri = k % 3
+        if host_img:
+            src = ori_img if torch.is_tensor(ori_img) else torch.from_numpy(np.ascontiguousarray(ori_img))
+            with torch.cuda.device(self.device), torch.cuda.stream(self._p_copy):
+                self._p_copy.wait_event(self._p_img_free[ri])         # frame k-3's embedding has read this buffer
+                if self._p_img[ri] is None or tuple(self._p_img[ri].shape) != tuple(src.shape):
+                    self._p_img[ri] = torch.empty(tuple(src.shape), dtype=torch.uint8, device=self.device)
+                self._p_img[ri].copy_(src, non_blocking=True)
+                self._p_img_ready[ri].record(self._p_copy)
         with torch.cuda.device(self.device), torch.cuda.stream(pst):
             pst.wait_event(self._p_assoc_done[slot])                  # slot free (frame k-2 associated)
             if n:
@@ -397,15 +413,14 @@ class StrongSORT:
                     self._after_producer(ori_img, pst, caller)
                     img_dev = ori_img.contiguous()
                 else:
-                    src = ori_img if torch.is_tensor(ori_img) else torch.from_numpy(np.ascontiguousarray(ori_img))
-                    if self._p_img[slot] is None or tuple(self._p_img[slot].shape) != tuple(src.shape):
-                        self._p_img[slot] = torch.empty(tuple(src.shape), dtype=torch.uint8, device=self.device)
-                    self._p_img[slot].copy_(src, non_blocking=True)
-                    img_dev = self._p_img[slot]
+                    pst.wait_event(self._p_img_ready[ri])
+                    img_dev = self._p_img[ri]
             _lib.check(self._lib.ssb_embed(self._h, slot, _lib.ptr(self._p_dets[slot]), n,
                                            _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
                                            C.c_void_p(pst.cuda_stream)), "ssb_embed")
             self._p_embed_done[slot].record(pst)
+            if host_img:
+                self._p_img_free[ri].record(pst)
         # The association of THIS frame is enqueued before any earlier frame's result is read back: the host never
         # holds the next ReID launch hostage to a device->host round trip.  track_hint only sizes grids and shared
         # memory, so a bound suffices: the live tracks last read back + the detections of the frames submitted since

@@ -11,7 +11,7 @@ timeout 1200 python -m pytest tests -m gpu -q > gpurun_out/${tag}_pytest.log 2>&
 echo "pytest rc=$?" >> gpurun_out/${tag}_pytest.log
 tail -12 gpurun_out/${tag}_pytest.log
 timeout 420 python tools/time_stages.py > gpurun_out/${tag}_stages.json 2> gpurun_out/${tag}_stages.err
-SSB_LSAP_DENSE_MAX=100000000 timeout 420 python tools/time_stages.py > gpurun_out/${tag}_stages_dense.json 2>> gpurun_out/${tag}_stages.err
+SSB_LSAP_SMEM_CAP=100000000 timeout 420 python tools/time_stages.py > gpurun_out/${tag}_stages_dense.json 2>> gpurun_out/${tag}_stages.err
 timeout 900 python tools/build_variants.py time > gpurun_out/${tag}_variants.json 2> gpurun_out/${tag}_variants.err
 cat gpurun_out/${tag}_variants.json
 python - <<PY
