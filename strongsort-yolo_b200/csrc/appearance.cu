@@ -178,9 +178,18 @@ int ssb_launch_appearance(const float *gallery, const int *gal_count, const int 
 // ---------------------------------------------------------------------------------------------
 template <int NTILES>
 struct AptCfg {
+    // Stage sizes chosen so that the CTA (80-96 KB) fits the slot a retiring stage-2 ReID CTA leaves: in the two-stage
+    // pipeline the previous frame's association runs under the next frame's embedding, and a 160-192 KB request
+    // (SSB_APT_BIG: 8 / NTILES chunks per stage) would wait for an SM to drain completely -- which a many-wave ReID
+    // kernel never lets happen.
+#ifdef SSB_APT_BIG
     static constexpr int KCH = 8 / NTILES;                 // 16-byte K chunks per stage
-    static constexpr int NPAD = NTILES * 128;
     static constexpr int NSTAGE = NTILES == 1 ? 3 : 4;
+#else
+    static constexpr int KCH = NTILES == 1 ? 4 : 2;
+    static constexpr int NSTAGE = NTILES == 1 ? 3 : NTILES == 2 ? 4 : 2;
+#endif
+    static constexpr int NPAD = NTILES * 128;
     static constexpr int A_HALF_B = KCH * NPAD * 16, A_B = 2 * A_HALF_B;            // detections
     static constexpr int B_HALF_B = KCH * SSB_GAL_ROWS * 16, B_B = 2 * B_HALF_B;    // gallery
     static constexpr int STAGE_B = A_B + B_B;

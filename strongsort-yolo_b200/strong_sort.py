@@ -415,10 +415,16 @@ class StrongSORT:
                 else:
                     pst.wait_event(self._p_img_ready[ri])
                     img_dev = self._p_img[ri]
+            trace = getattr(self, "pipeline_trace", None)       # tools/pipe_trace.py: a list collects timing events
+            if trace is not None:
+                tev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                tev[0].record(pst)
             _lib.check(self._lib.ssb_embed(self._h, slot, _lib.ptr(self._p_dets[slot]), n,
                                            _lib.ptr(img_dev) if img_dev is not None else None, H, W, 3 * W,
                                            C.c_void_p(pst.cuda_stream)), "ssb_embed")
             self._p_embed_done[slot].record(pst)
+            if trace is not None:
+                tev[1].record(pst)
             if host_img:
                 self._p_img_free[ri].record(pst)
         # The association of THIS frame is enqueued before any earlier frame's result is read back: the host never
@@ -429,10 +435,15 @@ class StrongSORT:
         r = k % self._p_ring
         with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
             self.stream.wait_event(self._p_embed_done[slot])
+            if trace is not None:
+                tev[2].record(self.stream)
             _lib.check(self._lib.ssb_associate(
                 self._h, slot, n, H, W, None, C.c_void_p(self._p_out[r].data_ptr() + _HDR_BYTES),
                 _lib.ptr(self._p_out[r]), hint, C.c_void_p(self.stream.cuda_stream)),
                 "ssb_associate")
+            if trace is not None:
+                tev[3].record(self.stream)
+                trace.append((k, tev))
             self._p_pin[r].copy_(self._p_out[r], non_blocking=True)
             self._p_assoc_done[slot].record(self.stream)
             self._p_res_done[r].record(self.stream)

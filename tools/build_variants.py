@@ -21,6 +21,7 @@ VARIANTS = {
     "dw1chain": (["-DSSB_DW_CHAINS=1"], {}),                # single 9-term depthwise chain (4 fewer instructions per row)
     "s3split": (["-DSSB_S3_SPLIT=true"], {}),
     "s2r16": (["-DSSB_S2_R=16", "-DSSB_S2_SPLIT=true"], {}),
+    "aptbig": (["-DSSB_APT_BIG"], {}),                      # appearance_tc with 160-192 KB stages (round-2 first version)
     "stem8": (["-DSSB_STEM_PR=8"], {}),                     # stem with 8 pooled rows per CTA, 512 threads, one CTA per SM
 }
 
