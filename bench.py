@@ -120,14 +120,19 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index):
+    def __init__(self, gpu_index, mode="nvml"):
         self.idx = gpu_index
         self.samples, self.reasons, self.max_mhz = [], set(), None
         self._stop = False
         self._thr = None
         self._smi = None
         self._nv = None
+        self.mode = mode
+        if mode == "off":
+            return
         try:
+            if mode == "smi":
+                raise RuntimeError("nvidia-smi subprocess requested")
             import pynvml
             import torch
             pynvml.nvmlInit()
@@ -169,6 +174,8 @@ class ClockSampler:
             time.sleep(0.02)
 
     def start(self):
+        if self.mode == "off":
+            return
         if self._nv is not None:
             import threading
             try:
@@ -466,7 +473,7 @@ def run_gpu_config(args, device, rank, world, lib, barrier, max_over_ranks, K, W
             gal.step()
     trk.flush_pipelined()
     barrier()
-    clocks = ClockSampler(device.index)
+    clocks = ClockSampler(device.index, args.clock_sampler)
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     l0 = lib.ssb_launch_count()
@@ -621,6 +628,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-sampler", default="nvml", choices=["nvml", "smi", "off"],
+                    help="how the SM clock is sampled during the timed region (in-process NVML thread / nvidia-smi subprocess)")
     ap.add_argument("--cpu-frames", type=int, default=20)
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS),
                     help="C2 (default, the BASELINE.json metric) or C4 (4K, 500 dets/frame)")

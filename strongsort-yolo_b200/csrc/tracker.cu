@@ -513,6 +513,34 @@ struct LsapSparse {
     const double *eval;
 };
 
+// One search step's per-lane work, branch-free: the CPL columns of a lane are independent, and written as guarded
+// blocks the compiler serialises them (four BSSY regions of LDS -> 3 DADD -> DSETP chains: ~110 cycles each, the
+// step's critical path).  Here every column's reduced cost is computed unconditionally (in-range address for the
+// columns past nc), the updates are selects, and the lane's arg-min (value ascending, tie key descending -- keys are
+// unique per column, so the order of comparison does not matter) is a tree.
+template <int CPL>
+__device__ __forceinline__ void lsap_lane_best(const double (&cand)[CPL], const unsigned (&ckey)[CPL],
+                                               double &bv, unsigned &bkey, int &bk) {
+    if (CPL == 4) {
+        const bool t01 = cand[1] < cand[0] || (cand[1] == cand[0] && ckey[1] > ckey[0]);
+        const bool t23 = cand[3] < cand[2] || (cand[3] == cand[2] && ckey[3] > ckey[2]);
+        const double v01 = t01 ? cand[1] : cand[0], v23 = t23 ? cand[3] : cand[2];
+        const unsigned k01 = t01 ? ckey[1] : ckey[0], k23 = t23 ? ckey[3] : ckey[2];
+        const bool t = v23 < v01 || (v23 == v01 && k23 > k01);
+        bv = t ? v23 : v01;
+        bkey = t ? k23 : k01;
+        bk = t ? (t23 ? 3 : 2) : (t01 ? 1 : 0);
+    } else {
+        bv = cand[0]; bkey = ckey[0]; bk = 0;
+#pragma unroll
+        for (int k = 1; k < CPL; k++) {
+            const bool t = cand[k] < bv || (cand[k] == bv && ckey[k] > bkey);
+            bv = t ? cand[k] : bv; bkey = t ? ckey[k] : bkey; bk = t ? k : bk;
+        }
+    }
+    if (bkey == 0u) bk = -1;                        // no active column on this lane (active keys are > 0)
+}
+
 template <int CPL, bool SPARSE>
 __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr, int nc0, int nr,
                               int nc, double *u, int *col4row, int *row4col_out, int lane,
@@ -537,9 +565,9 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
         while (sink == -1) {
             st_steps++;
             const double ui = u[i];
-            double bv = INFINITY;
-            unsigned bkey = 0;
-            int bk = -1;
+            double bv;
+            unsigned bkey;
+            int bk;
             double cs[SPARSE ? CPL : 1];
             if (SPARSE) {
 #pragma unroll
@@ -548,25 +576,30 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
                 for (int e = e0; e < e1; e++) {                  // warp-uniform trip count
                     const int cj = sp.ecol[e];
                     const double cv = sp.eval[e];
+                    const bool mine = lane == (cj & 31);
 #pragma unroll
-                    for (int k = 0; k < CPL; k++)
-                        if (k == (cj >> 5) && lane == (cj & 31)) cs[k] = cv;
+                    for (int k = 0; k < CPL; k++) cs[k] = (mine && k == (cj >> 5)) ? cv : cs[k];     // selects, not a dynamic index
                 }
             }
+            double cand[CPL];
+            unsigned ckey[CPL];
 #pragma unroll
             for (int k = 0; k < CPL; k++) {
                 const int j = lane + 32 * k;
-                if (j < nc && !((sc >> k) & 1u)) {
-                    const double cij = SPARSE ? cs[SPARSE ? k : 0]
-                                              : (staged ? C[(size_t)i * nc + j]
-                                                        : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]));
-                    const double r = minVal + cij - ui - v[k];
-                    if (r < spc[k]) { path[k] = i; spc[k] = r; }
-                    const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k])
-                                                      : (unsigned)(nc - pos[k]);
-                    if (spc[k] < bv || (spc[k] == bv && key > bkey)) { bv = spc[k]; bkey = key; bk = k; }
-                }
+                const bool act = j < nc && !((sc >> k) & 1u);
+                const int jj = j < nc ? j : 0;
+                const double cij = SPARSE ? cs[SPARSE ? k : 0]
+                                          : (staged ? C[(size_t)i * nc + jj]
+                                                    : (tr ? C[(size_t)jj * nc0 + i] : C[(size_t)i * nc0 + jj]));
+                const double r = minVal + cij - ui - v[k];
+                const bool upd = act && r < spc[k];
+                path[k] = upd ? i : path[k];
+                spc[k] = upd ? r : spc[k];
+                const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k]) : (unsigned)(nc - pos[k]);
+                cand[k] = act ? spc[k] : INFINITY;
+                ckey[k] = act ? key : 0u;
             }
+            lsap_lane_best<CPL>(cand, ckey, bv, bkey, bk);
             // warp arg-min: value (two 32-bit REDUX over an order-preserving key), then tie key
             const unsigned long long ok = f64_order_key(bv);
             const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
@@ -678,9 +711,9 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
         int i = curRow, num_remaining = nc, sink = -1;
         while (sink == -1) {
             const double ui = u[i];
-            double bv = INFINITY;
-            unsigned bkey = 0;
-            int bk = -1;
+            double bv;
+            unsigned bkey;
+            int bk;
             double cs[SPARSE ? CPL : 1];
             if (SPARSE) {
 #pragma unroll
@@ -689,24 +722,29 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
                 for (int e = e0; e < e1; e++) {                  // block-uniform trip count
                     const int cj = sp.ecol[e] - base;
                     const double cv = sp.eval[e];
+                    const bool mine = cj >= 0 && cj < 128 && lane == (cj & 31);
 #pragma unroll
-                    for (int k = 0; k < CPL; k++)
-                        if (cj >= 0 && k == (cj >> 5) && lane == (cj & 31) && cj < 128) cs[k] = cv;
+                    for (int k = 0; k < CPL; k++) cs[k] = (mine && k == (cj >> 5)) ? cv : cs[k];     // selects, not a dynamic index
                 }
             }
+            double cand[CPL];
+            unsigned ckey[CPL];
 #pragma unroll
-            for (int k = 0; k < CPL; k++) {
+            for (int k = 0; k < CPL; k++) {                      // branch-free, as in lsap_warp_reg
                 const int j = base + lane + 32 * k;
-                if (j < nc && !((sc >> k) & 1u)) {
-                    const double cij = SPARSE ? cs[SPARSE ? k : 0]
-                                              : (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]);
-                    const double r = minVal + cij - ui - v[k];
-                    if (r < spc[k]) { path[k] = i; spc[k] = r; }
-                    const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k])
-                                                      : (unsigned)(nc - pos[k]);
-                    if (spc[k] < bv || (spc[k] == bv && key > bkey)) { bv = spc[k]; bkey = key; bk = k; }
-                }
+                const bool act = j < nc && !((sc >> k) & 1u);
+                const int jj = j < nc ? j : 0;
+                const double cij = SPARSE ? cs[SPARSE ? k : 0]
+                                          : (tr ? C[(size_t)jj * nc0 + i] : C[(size_t)i * nc0 + jj]);
+                const double r = minVal + cij - ui - v[k];
+                const bool upd = act && r < spc[k];
+                path[k] = upd ? i : path[k];
+                spc[k] = upd ? r : spc[k];
+                const unsigned key = r4c[k] == -1 ? (0x40000000u | (unsigned)pos[k]) : (unsigned)(nc - pos[k]);
+                cand[k] = act ? spc[k] : INFINITY;
+                ckey[k] = act ? key : 0u;
             }
+            lsap_lane_best<CPL>(cand, ckey, bv, bkey, bk);
             // this warp's winner (value, then tie key), as in lsap_warp_reg
             const unsigned long long ok = f64_order_key(bv);
             const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
@@ -812,10 +850,21 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     const int nr = tr ? nc0 : nr0, nc = tr ? nr0 : nc0;
     const bool staged = (size_t)nr * nc * 8 <= cost_smem_bytes;
     if (staged) {
-        for (int e = tid; e < nr0 * nc0; e += blockDim.x) {
-            const int i0 = e / nc0, j0 = e - i0 * nc0;
-            const double c = C[e];
-            if (tr) m.cost[(size_t)j0 * nc + i0] = c; else m.cost[e] = c;
+        // eight loads in flight per thread: the matrix was just written by the cost kernels (L2), and a one-load-per-
+        // iteration loop spent 20 K cycles (11 us) on round trips for config C2's 78 KB
+        const int total = nr0 * nc0, step = blockDim.x;
+        for (int e0 = tid; e0 < total; e0 += 8 * step) {
+            double c[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const int e = e0 + q * step; c[q] = e < total ? C[e] : 0.0; }
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = e0 + q * step;
+                if (e < total) {
+                    const int i0 = e / nc0, j0 = e - i0 * nc0;
+                    if (tr) m.cost[(size_t)j0 * nc + i0] = c[q]; else m.cost[e] = c[q];
+                }
+            }
         }
     }
     for (int i = tid; i < nr; i += blockDim.x) { m.u[i] = 0.0; m.col4row[i] = -1; }
