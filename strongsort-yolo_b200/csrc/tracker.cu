@@ -604,24 +604,29 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
             const unsigned long long ok = f64_order_key(bv);
             const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
             const unsigned hmin = __reduce_min_sync(0xffffffffu, bk >= 0 ? hi : 0xffffffffu);
-            const unsigned lmin = __reduce_min_sync(0xffffffffu, (bk >= 0 && hi == hmin) ? lo : 0xffffffffu);
-            const bool vwin = bk >= 0 && hi == hmin && lo == lmin;
+            bool vwin = bk >= 0 && hi == hmin;
             unsigned wmask = __ballot_sync(0xffffffffu, vwin);
             if (wmask == 0) return false;
-            if (wmask & (wmask - 1)) {              // several lanes tie on the value: scipy's scan-order rule
-                const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
-                wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            if (wmask & (wmask - 1)) {              // several lanes share the top word: compare the low word ...
+                const unsigned lmin = __reduce_min_sync(0xffffffffu, vwin ? lo : 0xffffffffu);
+                vwin = vwin && lo == lmin;
+                wmask = __ballot_sync(0xffffffffu, vwin);
+                if (wmask & (wmask - 1)) {          // ... and on equal values scipy's scan-order rule
+                    const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
+                    wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+                }
             }
             const int wl = __ffs(wmask) - 1;
-            minVal = __shfl_sync(0xffffffffu, bv, wl);
-            if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible
-            const int wk = __shfl_sync(0xffffffffu, bk, wl);
+            // every lane prepares the (position, row) of ITS best column, so the four broadcasts from the winning lane
+            // are independent (one shuffle round instead of two dependent ones)
             int my_pos = -1, my_r = -1;
 #pragma unroll
-            for (int k = 0; k < CPL; k++)
-                if (k == wk) { my_pos = pos[k]; my_r = r4c[k]; }
+            for (int k = 0; k < CPL; k++) { my_pos = k == bk ? pos[k] : my_pos; my_r = k == bk ? r4c[k] : my_r; }
+            const int wk = __shfl_sync(0xffffffffu, bk, wl);
             const int index = __shfl_sync(0xffffffffu, my_pos, wl);
             const int rj = __shfl_sync(0xffffffffu, my_r, wl);
+            minVal = __shfl_sync(0xffffffffu, bv, wl);
+            if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible
             const int jwin = wl + 32 * wk;
             if (lane == wl) sc |= 1u << wk;
 #pragma unroll
@@ -633,13 +638,20 @@ __device__ bool lsap_warp_reg(const double *__restrict__ C, bool staged, bool tr
         if (stats) { const long long t = clock64(); st_search += t - st_t; st_t = t; }
         // dual updates (column-wise: visited column j with row r = row4col[j] gives u[r])
         if (lane == 0) u[curRow] += minVal;
+        {   // the CPL columns' updates interleaved (loads first, then the stores); rows of distinct columns are distinct
+            double nu[CPL];
+            bool wr[CPL];
 #pragma unroll
-        for (int k = 0; k < CPL; k++) {
-            if ((sc >> k) & 1u) {
+            for (int k = 0; k < CPL; k++) {
+                const bool vis = (sc >> k) & 1u;
                 const double dlt = minVal - spc[k];
-                if (r4c[k] >= 0) u[r4c[k]] += dlt;
-                v[k] -= dlt;
+                wr[k] = vis && r4c[k] >= 0;
+                nu[k] = u[wr[k] ? r4c[k] : curRow] + dlt;
+                v[k] = vis ? v[k] - dlt : v[k];
             }
+#pragma unroll
+            for (int k = 0; k < CPL; k++)
+                if (wr[k]) u[r4c[k]] = nu[k];
         }
         __syncwarp();
         // augment along the path
@@ -749,12 +761,16 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
             const unsigned long long ok = f64_order_key(bv);
             const unsigned hi = (unsigned)(ok >> 32), lo = (unsigned)ok;
             const unsigned hmin = __reduce_min_sync(0xffffffffu, bk >= 0 ? hi : 0xffffffffu);
-            const unsigned lmin = __reduce_min_sync(0xffffffffu, (bk >= 0 && hi == hmin) ? lo : 0xffffffffu);
-            const bool vwin = bk >= 0 && hi == hmin && lo == lmin;
+            bool vwin = bk >= 0 && hi == hmin;
             unsigned wmask = __ballot_sync(0xffffffffu, vwin);
-            if (wmask & (wmask - 1)) {
-                const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
-                wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+            if (wmask & (wmask - 1)) {              // several lanes share the top word: low word, then the tie key
+                const unsigned lmin = __reduce_min_sync(0xffffffffu, vwin ? lo : 0xffffffffu);
+                vwin = vwin && lo == lmin;
+                wmask = __ballot_sync(0xffffffffu, vwin);
+                if (wmask & (wmask - 1)) {
+                    const unsigned kmax = __reduce_max_sync(0xffffffffu, vwin ? bkey : 0u);
+                    wmask = __ballot_sync(0xffffffffu, vwin && bkey == kmax);
+                }
             }
             const int wl = wmask ? __ffs(wmask) - 1 : -1;
             int my_pos = -1, my_r = -1;
