@@ -117,8 +117,9 @@ int ssb_update(ssb_tracker *t, const float *dets_dev, int n, const uint8_t *img_
 /* The same step split in its two stages, for callers that overlap them on two streams:
  * ssb_embed (detection prep + OSNet embeddings into slot 0/1; independent of the track
  * table) for frame t+1 may run while ssb_associate (everything else) runs for frame t.
- * ssb_update(...) == ssb_embed(slot 0) + ssb_associate(slot 0).  (Frames of >= 48 crops are embedded as two halves,
- * the second on an internal stream of the slot, inside the slot's own workspace.)  The caller orders the stages with
+ * ssb_update(...) == ssb_embed(slot 0) + ssb_associate(slot 0).  (Frames of >= 48 crops are embedded in up to
+ * three parts -- the others on internal streams of the slot, of the caller's stream priority, joined back before the
+ * call returns control of `stream` -- inside the slot's own workspace.)  The caller orders the stages with
  * events; img_dev == NULL in ssb_embed skips the OSNet (the caller then passes feats_dev to ssb_associate). */
 int ssb_embed(ssb_tracker *t, int slot, const float *dets_dev, int n, const uint8_t *img_dev,
               int h, int w, int pitch, ssb_stream_t stream);
