@@ -899,8 +899,20 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
         __shared__ double s_bg[8];
         __shared__ int s_total;
         const int wid = tid >> 5, nwarp = blockDim.x >> 5;
+        // All three passes keep EIGHT loads in flight per thread: the matrix sits in L2 (the cost kernels just wrote
+        // it), and with one load per iteration each pass cost (elements / 256) x one L2 round trip -- ~0.3 ms per pass
+        // at C4's 600 x 496, three passes, half of the stage.
         double mx = -INFINITY;
-        for (int e = tid; e < nr0 * nc0; e += blockDim.x) { const double c = C[e]; if (c > mx) mx = c; }
+        {
+            const int total = nr0 * nc0, step = blockDim.x;
+            for (int e0 = tid; e0 < total; e0 += 8 * step) {
+                double c[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) { const int e = e0 + q * step; c[q] = e < total ? C[e] : -INFINITY; }
+#pragma unroll
+                for (int q = 0; q < 8; q++) if (c[q] > mx) mx = c[q];
+            }
+        }
 #pragma unroll
         for (int o = 16; o; o >>= 1) { const double t = __shfl_xor_sync(0xffffffffu, mx, o); if (t > mx) mx = t; }
         if (lane == 0) s_bg[wid] = mx;
@@ -911,33 +923,71 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
         double *evals = m.cost;
         int *ecols = (int *)(m.cost + cap);
         int *rowptr = m.remaining, *rowlen = m.path;
-        // pass 1: entries != bg per working row (warp per row)
-        for (int i = wid; i < nr; i += nwarp) {
-            int cnt = 0;
-            for (int j0 = 0; j0 < nc; j0 += 32) {
-                const int j = j0 + lane;
-                const bool nz = j < nc && !((tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]) == mx);
-                cnt += __popc(__ballot_sync(0xffffffffu, nz));
+        // pass 1: entries != bg per working row.  Not transposed: warp per row, lanes across the (contiguous) columns.
+        // Transposed (working row = original column): lane per working row, so that a warp's 32 loads of one original
+        // row are contiguous -- lanes across columns would touch 32 cache lines per load.
+        if (!tr) {
+            for (int i = wid; i < nr; i += nwarp) {
+                int cnt = 0;
+                for (int j0 = 0; j0 < nc; j0 += 256) {
+                    double c[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) { const int j = j0 + 32 * q + lane; c[q] = j < nc ? C[(size_t)i * nc0 + j] : mx; }
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cnt += __popc(__ballot_sync(0xffffffffu, !(c[q] == mx)));
+                }
+                if (lane == 0) rowlen[i] = cnt;
             }
-            if (lane == 0) rowlen[i] = cnt;
+        } else {
+            for (int i0 = wid * 32; i0 < nr; i0 += nwarp * 32) {
+                const int i = i0 + lane;
+                int cnt = 0;
+                for (int j0 = 0; j0 < nc; j0 += 8) {
+                    double c[8];
+#pragma unroll
+                    for (int q = 0; q < 8; q++) c[q] = (i < nr && j0 + q < nc) ? C[(size_t)(j0 + q) * nc0 + i] : mx;
+#pragma unroll
+                    for (int q = 0; q < 8; q++) cnt += !(c[q] == mx);
+                }
+                if (i < nr) rowlen[i] = cnt;
+            }
         }
         __syncthreads();
-        if (tid == 0) {                                    // serial exclusive scan (nr <= 512)
+        if (tid == 0) {                                    // serial exclusive scan (nr <= 1024)
             int acc = 0;
             for (int i = 0; i < nr; i++) { rowptr[i] = acc; acc += rowlen[i]; }
             s_total = acc;
         }
         __syncthreads();
         if ((size_t)s_total <= cap) {
-            for (int i = wid; i < nr; i += nwarp) {        // pass 2: fill, column order
-                int off = rowptr[i];
-                for (int j0 = 0; j0 < nc; j0 += 32) {
-                    const int j = j0 + lane;
-                    const double c = j < nc ? (tr ? C[(size_t)j * nc0 + i] : C[(size_t)i * nc0 + j]) : mx;
-                    const bool nz = j < nc && !(c == mx);
-                    const unsigned bal = __ballot_sync(0xffffffffu, nz);
-                    if (nz) { const int q = off + __popc(bal & ((1u << lane) - 1)); evals[q] = c; ecols[q] = j; }
-                    off += __popc(bal);
+            if (!tr) {
+                for (int i = wid; i < nr; i += nwarp) {        // pass 2: fill, column order
+                    int off = rowptr[i];
+                    for (int j0 = 0; j0 < nc; j0 += 256) {
+                        double c[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) { const int j = j0 + 32 * q + lane; c[q] = j < nc ? C[(size_t)i * nc0 + j] : mx; }
+#pragma unroll
+                        for (int q = 0; q < 8; q++) {
+                            const bool nz = !(c[q] == mx);
+                            const unsigned bal = __ballot_sync(0xffffffffu, nz);
+                            if (nz) { const int w = off + __popc(bal & ((1u << lane) - 1)); evals[w] = c[q]; ecols[w] = j0 + 32 * q + lane; }
+                            off += __popc(bal);
+                        }
+                    }
+                }
+            } else {
+                for (int i0 = wid * 32; i0 < nr; i0 += nwarp * 32) {
+                    const int i = i0 + lane;
+                    int off = i < nr ? rowptr[i] : 0;
+                    for (int j0 = 0; j0 < nc; j0 += 8) {
+                        double c[8];
+#pragma unroll
+                        for (int q = 0; q < 8; q++) c[q] = (i < nr && j0 + q < nc) ? C[(size_t)(j0 + q) * nc0 + i] : mx;
+#pragma unroll
+                        for (int q = 0; q < 8; q++)
+                            if (!(c[q] == mx)) { evals[off] = c[q]; ecols[off] = j0 + q; off++; }
+                    }
                 }
             }
             sparse = true;
