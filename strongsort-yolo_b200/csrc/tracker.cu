@@ -1396,32 +1396,60 @@ __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H
     }
     __syncthreads();
     const int n_new = s_nnew;
-    for (int k = wid; k < n_new; k += nw) {
+    // (C4 starts ~240 tracks per frame: as one warp per track with lane 0 writing the scalars and the 64 covariance
+    // entries and 16 dependent load -> divide -> store rounds for the feature, this step was 140 of the kernel's
+    // 162 us; now three flat loops over all threads, the feature copy with eight loads in flight)
+    for (int k = tid; k < n_new; k += blockDim.x) {            // 2a. scalars + mean
         const int det = fs.undet[k];
         const int s = tt.free_stack[n_free - 1 - k];
-        if (lane == 0) {
-            tt.order[T0 + k] = s;
+        tt.order[T0 + k] = s;
+        const float *z = fs.det_xyah + det * 4;
+        double *m = tt.mean + (size_t)s * 8;
+        m[0] = (double)z[0]; m[1] = (double)z[1]; m[2] = (double)z[2]; m[3] = (double)z[3];
+        m[4] = 0; m[5] = 0; m[6] = 0; m[7] = 0;
+        tt.track_id[s] = next_id + k;
+        tt.state[s] = SSB_TENTATIVE;
+        tt.hits[s] = 1; tt.age[s] = 1; tt.tsu[s] = 0;
+        tt.cls[s] = (int)fs.det_cls[det];
+        tt.conf[s] = fs.det_conf[det];
+        tt.last_det[s] = det;
+        tt.gal_count[s] = 0; tt.gal_head[s] = 0;
+    }
+    for (int e = tid; e < n_new * 64; e += blockDim.x) {       // 2b. covariance: diag(std^2), zeros elsewhere
+        const int k = e >> 6, idx = e & 63, i = idx / 9;
+        const int det = fs.undet[k];
+        const int s = tt.free_stack[n_free - 1 - k];
+        double v = 0.0;
+        if (idx == i * 9) {
             const float *z = fs.det_xyah + det * 4;
             const double z0 = z[0], z1 = z[1], z2 = z[2], z3 = z[3];
-            double *m = tt.mean + (size_t)s * 8;
-            m[0] = z0; m[1] = z1; m[2] = z2; m[3] = z3; m[4] = 0; m[5] = 0; m[6] = 0; m[7] = 0;
-            double std[8] = {2 * KF_WP * z0, 2 * KF_WP * z1, 1 * z2, 2 * KF_WP * z3,
-                             10 * KF_WV * z0, 10 * KF_WV * z1, 0.1 * z2, 10 * KF_WV * z3};
-            double *P = tt.cov + (size_t)s * 64;
-            for (int e = 0; e < 64; e++) P[e] = 0.0;
-            for (int i = 0; i < 8; i++) P[i * 9] = std[i] * std[i];
-            tt.track_id[s] = next_id + k;
-            tt.state[s] = SSB_TENTATIVE;
-            tt.hits[s] = 1; tt.age[s] = 1; tt.tsu[s] = 0;
-            tt.cls[s] = (int)fs.det_cls[det];
-            tt.conf[s] = fs.det_conf[det];
-            tt.last_det[s] = det;
-            tt.gal_count[s] = 0; tt.gal_head[s] = 0;
+            const double std = i == 0 ? 2 * KF_WP * z0 : i == 1 ? 2 * KF_WP * z1 : i == 2 ? 1 * z2 : i == 3 ? 2 * KF_WP * z3
+                             : i == 4 ? 10 * KF_WV * z0 : i == 5 ? 10 * KF_WV * z1 : i == 6 ? 0.1 * z2 : 10 * KF_WV * z3;
+            v = std * std;
         }
-        const float nrm = fs.det_norm[det];
-        const float *f = fs.feats + (size_t)det * d.D;
-        float *tf = tt.feat + (size_t)s * d.D;
-        for (int i = lane; i < d.D; i += 32) tf[i] = f[i] / nrm;
+        tt.cov[(size_t)s * 64 + idx] = v;
+    }
+    {                                                          // 2c. EMA feature = unit embedding
+        const int D = d.D, total = n_new * D, step = blockDim.x;
+        for (int e0 = tid; e0 < total; e0 += 8 * step) {
+            float f[8], nrm[8];
+            int dst[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+                const int e = e0 + q * step;
+                dst[q] = -1; f[q] = 0.f; nrm[q] = 1.f;
+                if (e < total) {
+                    const int k = e / D, i = e - k * D;
+                    const int det = fs.undet[k];
+                    f[q] = fs.feats[(size_t)det * D + i];
+                    nrm[q] = fs.det_norm[det];
+                    dst[q] = tt.free_stack[n_free - 1 - k] * D + i;
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; q++)
+                if (dst[q] >= 0) tt.feat[dst[q]] = f[q] / nrm[q];
+        }
     }
     __syncthreads();
     // 3. drop deleted tracks, keep order; recycle their slots
