@@ -1467,8 +1467,13 @@ __global__ void bookkeep_kernel(TrackTable tt, FrameScratch fs, SsbDims d, int H
         if (tt.state[s] != SSB_DELETED) tt.order_tmp[off++] = s;
         else {
             tt.free_stack[free_base + offd] = s; offd++; tt.gal_count[s] = 0; tt.gal_head[s] = 0;
-            const int maj = hist_majority(tt.cls_hist + (size_t)s * SSB_NCLS, true);    // --count: the id keeps counting
-            if (maj >= 0) atomicAdd(&tt.dead_count[maj], 1);
+            // --count: a deleted id keeps counting.  Only a track that was ever confirmed (hits >= n_init; a tentative
+            // track dies on its first miss) has label lines, i.e. a non-zero histogram: the 80-entry scan + clear of the
+            // ~240 tentative tracks C4 drops per frame was 100 of this kernel's 160 us
+            if (tt.hits[s] >= d.n_init) {
+                const int maj = hist_majority(tt.cls_hist + (size_t)s * SSB_NCLS, true);
+                if (maj >= 0) atomicAdd(&tt.dead_count[maj], 1);
+            }
         }
     }
     __syncthreads();
@@ -1655,7 +1660,12 @@ static int lsap_prepare(int L, size_t want_cost_bytes, size_t *dyn_bytes, size_t
     // 113 vs 134 us); a bigger matrix is kept as its non-background entries (12 bytes each; C4 has ~2 500) -- beyond
     // that the dense global path runs.
     static const size_t total_cap = [] { const char *v = getenv("SSB_LSAP_SMEM_CAP"); return v && *v ? (size_t)atoll(v) : (size_t)114688; }();
-    size_t cap = total_cap > fixed + 16 + 16384 ? total_cap - fixed - 16 : 16384;
+    size_t cap = total_cap > fixed + 16 ? total_cap - fixed - 16 : 0;
+    // ... but never at the price of matrix capacity: once the per-row/column state leaves less than 64 KB under the
+    // cap (C4 with two frames of detections in the track bound: 80 KB of state), the request takes what the SM has --
+    // a stream whose non-background entries outgrow the store falls to the dense global path, 10 ms instead of 2.5
+    // per frame (profiles/r02_pipeline_trace.md, frames 27+ of the C4 stream under the 112 KB cap).
+    if (cap < 65536) cap = avail;
     size_t cost = want_cost_bytes < cap ? want_cost_bytes : cap;
     if (cost > avail) cost = avail;
     if (cost < 16384) cost = 16384 < avail ? 16384 : avail;
