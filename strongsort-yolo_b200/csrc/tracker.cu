@@ -699,12 +699,12 @@ struct LsapXch {                 // one warp's winner of a search step
 };
 __device__ __forceinline__ void lsap_bar(int nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 
-template <int NW, bool SPARSE>
+template <int NW, bool SPARSE, int CPL = 4>
 __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, int nr, int nc, double *u, int *col4row,
                                int *row4col_out, LsapXch *xch /* [2][NW] shared */, int *s_aug /* [2] shared */,
                                LsapSparse sp = LsapSparse()) {
-    constexpr int CPL = 4;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, base = wid * 128;
+    constexpr int WC = 32 * CPL;                 // columns per warp (CPL = 8: 1025 .. 2048 working columns on 8 warps)
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, base = wid * WC;
     double v[CPL], spc[CPL];
     int pos[CPL], r4c[CPL], path[CPL];
     unsigned sc = 0;
@@ -734,7 +734,7 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
                 for (int e = e0; e < e1; e++) {                  // block-uniform trip count
                     const int cj = sp.ecol[e] - base;
                     const double cv = sp.eval[e];
-                    const bool mine = cj >= 0 && cj < 128 && lane == (cj & 31);
+                    const bool mine = cj >= 0 && cj < WC && lane == (cj & 31);
 #pragma unroll
                     for (int k = 0; k < CPL; k++) cs[k] = (mine && k == (cj >> 5)) ? cv : cs[k];     // selects, not a dynamic index
                 }
@@ -799,7 +799,7 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
             minVal = g.bv;
             if (!(minVal < INFINITY)) return false;                 // NaN / inf costs: infeasible
             const int jwin = g.j, index = g.pos, rj = g.r4c;
-            if (jwin - base == lane + 32 * ((jwin - base) >> 5) && jwin >= base && jwin < base + 128)
+            if (jwin - base == lane + 32 * ((jwin - base) >> 5) && jwin >= base && jwin < base + WC)
                 sc |= 1u << ((jwin - base) >> 5);
 #pragma unroll
             for (int k = 0; k < CPL; k++)
@@ -822,7 +822,7 @@ __device__ bool lsap_block_reg(const double *__restrict__ C, bool tr, int nc0, i
         int j = sink;
         while (true) {
             const int lj = j - base;
-            const bool mine = lj >= 0 && lj < 128 && (lj & 31) == lane;
+            const bool mine = lj >= 0 && lj < WC && (lj & 31) == lane;
             if (mine) {
                 int r = -1;
 #pragma unroll
@@ -895,7 +895,7 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
     // global-memory path when the real entries do not fit.
     LsapSparse sp;
     bool sparse = false;
-    if (!staged && nc <= 1024) {
+    if (!staged && nc <= 2048) {
         __shared__ double s_bg[8];
         __shared__ int s_total;
         const int wid = tid >> 5, nwarp = blockDim.x >> 5;
@@ -1015,8 +1015,10 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
                 for (int j = lane; j < nc; j += 32) m.row4col[j] = -1;
             }
         }
-    } else if (nc <= 1024) {
-        // 129 .. 1024 working columns: 4 columns per lane on 2 / 4 / 8 warps (lsap_block_reg)
+    } else if (nc <= 2048) {
+        // 129 .. 1024 working columns: 4 columns per lane on 2 / 4 / 8 warps (lsap_block_reg); up to 2048: 8 per lane
+        // (a crowded stream confirms short-lived tracks by chance overlaps and keeps them max_age frames: C4 passes
+        // 1024 confirmed tracks after ~25 frames, and the dense global path behind this branch costs 10 ms a frame)
         const int nwarp_s = nc <= 256 ? 2 : (nc <= 512 ? 4 : 8);
         if (tid < 32 * nwarp_s) {
             const double *Cw = staged ? m.cost : C;
@@ -1029,9 +1031,12 @@ __device__ void lsap_block(const double *__restrict__ C, int nr0, int nc0, LsapS
             else if (nwarp_s == 4)
                 okr = sparse ? lsap_block_reg<4, true>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
                              : lsap_block_reg<4, false>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
-            else
+            else if (nc <= 1024)
                 okr = sparse ? lsap_block_reg<8, true>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
                              : lsap_block_reg<8, false>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
+            else
+                okr = sparse ? lsap_block_reg<8, true, 8>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug, sp)
+                             : lsap_block_reg<8, false, 8>(Cw, trw, ldw, nr, nc, m.u, m.col4row, m.row4col, s_xch, s_aug);
             if (!okr) {
                 for (int i = tid; i < nr; i += 32 * nwarp_s) m.col4row[i] = -1;
                 for (int j = tid; j < nc; j += 32 * nwarp_s) m.row4col[j] = -1;

@@ -139,7 +139,8 @@ def _lsap_cases():
     rng = np.random.default_rng(8)
     shapes = [(1, 1), (1, 9), (9, 1), (10, 10), (33, 64), (64, 33), (100, 100), (115, 100),
               (100, 130), (256, 500), (300, 170), (40, 40), (344, 498), (498, 491), (500, 300),
-              (600, 496), (300, 700), (1000, 640)]          # 513 .. 1024 working columns: 32 columns per lane
+              (600, 496), (300, 700), (1000, 640),          # 513 .. 1024 working columns: 8 warps x 4 columns per lane
+              (1100, 500), (480, 1900)]                     # 1025 .. 2048: 8 columns per lane (C4 after ~25 frames)
     for (nr, nc) in shapes:
         for kind in range(6):
             if kind == 0:
