@@ -18,5 +18,5 @@ try:
 except Exception as e:
     print("bench parse:", e)
 PY
-timeout 600 python bench.py --impl reference --steps 10 --warmup 2 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err
+timeout 200 python bench.py --impl reference --steps 4 --warmup 1 > gpurun_out/${tag}_bench_ref.json 2>> gpurun_out/${tag}_bench.err
 tail -c 400 gpurun_out/${tag}_bench_ref.json
