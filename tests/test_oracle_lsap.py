@@ -44,3 +44,33 @@ def test_lsap_c_edge_shapes(shape):
     r2, c2 = linear_sum_assignment_c(c)
     np.testing.assert_array_equal(r1, r2)
     np.testing.assert_array_equal(c1, c2)
+
+
+def test_lane_arg_min_tree_equals_the_sequential_scan():
+    """csrc/tracker.cu `lsap_lane_best`: the lane's winner among its (value, tie key) candidates is taken by a compare
+    tree instead of the sequential scan the solver was first written with.  Both pick min value, then max key; keys are
+    unique per column (they encode the column's scan position) and inactive columns carry (inf, 0) -- under those
+    conditions the order of comparison cannot matter.  Checked here on the rule itself, ties and infinities included."""
+    rng = np.random.default_rng(11)
+
+    def sequential(vals, keys):
+        bv, bkey, bk = np.inf, 0, -1
+        for k, (v, key) in enumerate(zip(vals, keys)):
+            if key and (v < bv or (v == bv and key > bkey)):
+                bv, bkey, bk = v, key, k
+        return bk
+
+    def tree(vals, keys):
+        def better(a, b):               # does b beat a
+            return vals[b] < vals[a] or (vals[b] == vals[a] and keys[b] > keys[a])
+        w01 = 1 if better(0, 1) else 0
+        w23 = 3 if better(2, 3) else 2
+        w = w23 if better(w01, w23) else w01
+        return w if keys[w] else -1
+
+    pool = np.array([0.0, 0.05, 0.2 + 1e-5, 0.2 + 1e-5, 0.7, np.inf])
+    for _ in range(20000):
+        vals = rng.choice(pool, 4)
+        keys = rng.permutation(np.arange(1, 9))[:4] * rng.integers(0, 2, 4)      # unique non-zero keys, 0 = inactive
+        vals = np.where(keys == 0, np.inf, vals)
+        assert sequential(vals, keys) == tree(vals, keys), (vals, keys)
