@@ -6,26 +6,24 @@ Metric (BASELINE.json): tracked frames/sec at 1080p, 100 dets/frame (config C2:
 independent synthetic video stream per GPU (stream i -> GPU i, no data-path
 collective: weak scaling).
 
-One step = one frame through ``StrongSORT.update(dets, img)``: OSNet ReID of
-every detection crop + Kalman predict + gated appearance cost + IoU cost + two
-linear assignments + track-table update.  Seeded random-weight OSNet (no
-pretrained file exists offline) and synthetic frames -- "data": "synthetic".
-
-One step = detector post-process of that frame's raw YOLOv8 head (DFL decode + class-aware NMS +
-scale_boxes, synthetic ``[144, 5040]`` head of the 384x640 letterboxed frame -- the backbone itself is
-out of scope) + ``StrongSORT.update``.
+One step = one frame: detector post-process of that frame's raw YOLOv8 head (DFL decode + class-aware NMS +
+scale_boxes, synthetic ``[144, 5040]`` head of the 384x640 letterboxed frame -- the backbone itself is out of
+scope) + the tracker update (``StrongSORT.update(dets, img)``: OSNet ReID of every detection crop + Kalman
+predict + gated appearance cost + IoU cost + two linear assignments + track-table update).  Seeded
+random-weight OSNet (no pretrained file exists offline) and synthetic frames -- "data": "synthetic".
 
   value  : frames/s with frames and raw heads already resident in HBM, through the
-           two-stage pipeline (``update_pipelined``: the OSNet of frame k on one stream
-           overlaps the association of frame k-1 on another; identical results), K frames
+           two-stage pipeline (``update_pipelined(lag=2)``: the OSNet of frame k on one stream
+           overlaps the association of frame k-1 on another, rows come back two calls later so
+           that no host round trip sits between frames; identical results), K frames
            timed as a whole with CUDA events; inputs rotate through W+K distinct frames
            (>= 5x the L2), ``detail.serial_flushed_ms_per_step`` is the one-frame-at-a-
            time figure with a 256 MiB L2 flush between steps
   e2e    : frames/s through the public streaming call ``StrongSORT.update_pipelined`` (what the
            CLI's frame loop calls) with the frame in pinned HOST memory (the raw head is what the
            detector backbone leaves on the device): H2D of the frame and the D2H of the result
-           rows inside the timed region every step, results lag one frame;
-           ``e2e.synchronous`` is the blocking ``StrongSORT.update`` (the reference's call
+           rows inside the timed region every step, the same ``lag=2``; ``e2e.lag1`` is the call
+           at one frame of latency, ``e2e.synchronous`` the blocking ``StrongSORT.update`` (the reference's call
            shape: one host synchronisation per frame, nothing overlaps across frames)
   stages : per-stage microseconds of one serial frame (CUDA events between the kernels)
   roofline     : ReID forward (``ssb_reid``, the dominant kernels) timed alone with CUDA
@@ -38,7 +36,8 @@ out of scope) + ``StrongSORT.update``.
   clocks       : SM clock / throttle reasons polled through NVML during the timed region
 
 ``--workload C4`` runs BASELINE.json's configs[3]; ``--shared-gallery`` adds config C5's
-per-frame cross-stream exchange (NCCL all-gather) to the timed region.
+per-frame cross-stream exchange (peer memory over NVLink, NCCL all-gather as the fallback) to the timed
+region; at N > 1 the default line measures it in its ``shared_gallery`` block.
 ``--impl reference`` times that CPU oracle alone and prints the same line.
 """
 from __future__ import annotations
